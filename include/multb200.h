@@ -1,0 +1,189 @@
+/* multb200.h -- C ABI of libmultb200.so: hand-written sm_100a kernels for the dynamic
+ * MulT transformer stacks (weight-sliced multi-head attention, dynamic Linear /
+ * LayerNorm, sinusoidal position embedding) of duyubo/Multimodal-Transformer-Robustness.
+ *
+ * The reference has no FFI: its boundary for this path is the Python class API of the
+ * package `modules`.  These entry points are what that API's
+ * forward/backward bind to; each one cites the reference code it replaces (paths
+ * relative to the reference root).  Rules of the boundary:
+ *   - plain pointers + sizes only (no torch types); every pointer is a DEVICE pointer
+ *     to fp32 data unless stated otherwise; `stream` is a cudaStream_t passed as void*.
+ *   - every op is GROUPED: it takes an array of `n` problem descriptors (host memory,
+ *     n <= MTB_MAX_GROUP) and runs all of them in ONE kernel launch -- this is how all
+ *     active fusion branches of a stage run concurrently (north-star item (d)).
+ *   - the library never owns tensor memory and keeps no mutable global state apart from
+ *     a per-thread last-error string.
+ *   - return value 0 = success; negative = error (message via mtb_last_error()).
+ *   - activations are row-major [tokens, features] with an explicit leading dimension;
+ *     a seq-first [L, B, E] tensor is the matrix [L*B, E] (token t = l*B + b).
+ */
+#ifndef MULTB200_H
+#define MULTB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTB_ABI_VERSION 3
+#define MTB_MAX_GROUP 24
+
+/* Dropout RNG: Philox4x32-10.  Element `i` of a dropout site is kept iff
+ * philox(key = seed, counter = offset + i/4)[i % 4] >= (uint32)(p * 2^32).
+ * If `dev` is non-null it points to two device uint64 {seed_add, offset_add} that are
+ * added to seed/offset at run time (lets a captured CUDA graph draw fresh masks on every
+ * replay).  Replaces F.dropout at modules/dynamic_transformer.py:68,77-78,173,182,185 and
+ * modules/dynamic_multihead_attention.py:110. */
+typedef struct {
+  uint64_t seed;
+  uint64_t offset;
+  const uint64_t* dev;
+} mtb_rng;
+
+/* ---- library ---------------------------------------------------------------------- */
+int mtb_abi_version(void);
+const char* mtb_last_error(void);
+int mtb_sm_count(void);
+/* which GEMM engine mtb_linear_* uses: 0 = fp32 CUDA-core (parity mode, 1e-5),
+ * 1 = tcgen05 TF32 tensor-core (TMA + TMEM).  Returns the previous mode. */
+int mtb_set_gemm_mode(int mode);
+int mtb_get_gemm_mode(void);
+
+/* materialise the keep-mask (1 byte per element, 1 = keep) a kernel would use for a
+ * dropout site; test support for injecting the same masks into the CPU oracle. */
+int mtb_dropout_mask(mtb_rng rng, float p, int64_t n, uint8_t* keep, void* stream);
+/* rng_dev[1] += delta  (advance the per-replay offset of a captured graph) */
+int mtb_rng_advance(uint64_t* rng_dev, uint64_t delta, void* stream);
+
+/* ---- (a1,a2) embed: y = scale * x + PE(pos(x[...,0])), then dropout ------------------
+ * modules/dynamic_transformer.py:64-68,72-78 + modules/position_embedding.py:8-27,45-83.
+ * x is a strided [L, B, E] view (element strides sl, sb, se); y is contiguous [L*B, E].
+ * pos = l+1 where x[l,b,0] != 0 else 0 (zero positional vector); PE(p, c) =
+ * sin(p*w) for even c, cos(p*w) for odd c, w = exp(-(c/2) * ln(1e4) / (E/2 - 1)).
+ * The sinusoid is evaluated in-register (no table, no host copy). */
+typedef struct {
+  const float* x; int64_t sl, sb, se;
+  float* y;
+  int L, B, E;
+  float scale; float p; mtb_rng rng;
+} mtb_embed_desc;
+int mtb_embed_fwd(const mtb_embed_desc* d, int n, void* stream);
+/* dx[L*B, E] (contiguous) = scale * keep/(1-p) * dy ; d->x = dy, d->y = dx */
+int mtb_embed_bwd(const mtb_embed_desc* d, int n, void* stream);
+
+/* ---- (a3,a10) dropout + residual + LayerNorm ------------------------------------------
+ * modules/dynamic_transformer.py:163,169-170,173-178,185-187,87 + modules/dynamic_layers.py:61-67.
+ *   x_new = res + dropout_p(a)      (a == NULL: x_new = res, nothing written to x_new)
+ *   y     = LayerNorm(x_new) * gamma[idx] + beta[idx]    (gamma == NULL: no LayerNorm)
+ * idx (int32[E], may be NULL) gathers the affine parameters (active_mask).
+ * mean/rstd ([T] each, may be NULL in inference) are saved for backward. */
+typedef struct {
+  const float* res; int64_t ld_res;
+  const float* a;   int64_t ld_a;
+  float* x_new;     int64_t ld_x;
+  float* y;         int64_t ld_y;
+  const float* gamma; const float* beta; const int32_t* idx;
+  float* mean; float* rstd;
+  int T, E;
+  float eps; float p; mtb_rng rng;
+} mtb_resln_desc;
+int mtb_resln_fwd(const mtb_resln_desc* d, int n, void* stream);
+
+/* backward of the above.
+ *   g    = d_xnew (may be NULL) + LayerNorm_backward(dy; x_new, mean, rstd, gamma[idx])
+ *   d_res = g ;  d_a = g * keep/(1-p)   (d_a may be NULL)
+ *   dgamma/dbeta (may be NULL: masked LayerNorm gets no gradient) are
+ *   ACCUMULATED (+=) at [idx]. */
+typedef struct {
+  const float* dy;     int64_t ld_dy;
+  const float* d_xnew; int64_t ld_dx;
+  const float* x_new;  int64_t ld_x;
+  const float* mean; const float* rstd;
+  const float* gamma; const int32_t* idx;
+  float* d_res; int64_t ld_dres;
+  float* d_a;   int64_t ld_da;
+  float* dgamma; float* dbeta;
+  int T, E;
+  float p; mtb_rng rng;
+} mtb_resln_bwd_desc;
+int mtb_resln_bwd(const mtb_resln_bwd_desc* d, int n, void* stream);
+
+/* ---- (a6,a7,a9) sliced / gathered linear ----------------------------------------------
+ * modules/dynamic_multihead_attention.py:259-282 (_in_proj/_out_proj) and
+ * modules/dynamic_layers.py:15-25 (DynamicLinear):
+ *   Y[M,N] = act( X[M,K] . W'^T + b' ),  W'[n,k] = W[row(n)*ldw + col(k)],  b'[n] = b[row(n)]
+ * row(n) = row_idx ? row_idx[n] : n ; col(k) = col_idx ? col_idx[k] : k  (int32 device
+ * arrays).  Head/dim prefix slicing of the [3,H,hd,E] in-projection and the column
+ * slicing of the out-projection are expressed as index arrays; plain prefix slices just
+ * use a smaller N/K with the full ldw.
+ * act: 0 = none, 1 = ReLU followed by dropout(p) (modules/dynamic_transformer.py:181-182). */
+typedef struct {
+  const float* X; int64_t ldx;
+  const float* W; int64_t ldw;
+  const float* bias;
+  const int32_t* row_idx; const int32_t* col_idx;
+  float* Y; int64_t ldy;
+  int M, N, K;
+  int act; float p; mtb_rng rng;
+} mtb_linear_desc;
+int mtb_linear_fwd(const mtb_linear_desc* d, int n, void* stream);
+
+/* backward.  dY' = dY                         (act == 0)
+ *            dY' = dY * [Yact > 0] / (1-p)    (act == 1; Yact is the forward output)
+ *   dX[M,K]  (+)= dY' . W'            (dX may be NULL; accumulate_dx: += instead of =)
+ *   dW[row(n)*ldw + col(k)] += dY'^T . X   and   db[row(n)] += colsum(dY')
+ *   (dW/db may be NULL; they are always ACCUMULATED into full-size, caller-zeroed grads so
+ *    rows/cols outside the active slice keep an explicit zero gradient). */
+typedef struct {
+  const float* dY; int64_t ldy;
+  const float* Yact; int64_t ldyact;
+  const float* X; int64_t ldx;
+  const float* W; int64_t ldw;
+  const int32_t* row_idx; const int32_t* col_idx;
+  float* dX; int64_t lddx; int accumulate_dx;
+  float* dW; float* db;
+  int M, N, K;
+  int act; float p;
+} mtb_linear_bwd_desc;
+int mtb_linear_bwd(const mtb_linear_bwd_desc* d, int n, void* stream);
+
+/* ---- (a4,a5) fused attention core -----------------------------------------------------
+ * modules/dynamic_multihead_attention.py:91-116 + modules/transformer.py:145-157:
+ *   S = scale * q k^T ; S[i,j] = -inf where j - i >= 1 + |Lk - Lq| ; P = softmax_fp32(S) ;
+ *   P~ = dropout_p(P) ; o = P~ v.      Scores are never written to HBM.
+ * q/k/v/o are token-major: row (l*B + b) with leading dimension ld*, head h occupies
+ * columns [h*hd, (h+1)*hd) -- i.e. the GEMM output layout, so no transposes exist.
+ * lse[(b*H + h)*Lq + i] = log-sum-exp of row i (saved for backward).
+ * dropout element index = ((b*H + h)*Lq + i)*Lk + j. */
+typedef struct {
+  const float* q; int64_t ldq;
+  const float* k; int64_t ldk;
+  const float* v; int64_t ldv;
+  float* o; int64_t ldo;
+  float* lse;
+  int Lq, Lk, B, H, hd;
+  float scale; float p; mtb_rng rng;
+} mtb_attn_desc;
+int mtb_attn_fwd(const mtb_attn_desc* d, int n, void* stream);
+
+typedef struct {
+  const float* q; int64_t ldq;
+  const float* k; int64_t ldk;
+  const float* v; int64_t ldv;
+  const float* o; int64_t ldo;
+  const float* d_o; int64_t lddo;
+  const float* lse;
+  float* delta;            /* scratch [B*H*Lq] */
+  float* dq; int64_t lddq;
+  float* dk; int64_t lddk;
+  float* dv; int64_t lddv;
+  int Lq, Lk, B, H, hd;
+  float scale; float p; mtb_rng rng;
+} mtb_attn_bwd_desc;
+int mtb_attn_bwd(const mtb_attn_bwd_desc* d, int n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MULTB200_H */

@@ -1,0 +1,22 @@
+#!/usr/bin/env bash
+# Build libmultb200.so in-tree for sm_100a (cross-compiles without a GPU).
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+OUT="$HERE/lib"
+mkdir -p "$OUT" "$HERE/build"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
+       --expt-relaxed-constexpr -Xptxas -v)
+objs=()
+pids=()
+for f in "$HERE"/csrc/*.cu; do
+  o="$HERE/build/$(basename "${f%.cu}").o"
+  objs+=("$o")
+  if [[ ! -f "$o" || "$f" -nt "$o" || "$HERE/csrc/common.cuh" -nt "$o" || "$HERE/../include/multb200.h" -nt "$o" ]]; then
+    ( "$NVCC" "${FLAGS[@]}" -c "$f" -o "$o" > "$o.log" 2>&1 || { cat "$o.log"; exit 1; } ) &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libmultb200.so" "${objs[@]}"
+echo "built $OUT/libmultb200.so"

@@ -1,0 +1,89 @@
+// api.cu -- C-ABI entry points of libmultb200.so (see include/multb200.h).
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+namespace mtb {
+
+static thread_local char g_err[512] = "";
+int g_gemm_mode = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+int linear_fwd_simt(const mtb_linear_desc* d, int n, cudaStream_t st);
+int linear_bwd_simt(const mtb_linear_bwd_desc* d, int n, cudaStream_t st);
+int linear_fwd_tc(const mtb_linear_desc* d, int n, cudaStream_t st);
+int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st);
+int attn_fwd_simt(const mtb_attn_desc* d, int n, cudaStream_t st);
+int attn_bwd_simt(const mtb_attn_bwd_desc* d, int n, cudaStream_t st);
+
+}  // namespace mtb
+
+extern "C" {
+
+int mtb_abi_version(void) { return MTB_ABI_VERSION; }
+const char* mtb_last_error(void) { return mtb::g_err; }
+int mtb_sm_count(void) { return mtb::sm_count(); }
+int mtb_set_gemm_mode(int mode) {
+  const int prev = mtb::g_gemm_mode;
+  mtb::g_gemm_mode = mode ? 1 : 0;
+  return prev;
+}
+int mtb_get_gemm_mode(void) { return mtb::g_gemm_mode; }
+
+int mtb_linear_fwd(const mtb_linear_desc* d, int n, void* stream) {
+  MTB_CHECK(n >= 1 && n <= MTB_MAX_GROUP, "linear_fwd: group size %d out of range", n);
+  for (int i = 0; i < n; ++i) {
+    MTB_CHECK(d[i].X && d[i].W && d[i].Y, "linear_fwd: null operand in problem %d", i);
+    MTB_CHECK(d[i].M >= 0 && d[i].N >= 0 && d[i].K >= 0, "linear_fwd: negative size in problem %d", i);
+    MTB_CHECK(d[i].act == 0 || d[i].act == 1, "linear_fwd: unknown activation %d", d[i].act);
+  }
+  if (mtb::g_gemm_mode == 1) return mtb::linear_fwd_tc(d, n, (cudaStream_t)stream);
+  return mtb::linear_fwd_simt(d, n, (cudaStream_t)stream);
+}
+
+int mtb_linear_bwd(const mtb_linear_bwd_desc* d, int n, void* stream) {
+  MTB_CHECK(n >= 1 && n <= MTB_MAX_GROUP, "linear_bwd: group size %d out of range", n);
+  for (int i = 0; i < n; ++i) {
+    MTB_CHECK(d[i].dY && d[i].W, "linear_bwd: null operand in problem %d", i);
+    MTB_CHECK(!d[i].db || d[i].dW, "linear_bwd: bias gradient requested without weight gradient (problem %d)", i);
+    MTB_CHECK(!d[i].dW || d[i].X, "linear_bwd: weight gradient needs the forward input (problem %d)", i);
+    MTB_CHECK(d[i].act == 0 || d[i].Yact, "linear_bwd: act=1 needs the forward output (problem %d)", i);
+  }
+  if (mtb::g_gemm_mode == 1) return mtb::linear_bwd_tc(d, n, (cudaStream_t)stream);
+  return mtb::linear_bwd_simt(d, n, (cudaStream_t)stream);
+}
+
+int mtb_attn_fwd(const mtb_attn_desc* d, int n, void* stream) {
+  MTB_CHECK(n >= 1 && n <= MTB_MAX_GROUP, "attn_fwd: group size %d out of range", n);
+  for (int i = 0; i < n; ++i)
+    MTB_CHECK(d[i].q && d[i].k && d[i].v && d[i].o && d[i].Lq > 0 && d[i].Lk > 0 && d[i].hd > 0,
+              "attn_fwd: bad problem %d", i);
+  return mtb::attn_fwd_simt(d, n, (cudaStream_t)stream);
+}
+
+int mtb_attn_bwd(const mtb_attn_bwd_desc* d, int n, void* stream) {
+  MTB_CHECK(n >= 1 && n <= MTB_MAX_GROUP, "attn_bwd: group size %d out of range", n);
+  for (int i = 0; i < n; ++i)
+    MTB_CHECK(d[i].q && d[i].k && d[i].v && d[i].o && d[i].d_o && d[i].lse && d[i].delta && d[i].dq && d[i].dk && d[i].dv,
+              "attn_bwd: null operand in problem %d", i);
+  return mtb::attn_bwd_simt(d, n, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+// common.cuh -- shared device helpers for libmultb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/multb200.h"
+
+#ifndef __CUDA_ARCH__
+#define MTB_HOST_ONLY 1
+#endif
+
+namespace mtb {
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const char* fmt, ...);
+#define MTB_CHECK(cond, ...)                  \
+  do {                                        \
+    if (!(cond)) {                            \
+      mtb::set_error(__VA_ARGS__);            \
+      return -1;                              \
+    }                                         \
+  } while (0)
+#define MTB_CUDA(expr)                                                         \
+  do {                                                                         \
+    cudaError_t e__ = (expr);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      mtb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),  \
+                     __FILE__, __LINE__);                                      \
+      return -2;                                                               \
+    }                                                                          \
+  } while (0)
+
+template <typename D>
+struct Group {          // descriptors travel by value in the kernel parameter block
+  D d[MTB_MAX_GROUP];
+  int start[MTB_MAX_GROUP + 1];   // prefix sum of work items (CTAs) per problem
+  int n;
+};
+
+// blockIdx -> (problem, local block) by linear scan (n <= 24)
+template <typename D>
+__device__ __forceinline__ int find_problem(const Group<D>& g, int blk, int& local) {
+  int p = 0;
+#pragma unroll 1
+  while (p + 1 < g.n && blk >= g.start[p + 1]) ++p;
+  local = blk - g.start[p];
+  return p;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10
+struct Philox {
+  uint32_t k0, k1;
+  __host__ __device__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+  __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#ifdef __CUDA_ARCH__
+    hi = __umulhi(a, b);
+    lo = a * b;
+#else
+    uint64_t p = (uint64_t)a * b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+#endif
+  }
+  __host__ __device__ inline uint4 operator()(uint64_t ctr) const {
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x5bd1e995u, c3 = 0u;
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t h0, l0, h1, l1;
+      mulhilo(0xD2511F53u, c0, h0, l0);
+      mulhilo(0xCD9E8D57u, c2, h1, l1);
+      uint32_t n0 = h1 ^ c1 ^ a, n1 = l1, n2 = h0 ^ c3 ^ b, n3 = l0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+
+struct DropCtx {        // resolved per kernel: effective seed/offset, integer threshold, 1/(1-p)
+  uint64_t seed, offset;
+  uint32_t thr;
+  float inv_keep;
+  bool on;
+};
+
+__device__ __forceinline__ DropCtx make_drop(const mtb_rng& r, float p) {
+  DropCtx c;
+  c.on = p > 0.f;
+  c.seed = r.seed; c.offset = r.offset;
+  if (c.on && r.dev != nullptr) { c.seed += r.dev[0]; c.offset += r.dev[1]; }
+  double t = (double)p * 4294967296.0;
+  c.thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+  c.inv_keep = c.on ? 1.f / (1.f - p) : 1.f;
+  return c;
+}
+
+// keep-bits for the 4 elements of group `grp` (elements 4*grp .. 4*grp+3)
+__device__ __forceinline__ uint4 drop_rand4(const DropCtx& c, uint64_t grp) {
+  return Philox(c.seed)(c.offset + grp);
+}
+__device__ __forceinline__ bool drop_keep1(const DropCtx& c, uint64_t idx) {
+  uint4 r = drop_rand4(c, idx >> 2);
+  uint32_t v = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
+  return v >= c.thr;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+int sm_count();
+extern int g_gemm_mode;
+
+}  // namespace mtb

@@ -1,0 +1,335 @@
+// layernorm.cu -- fused dropout + residual add + LayerNorm (forward and backward).
+// modules/dynamic_transformer.py:163,169-170,173-178,185-187,87; modules/dynamic_layers.py:61-67.
+// One warp per token row, the row lives in registers (128-bit loads/stores, warp-shuffle
+// reductions, two-pass mean/variance).  HBM-bound: forward 4*4 B per element
+// (read branch, read residual, write new residual, write normed) + 8 B per row of stats.
+#include "common.cuh"
+
+namespace mtb {
+
+constexpr int LN_WARPS = 8;
+constexpr int LN_THREADS = LN_WARPS * 32;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 gather4(const float* w, const int32_t* idx, int c) {
+  if (idx == nullptr) return ld4(w + c);
+  return make_float4(w[idx[c]], w[idx[c + 1]], w[idx[c + 2]], w[idx[c + 3]]);
+}
+__device__ __forceinline__ float4 keep4(const DropCtx& dc, uint64_t grp) {
+  float4 k = make_float4(dc.inv_keep, dc.inv_keep, dc.inv_keep, dc.inv_keep);
+  if (dc.on) {
+    uint4 r = drop_rand4(dc, grp);
+    k.x = r.x >= dc.thr ? dc.inv_keep : 0.f; k.y = r.y >= dc.thr ? dc.inv_keep : 0.f;
+    k.z = r.z >= dc.thr ? dc.inv_keep : 0.f; k.w = r.w >= dc.thr ? dc.inv_keep : 0.f;
+  }
+  return k;
+}
+
+// ------------------------------------------------------------------ forward (vector path)
+template <int MAXV>
+__global__ void __launch_bounds__(LN_THREADS) resln_fwd_kernel(const __grid_constant__ Group<mtb_resln_desc> g) {
+  int local;
+  const int pi = find_problem(g, blockIdx.x, local);
+  const mtb_resln_desc& d = g.d[pi];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = local * LN_WARPS + warp;
+  if (t >= d.T) return;
+  const int E = d.E, nv = E >> 2;
+  const DropCtx dc = make_drop(d.rng, d.p);
+  float4 x[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + 32 * i;
+    x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (v < nv) {
+      const int c = v << 2;
+      float4 r = d.res ? ld4(d.res + (int64_t)t * d.ld_res + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (d.a) {
+        const float4 a = ld4(d.a + (int64_t)t * d.ld_a + c);
+        const float4 k = keep4(dc, ((uint64_t)t * E + c) >> 2);
+        r.x += a.x * k.x; r.y += a.y * k.y; r.z += a.z * k.z; r.w += a.w * k.w;
+        if (d.x_new) st4(d.x_new + (int64_t)t * d.ld_x + c, r);
+      }
+      x[i] = r;
+      sum += (r.x + r.y) + (r.z + r.w);
+    }
+  }
+  if (d.gamma == nullptr) return;
+  const float mean = warp_sum(sum) / (float)E;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (lane + 32 * i < nv) {
+      const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, e = x[i].w - mean;
+      sq += (a * a + b * b) + (c * c + e * e);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)E + d.eps);
+  if (lane == 0 && d.mean) { d.mean[t] = mean; d.rstd[t] = rstd; }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nv) {
+      const int c = v << 2;
+      const float4 gm = gather4(d.gamma, d.idx, c), bt = gather4(d.beta, d.idx, c);
+      float4 y;
+      y.x = (x[i].x - mean) * rstd * gm.x + bt.x; y.y = (x[i].y - mean) * rstd * gm.y + bt.y;
+      y.z = (x[i].z - mean) * rstd * gm.z + bt.z; y.w = (x[i].w - mean) * rstd * gm.w + bt.w;
+      st4(d.y + (int64_t)t * d.ld_y + c, y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ forward (generic width)
+__global__ void __launch_bounds__(LN_THREADS) resln_fwd_generic(const __grid_constant__ Group<mtb_resln_desc> g) {
+  int local;
+  const int pi = find_problem(g, blockIdx.x, local);
+  const mtb_resln_desc& d = g.d[pi];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = local * LN_WARPS + warp;
+  if (t >= d.T) return;
+  const int E = d.E;
+  const DropCtx dc = make_drop(d.rng, d.p);
+  auto value = [&](int c) -> float {
+    float r = d.res ? d.res[(int64_t)t * d.ld_res + c] : 0.f;
+    if (d.a) {
+      const float k = dc.on ? (drop_keep1(dc, (uint64_t)t * E + c) ? dc.inv_keep : 0.f) : 1.f;
+      r += d.a[(int64_t)t * d.ld_a + c] * k;
+    }
+    return r;
+  };
+  float sum = 0.f;
+  for (int c = lane; c < E; c += 32) {
+    const float r = value(c);
+    if (d.a && d.x_new) d.x_new[(int64_t)t * d.ld_x + c] = r;
+    sum += r;
+  }
+  if (d.gamma == nullptr) return;
+  const float mean = warp_sum(sum) / (float)E;
+  float sq = 0.f;
+  for (int c = lane; c < E; c += 32) { const float r = value(c) - mean; sq += r * r; }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)E + d.eps);
+  if (lane == 0 && d.mean) { d.mean[t] = mean; d.rstd[t] = rstd; }
+  for (int c = lane; c < E; c += 32) {
+    const int ic = d.idx ? d.idx[c] : c;
+    d.y[(int64_t)t * d.ld_y + c] = (value(c) - mean) * rstd * d.gamma[ic] + d.beta[ic];
+  }
+}
+
+// ------------------------------------------------------------------ backward (vector path)
+// Each CTA owns `rows_per_cta` consecutive rows; per-lane partial dgamma/dbeta live in
+// registers, are combined through shared memory once per CTA and leave as one atomicAdd
+// per feature per CTA.
+template <int MAXV, bool AFFINE_GRAD>
+__global__ void __launch_bounds__(LN_THREADS) resln_bwd_kernel(const __grid_constant__ Group<mtb_resln_bwd_desc> g,
+                                                               int rows_per_cta) {
+  extern __shared__ float sred[];   // [2][E] when AFFINE_GRAD
+  int local;
+  const int pi = find_problem(g, blockIdx.x, local);
+  const mtb_resln_bwd_desc& d = g.d[pi];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int E = d.E, nv = E >> 2;
+  const DropCtx dc = make_drop(d.rng, d.p);
+  const bool has_ln = d.dy != nullptr;
+  const bool agrad = AFFINE_GRAD && d.dgamma != nullptr && has_ln;
+  float4 dg[AFFINE_GRAD ? MAXV : 1], db[AFFINE_GRAD ? MAXV : 1];
+  if (AFFINE_GRAD) {
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) { dg[i] = make_float4(0, 0, 0, 0); db[i] = make_float4(0, 0, 0, 0); }
+    for (int c = threadIdx.x; c < 2 * E; c += LN_THREADS) sred[c] = 0.f;
+    __syncthreads();
+  }
+  const int row0 = local * rows_per_cta;
+  const int row1 = min(d.T, row0 + rows_per_cta);
+  for (int t = row0 + warp; t < row1; t += LN_WARPS) {
+    float4 wdy[MAXV], xh[MAXV];
+    float s1 = 0.f, s2 = 0.f;
+    float mean = 0.f, rstd = 0.f;
+    if (has_ln) { mean = d.mean[t]; rstd = d.rstd[t]; }
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + 32 * i;
+      wdy[i] = make_float4(0, 0, 0, 0); xh[i] = make_float4(0, 0, 0, 0);
+      if (v < nv && has_ln) {
+        const int c = v << 2;
+        const float4 dy = ld4(d.dy + (int64_t)t * d.ld_dy + c);
+        const float4 x = ld4(d.x_new + (int64_t)t * d.ld_x + c);
+        const float4 gm = gather4(d.gamma, d.idx, c);
+        xh[i] = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
+        wdy[i] = make_float4(dy.x * gm.x, dy.y * gm.y, dy.z * gm.z, dy.w * gm.w);
+        s1 += (wdy[i].x * xh[i].x + wdy[i].y * xh[i].y) + (wdy[i].z * xh[i].z + wdy[i].w * xh[i].w);
+        s2 += (wdy[i].x + wdy[i].y) + (wdy[i].z + wdy[i].w);
+        if (AFFINE_GRAD && agrad) {
+          dg[i].x += dy.x * xh[i].x; dg[i].y += dy.y * xh[i].y; dg[i].z += dy.z * xh[i].z; dg[i].w += dy.w * xh[i].w;
+          db[i].x += dy.x; db[i].y += dy.y; db[i].z += dy.z; db[i].w += dy.w;
+        }
+      }
+    }
+    const float c1 = warp_sum(s1) / (float)E, c2 = warp_sum(s2) / (float)E;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nv) {
+        const int c = v << 2;
+        float4 gx;
+        gx.x = rstd * (wdy[i].x - c2 - xh[i].x * c1); gx.y = rstd * (wdy[i].y - c2 - xh[i].y * c1);
+        gx.z = rstd * (wdy[i].z - c2 - xh[i].z * c1); gx.w = rstd * (wdy[i].w - c2 - xh[i].w * c1);
+        if (d.d_xnew) {
+          const float4 e = ld4(d.d_xnew + (int64_t)t * d.ld_dx + c);
+          gx.x += e.x; gx.y += e.y; gx.z += e.z; gx.w += e.w;
+        }
+        if (d.d_res) st4(d.d_res + (int64_t)t * d.ld_dres + c, gx);
+        if (d.d_a) {
+          const float4 k = keep4(dc, ((uint64_t)t * E + c) >> 2);
+          st4(d.d_a + (int64_t)t * d.ld_da + c, make_float4(gx.x * k.x, gx.y * k.y, gx.z * k.z, gx.w * k.w));
+        }
+      }
+    }
+  }
+  if (AFFINE_GRAD) {
+    if (agrad) {
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nv) {
+          const int c = v << 2;
+          atomicAdd(&sred[c], dg[i].x); atomicAdd(&sred[c + 1], dg[i].y);
+          atomicAdd(&sred[c + 2], dg[i].z); atomicAdd(&sred[c + 3], dg[i].w);
+          atomicAdd(&sred[E + c], db[i].x); atomicAdd(&sred[E + c + 1], db[i].y);
+          atomicAdd(&sred[E + c + 2], db[i].z); atomicAdd(&sred[E + c + 3], db[i].w);
+        }
+      }
+    }
+    __syncthreads();
+    if (agrad) {
+      for (int c = threadIdx.x; c < E; c += LN_THREADS) {
+        const int ic = d.idx ? d.idx[c] : c;
+        atomicAdd(&d.dgamma[ic], sred[c]);
+        if (d.dbeta) atomicAdd(&d.dbeta[ic], sred[E + c]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward (generic width)
+__global__ void __launch_bounds__(LN_THREADS) resln_bwd_generic(const __grid_constant__ Group<mtb_resln_bwd_desc> g) {
+  int local;
+  const int pi = find_problem(g, blockIdx.x, local);
+  const mtb_resln_bwd_desc& d = g.d[pi];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = local * LN_WARPS + warp;
+  if (t >= d.T) return;
+  const int E = d.E;
+  const DropCtx dc = make_drop(d.rng, d.p);
+  const bool has_ln = d.dy != nullptr;
+  float mean = 0.f, rstd = 0.f, s1 = 0.f, s2 = 0.f;
+  if (has_ln) {
+    mean = d.mean[t]; rstd = d.rstd[t];
+    for (int c = lane; c < E; c += 32) {
+      const int ic = d.idx ? d.idx[c] : c;
+      const float dy = d.dy[(int64_t)t * d.ld_dy + c];
+      const float xh = (d.x_new[(int64_t)t * d.ld_x + c] - mean) * rstd;
+      const float w = dy * d.gamma[ic];
+      s1 += w * xh; s2 += w;
+      if (d.dgamma) { atomicAdd(&d.dgamma[ic], dy * xh); if (d.dbeta) atomicAdd(&d.dbeta[ic], dy); }
+    }
+  }
+  const float c1 = warp_sum(s1) / (float)E, c2 = warp_sum(s2) / (float)E;
+  for (int c = lane; c < E; c += 32) {
+    float gx = 0.f;
+    if (has_ln) {
+      const int ic = d.idx ? d.idx[c] : c;
+      const float xh = (d.x_new[(int64_t)t * d.ld_x + c] - mean) * rstd;
+      gx = rstd * (d.dy[(int64_t)t * d.ld_dy + c] * d.gamma[ic] - c2 - xh * c1);
+    }
+    if (d.d_xnew) gx += d.d_xnew[(int64_t)t * d.ld_dx + c];
+    if (d.d_res) d.d_res[(int64_t)t * d.ld_dres + c] = gx;
+    if (d.d_a) {
+      const float k = dc.on ? (drop_keep1(dc, (uint64_t)t * E + c) ? dc.inv_keep : 0.f) : 1.f;
+      d.d_a[(int64_t)t * d.ld_da + c] = gx * k;
+    }
+  }
+}
+
+static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+}  // namespace mtb
+
+extern "C" {
+
+int mtb_resln_fwd(const mtb_resln_desc* d, int n, void* stream) {
+  using namespace mtb;
+  MTB_CHECK(n >= 1 && n <= MTB_MAX_GROUP, "resln_fwd: group size %d out of range", n);
+  Group<mtb_resln_desc> g;
+  g.n = n;
+  int tot = 0, maxE = 0;
+  bool vec = true;
+  for (int i = 0; i < n; ++i) {
+    const mtb_resln_desc& x = d[i];
+    MTB_CHECK(x.res || x.a, "resln_fwd: problem %d has neither residual nor branch input", i);
+    MTB_CHECK(!x.gamma || x.y, "resln_fwd: problem %d has gamma but no output", i);
+    g.d[i] = x;
+    g.start[i] = tot;
+    tot += (x.T + LN_WARPS - 1) / LN_WARPS;
+    maxE = x.E > maxE ? x.E : maxE;
+    vec = vec && (x.E % 4 == 0) && (!x.res || (aligned16(x.res) && x.ld_res % 4 == 0)) &&
+          (!x.a || (aligned16(x.a) && x.ld_a % 4 == 0)) && (!x.x_new || (aligned16(x.x_new) && x.ld_x % 4 == 0)) &&
+          (!x.y || (aligned16(x.y) && x.ld_y % 4 == 0)) && (!x.gamma || x.idx || (aligned16(x.gamma) && aligned16(x.beta)));
+  }
+  g.start[n] = tot;
+  if (tot == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec && maxE <= 256) resln_fwd_kernel<2><<<tot, LN_THREADS, 0, st>>>(g);
+  else if (vec && maxE <= 1024) resln_fwd_kernel<8><<<tot, LN_THREADS, 0, st>>>(g);
+  else resln_fwd_generic<<<tot, LN_THREADS, 0, st>>>(g);
+  MTB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int mtb_resln_bwd(const mtb_resln_bwd_desc* d, int n, void* stream) {
+  using namespace mtb;
+  MTB_CHECK(n >= 1 && n <= MTB_MAX_GROUP, "resln_bwd: group size %d out of range", n);
+  Group<mtb_resln_bwd_desc> g;
+  g.n = n;
+  int maxE = 0, maxT = 0;
+  bool vec = true, affine = false;
+  for (int i = 0; i < n; ++i) {
+    const mtb_resln_bwd_desc& x = d[i];
+    MTB_CHECK(x.dy || x.d_xnew, "resln_bwd: problem %d has no incoming gradient", i);
+    maxE = x.E > maxE ? x.E : maxE;
+    maxT = x.T > maxT ? x.T : maxT;
+    affine = affine || (x.dgamma != nullptr);
+    vec = vec && (x.E % 4 == 0) && (!x.dy || (aligned16(x.dy) && x.ld_dy % 4 == 0 && aligned16(x.x_new) && x.ld_x % 4 == 0)) &&
+          (!x.d_xnew || (aligned16(x.d_xnew) && x.ld_dx % 4 == 0)) && (!x.d_res || (aligned16(x.d_res) && x.ld_dres % 4 == 0)) &&
+          (!x.d_a || (aligned16(x.d_a) && x.ld_da % 4 == 0)) && (!x.dy || x.idx || aligned16(x.gamma));
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int tot = 0;
+  if (vec && maxE <= 1024) {
+    // enough CTAs for ~4 waves of the 148 SMs, at least one pass of the 8 warps per CTA
+    int rows = (maxT + sm_count() * 4 - 1) / (sm_count() * 4);
+    rows = ((rows + LN_WARPS - 1) / LN_WARPS) * LN_WARPS;
+    if (rows < LN_WARPS) rows = LN_WARPS;
+    for (int i = 0; i < n; ++i) { g.d[i] = d[i]; g.start[i] = tot; tot += (d[i].T + rows - 1) / rows; }
+    g.start[n] = tot;
+    if (tot == 0) return 0;
+    const size_t smem = affine ? 2 * (size_t)maxE * sizeof(float) : 0;
+    if (maxE <= 256) {
+      if (affine) resln_bwd_kernel<2, true><<<tot, LN_THREADS, smem, st>>>(g, rows);
+      else resln_bwd_kernel<2, false><<<tot, LN_THREADS, 0, st>>>(g, rows);
+    } else {
+      if (affine) resln_bwd_kernel<8, true><<<tot, LN_THREADS, smem, st>>>(g, rows);
+      else resln_bwd_kernel<8, false><<<tot, LN_THREADS, 0, st>>>(g, rows);
+    }
+  } else {
+    for (int i = 0; i < n; ++i) { g.d[i] = d[i]; g.start[i] = tot; tot += (d[i].T + LN_WARPS - 1) / LN_WARPS; }
+    g.start[n] = tot;
+    if (tot == 0) return 0;
+    resln_bwd_generic<<<tot, LN_THREADS, 0, st>>>(g);
+  }
+  MTB_CUDA(cudaGetLastError());
+  return 0;
+}
+}
