@@ -49,6 +49,8 @@ int mtb_sm_count(void);
  * 1 = tcgen05 TF32 tensor-core (TMA + TMEM).  Returns the previous mode. */
 int mtb_set_gemm_mode(int mode);
 int mtb_get_gemm_mode(void);
+/* number of kernels this library has launched so far in this process (bench bookkeeping) */
+uint64_t mtb_launch_count(void);
 
 /* materialise the keep-mask (1 byte per element, 1 = keep) a kernel would use for a
  * dropout site; test support for injecting the same masks into the CPU oracle. */

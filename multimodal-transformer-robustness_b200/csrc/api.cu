@@ -7,6 +7,9 @@ namespace mtb {
 
 static thread_local char g_err[512] = "";
 int g_gemm_mode = 0;
+static unsigned long long g_launches = 0;
+void note_launch() { ++g_launches; }
+unsigned long long launches() { return g_launches; }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -46,6 +49,7 @@ int mtb_set_gemm_mode(int mode) {
   return prev;
 }
 int mtb_get_gemm_mode(void) { return mtb::g_gemm_mode; }
+uint64_t mtb_launch_count(void) { return mtb::launches(); }
 
 int mtb_linear_fwd(const mtb_linear_desc* d, int n, void* stream) {
   MTB_CHECK(n >= 1 && n <= MTB_MAX_GROUP, "linear_fwd: group size %d out of range", n);

@@ -383,6 +383,7 @@ static int launch_fwd(const Group<mtb_attn_desc>& g, int tot, cudaStream_t st) {
     attr = true;
   }
   attn_fwd_kernel<HDP><<<tot, A_THREADS, fwd_smem<HDP>(), st>>>(g);
+  mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -396,8 +397,10 @@ static int launch_bwd(const Group<mtb_attn_bwd_desc>& gq, int totq, const Group<
     attr = true;
   }
   attn_bwd_dq_kernel<HDP><<<totq, A_THREADS, dq_smem<HDP>(), st>>>(gq);
+  mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
   attn_bwd_dkv_kernel<HDP><<<totk, A_THREADS, dkv_smem<HDP>(), st>>>(gk);
+  mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -117,6 +117,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 int sm_count();
+void note_launch();
 extern int g_gemm_mode;
 
 }  // namespace mtb

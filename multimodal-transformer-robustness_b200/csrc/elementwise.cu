@@ -112,6 +112,7 @@ static int launch_embed(const mtb_embed_desc* d, int n, cudaStream_t st) {
   g.start[n] = tot;
   if (tot == 0) return 0;
   embed_kernel<BWD><<<tot, EW_THREADS, 0, st>>>(g);
+  mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -136,11 +137,13 @@ int mtb_embed_bwd(const mtb_embed_desc* d, int n, void* stream) {
 int mtb_dropout_mask(mtb_rng rng, float p, int64_t n, uint8_t* keep, void* stream) {
   if (n <= 0) return 0;
   mtb::mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rng, p, n, keep);
+  mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
   return 0;
 }
 int mtb_rng_advance(uint64_t* rng_dev, uint64_t delta, void* stream) {
   mtb::rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(rng_dev, delta);
+  mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -284,6 +284,7 @@ int mtb_resln_fwd(const mtb_resln_desc* d, int n, void* stream) {
   if (vec && maxE <= 256) resln_fwd_kernel<2><<<tot, LN_THREADS, 0, st>>>(g);
   else if (vec && maxE <= 1024) resln_fwd_kernel<8><<<tot, LN_THREADS, 0, st>>>(g);
   else resln_fwd_generic<<<tot, LN_THREADS, 0, st>>>(g);
+  mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -329,6 +330,7 @@ int mtb_resln_bwd(const mtb_resln_bwd_desc* d, int n, void* stream) {
     if (tot == 0) return 0;
     resln_bwd_generic<<<tot, LN_THREADS, 0, st>>>(g);
   }
+  mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
   return 0;
 }

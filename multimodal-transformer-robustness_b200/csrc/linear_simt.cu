@@ -149,6 +149,7 @@ int launch_gemm_simt(const GemmP* p, int n, cudaStream_t st) {
     g.start[m] = tot;
     if (tot > 0) {
       gemm_simt_kernel<<<tot, G_THREADS, 0, st>>>(g);
+      mtb::note_launch();
       MTB_CUDA(cudaGetLastError());
     }
     off += m;

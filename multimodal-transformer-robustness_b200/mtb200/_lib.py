@@ -85,6 +85,7 @@ SYMBOLS = {
     "mtb_sm_count": ([], C.c_int),
     "mtb_set_gemm_mode": ([C.c_int], C.c_int),
     "mtb_get_gemm_mode": ([], C.c_int),
+    "mtb_launch_count": ([], C.c_uint64),
     "mtb_dropout_mask": ([Rng, C.c_float, C.c_int64, C.c_void_p, C.c_void_p], C.c_int),
     "mtb_rng_advance": ([C.c_void_p, C.c_uint64, C.c_void_p], C.c_int),
     "mtb_embed_fwd": ([C.POINTER(EmbedDesc), C.c_int, C.c_void_p], C.c_int),

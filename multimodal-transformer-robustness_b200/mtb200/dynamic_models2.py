@@ -1,0 +1,257 @@
+"""DynamicMULTModel -- the MulT supernet driver (reference: src/dynamic_models2.py:72-469).
+
+Same constructor signature, attribute names (trans_mems0 / trans / translation / trans_mems /
+proj1 / proj2 / out_layer, active_*), state_dict keys and sampler semantics as the reference
+class, so it can be injected as ``src.dynamic_models2.DynamicMULTModel`` and driven by the
+reference's src/train.py / EA.py unchanged.  Differences, all results-identical:
+  * encoders are the mtb200 kernel-backed modules;
+  * the per-modality `mems0` stack of a modality nobody consumes in this step is skipped
+    (the reference runs it and throws the result away, :229);
+  * the head's ReLU + dropout is the GEMM epilogue, gathers are GEMM operand indexing.
+Front-ends: ``front_end='gru'`` builds the reference's bi-GRU head (cuDNN, out of scope of the
+hot path; keeps constructor RNG order for names outside {'t','i','A'}); ``front_end='conv1d'``
+builds the sequence-preserving Conv1d(k=1, bias=False) projection the attention stacks were
+designed for, run as an mtb200 GEMM.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+from torch import nn
+
+from modules.dynamic_layers import DynamicLinear
+from modules.dynamic_transformer import DynamicTransformerEncoder
+from . import ops
+from .models2 import AmnSum, ModalityStr, gen_subnet
+
+__all__ = ["DynamicMULTModel", "Transpose", "RNN_Header", "Conv1x1FrontEnd"]
+
+
+class Transpose(nn.Module):
+    def __init__(self, dim0, dim1):
+        super().__init__()
+        self.dim0, self.dim1 = dim0, dim1
+
+    def forward(self, x):
+        return torch.transpose(x, self.dim0, self.dim1)
+
+
+class RNN_Header(nn.Module):
+    """The reference's bi-GRU front-end (src/dynamic_models2.py:23-40): returns only the final
+    hidden state, i.e. a length-1 sequence.  Library (cuDNN) code, outside the hot path."""
+
+    def __init__(self, input_dim, hidden_dim, num_layers):
+        super().__init__()
+        self.lstm1 = nn.GRU(input_size=input_dim, hidden_size=hidden_dim // 2, num_layers=num_layers,
+                            batch_first=True, bidirectional=True)
+        self.lstm2 = nn.GRU(input_size=hidden_dim, hidden_size=hidden_dim // 2, num_layers=num_layers,
+                            batch_first=True, bidirectional=True)
+        self.drop = nn.Dropout(p=0.2)
+        self.ln = nn.LayerNorm(hidden_dim, elementwise_affine=False)
+        self.ln1 = nn.LayerNorm(input_dim, elementwise_affine=False)
+
+    def forward(self, x):
+        x, _ = self.lstm1(x)
+        x = self.ln(x)
+        _, h2 = self.lstm2(x)
+        return torch.cat((h2[0], h2[1]), dim=1).unsqueeze(1)
+
+
+class Conv1x1FrontEnd(nn.Module):
+    """[B, L, D_in] -> [B, d, L] like Sequential(Transpose(1,2), Conv1d(D_in, d, 1, bias=False)),
+    computed as one GEMM over the B*L tokens.  ``weight`` keeps the Conv1d layout [d, D_in, 1]."""
+
+    def __init__(self, d_in, d):
+        super().__init__()
+        conv = nn.Conv1d(d_in, d, kernel_size=1, bias=False)       # same init draws as nn.Conv1d
+        self.weight = nn.Parameter(conv.weight.data.clone())
+        self.d_in, self.d = d_in, d
+
+    def forward(self, x):
+        B, L, D = x.shape
+        y = ops.linear(x.reshape(B * L, D), self.weight.view(self.d, self.d_in), None, N=self.d, K=self.d_in)
+        return y.view(B, L, self.d).transpose(1, 2)            # [B, d, L] view, like the conv output
+
+
+class DynamicMULTModel(nn.Module):
+    def __init__(self, origin_dimensions: list, dimension, num_heads, head_dim, layers_single_attn,
+                 layers_hybrid_attn, layers_self_attn, attn_dropout: list, relu_dropout, res_dropout, out_dropout,
+                 embed_dropout, attn_mask, output_dim, modality_set, all_steps, stride=0, padding=0, kernel_size=0,
+                 experiment_type="random_sample", front_end="gru", prune_dead_branches=True):
+        super().__init__()
+        self.orig_dimensions = origin_dimensions
+        self.d = dimension
+        self.attn_dropout = attn_dropout
+        assert len(self.attn_dropout) == len(self.orig_dimensions) + 1
+        self.relu_dropout = relu_dropout
+        self.res_dropout = res_dropout
+        self.out_dropout = out_dropout
+        self.embed_dropout = embed_dropout
+        self.attn_mask = attn_mask
+        self.output_dim = output_dim
+        self.modality_list = modality_set
+        self.all_steps = all_steps
+        self.m = ModalityStr(modality_set)
+        self.experiment_type = experiment_type
+        self.num_heads = num_heads
+        self.head_dim = head_dim
+        self.layers_single_attn = layers_single_attn
+        self.layers_hybrid_attn = layers_hybrid_attn
+        self.layers_self_attn = layers_self_attn
+        self.modality_num = len(self.orig_dimensions)
+        self.combined_dim = AmnSum(self.modality_num) * self.d
+        self.prune_dead_branches = prune_dead_branches
+
+        # front-ends (construction order = RNG order of the reference, :134-149)
+        proj = []
+        for i in range(self.modality_num):
+            if front_end == "conv1d":
+                proj.append(Conv1x1FrontEnd(self.orig_dimensions[i], self.d))
+            elif front_end == "gru":
+                if self.modality_list[i] in ("i", "A", "t"):
+                    raise NotImplementedError("image / BERT front-ends are outside the hot path; use names such as "
+                                              "['l','a','v'] or front_end='conv1d'")
+                proj.append(nn.Sequential(RNN_Header(self.orig_dimensions[i], self.d, 1), Transpose(1, 2)))
+            else:
+                proj.append(front_end(i, self.orig_dimensions[i], self.d))
+        self.proj = nn.ModuleList(proj)
+
+        self.trans_mems0 = nn.ModuleDict({'mems0' + self.modality_list[i]: self.get_network(i, 0, mem=False, layers=self.layers_single_attn)
+                                          for i in range(self.modality_num)})
+        combos = self.m.gen_modality_str_all()
+        self.trans = nn.ModuleDict({'cross' + combos[i]: self.get_network(i, i, mem=False, layers=self.layers_hybrid_attn)
+                                    for i in range(len(combos))})
+        self.translation = nn.ModuleDict({'translation' + c: nn.Linear(self.d, self.d) for c in combos})
+        self.modality_index_list = []
+        for ch in self.modality_list:
+            names = [ch] + self.m.gen_modality_str_all(modality_set=[ch])
+            self.modality_index_list.append({s: k for k, s in enumerate(names)})
+        self.trans_mems = nn.ModuleDict({'mems' + self.modality_list[i]: self.get_network(i, i, mem=True, layers=self.layers_self_attn)
+                                         for i in range(self.modality_num)})
+        self.proj1 = DynamicLinear(self.combined_dim, self.combined_dim, bias=True)
+        self.proj2 = DynamicLinear(self.combined_dim, self.combined_dim, bias=True)
+        self.out_layer = DynamicLinear(self.combined_dim, self.output_dim, bias=True)
+
+        self.active_modality = list(range(self.modality_num))
+        self.active_cross = [self.m.gen_modality_str(ch) for ch in self.modality_list]
+        self.active_cross_output = [self.m.gen_modality_str(ch) for ch in self.modality_list]
+        if len(self.modality_list) == 1:
+            self.active_cross_output = self.modality_list
+        self.cross = self.active_cross.copy()
+        self.cross_output = self.active_cross_output.copy()
+
+    def get_network(self, mod1, mod2, mem, layers=-1):
+        """Attention-dropout per encoder follows the reference (:201-210)."""
+        if not mem:
+            e = self.d
+            p = self.attn_dropout[mod1] if mod2 == 0 else 0.1
+        else:
+            e = int(self.combined_dim / self.modality_num)
+            p = self.attn_dropout[-1]
+        return DynamicTransformerEncoder(embed_dim=e, head_dim=self.head_dim, num_heads=self.num_heads, layers=layers,
+                                         attn_dropout=p, relu_dropout=self.relu_dropout, res_dropout=self.res_dropout,
+                                         embed_dropout=self.embed_dropout, attn_mask=self.attn_mask)
+
+    # ------------------------------------------------------------------ forward
+    def _needed_modalities(self) -> set:
+        need = set()
+        for i in self.active_modality:
+            if self.active_cross_output[i] == []:
+                continue
+            for name in list(self.active_cross[i]) + list(self.active_cross_output[i]):
+                need.update(name)
+        return need
+
+    def forward(self, x):
+        """x: list of per-modality inputs.  Returns (prediction, []) like the reference (:222-291)."""
+        assert len(x) == self.modality_num
+        need = self._needed_modalities() if self.prune_dead_branches else set(self.modality_list)
+        dev = next(self.parameters()).device
+        h_ = {}
+        for i, ch in enumerate(self.modality_list):
+            if ch in need:
+                px = self.proj[i](x[i]).permute(2, 0, 1)          # [L, B, d] view
+                h_[ch] = self.trans_mems0['mems0' + ch](px)
+        last_hs, hs, out_index = [], [], []
+        d = self.d
+        for i in self.active_modality:
+            if self.active_cross_output[i] == []:
+                continue
+            for name in self.active_cross[i]:
+                src = h_[name[:-1]]
+                h_[name] = self.trans['cross' + name](h_[name[-1]], src, src)
+            h = torch.cat([h_[name] for name in self.active_cross_output[i]], dim=2)
+            slot = len(self.modality_index_list[i])
+            mask = []
+            for name in self.active_cross_output[i]:
+                k = self.modality_index_list[i][name]
+                mask.extend(range(k * d, (k + 1) * d))
+                out_index.extend(range(d * slot * i + k * d, d * slot * i + (k + 1) * d))
+            mask_t = torch.tensor(mask, dtype=torch.int32, device=dev)
+            h = self.trans_mems['mems' + self.modality_list[i]](h, active_mask=mask_t)
+            if self.all_steps:
+                hs.append(h)
+            else:
+                last_hs.append(h[-1])
+        if self.all_steps:
+            out = torch.cat(hs, dim=2).permute(1, 0, 2)
+        else:
+            out = torch.cat(last_hs, dim=1)
+        idx = torch.tensor(out_index, dtype=torch.int32, device=dev)
+        lead = out.shape[:-1]
+        o2 = out.reshape(-1, out.shape[-1])
+        C = idx.numel()
+        z = ops.linear(o2, self.proj1.l.weight, self.proj1.l.bias, N=self.combined_dim, K=C, col_idx=idx, act=1,
+                       p=self.out_dropout, training=self.training)
+        z = ops.linear(z, self.proj2.l.weight, self.proj2.l.bias, N=C, K=self.combined_dim, row_idx=idx)
+        z = ops.res_drop(o2, z, 0.0, False)
+        y = ops.linear(z, self.out_layer.l.weight, self.out_layer.l.bias, N=self.output_dim, K=C, col_idx=idx)
+        return y.view(*lead, self.output_dim), []
+
+    # ------------------------------------------------------------------ configuration
+    def set_active(self, active_self_attn_layer_num, active_single_attn_layer_num: list, active_hybrid_attn_layer_num,
+                   active_dimension, active_head_num, active_head_dim, active_modality: list, active_cross: list,
+                   active_cross_output: list):
+        """reference :391-418"""
+        self.active_modality = active_modality
+        self.active_cross_output = active_cross_output
+        self.active_cross = active_cross
+        for i, k in enumerate(self.trans_mems0.keys()):
+            self.trans_mems0[k].set_active(active_layer_num=active_single_attn_layer_num[i], active_dimension=active_dimension,
+                                           active_head_num=active_head_num, active_head_dim=active_head_dim)
+        for k in self.trans.keys():
+            self.trans[k].set_active(active_layer_num=active_hybrid_attn_layer_num, active_dimension=active_dimension,
+                                     active_head_num=active_head_num, active_head_dim=active_head_dim)
+        for k in self.trans_mems.keys():
+            self.trans_mems[k].set_active(active_layer_num=active_self_attn_layer_num, active_dimension=active_dimension,
+                                          active_head_num=active_head_num, active_head_dim=active_head_dim)
+
+    def set_active_modalities(self, active_modality: list, active_cross: list, active_cross_output: list):
+        self.active_modality = active_modality
+        self.active_cross_output = active_cross_output
+        self.active_cross = active_cross
+
+    def gen_active_cross(self, active_modality: list, p_cross=0.6, p_cross_output=0.8):
+        """Random fusion-branch choice (reference :439-469).  Consumes the global CPU generator
+        exactly like the reference: per active modality one rand_gen_modality_str (several
+        torch.rand calls) followed by one gen_subnet draw."""
+        n = self.modality_num
+        active_cross: List[list] = [[]] * n
+        active_cross_output: List[list] = [[]] * n
+        if len(active_modality) == 1:
+            a = active_modality[0]
+            active_cross[a] = []
+            active_cross_output[a] = [self.modality_list[a]]
+            return active_cross, active_cross_output
+        sub = ModalityStr([self.modality_list[i] for i in active_modality])
+        for i in active_modality:
+            active_cross[i] = sub.rand_gen_modality_str(modality_set=[self.modality_list[i]], p=p_cross)
+            active_cross_output[i] = gen_subnet(parent_set=[self.modality_list[i]] + list(active_cross[i]), p=p_cross_output)
+        for i in active_modality:      # repair: a modality whose character appears in no chosen output
+            if active_cross_output[i]:
+                continue
+            ch = self.modality_list[i]
+            if not any(ch in name for j in active_modality for name in active_cross_output[j]):
+                active_cross_output[i] = [active_cross[i][0] if active_cross[i] else ch]
+        return active_cross, active_cross_output

@@ -240,9 +240,12 @@ def gen_sampler(m):
         cross, outs = m.gen_active_cross([0, 1, 2])
         ea_seq.append([[list(c) for c in cross], [list(o) for o in outs]])
     names_all = m.m.gen_modality_str_all()
+    torch.manual_seed(77)
+    enc = DynamicTransformerEncoder(20, 5, 4, 2, attn_mask=True)
+    ctor = dict(weights=sd(enc), after=torch.rand(4))
     torch.save(dict(pool=pool, names=["l", "a", "v"], train_seq=train_seq, ea_seq=ea_seq,
                     names_all=names_all, index_list=m.modality_index_list,
-                    state_keys=[k for k in m.state_dict().keys()]),
+                    state_keys=[k for k in m.state_dict().keys()], ctor=ctor),
                os.path.join(OUT, "sampler.pt"))
 
 

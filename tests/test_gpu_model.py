@@ -1,0 +1,132 @@
+"""GPU: the supernet driver (mtb200.dynamic_models2.DynamicMULTModel) against the outputs of
+the UNMODIFIED reference model (tests/golden/model.pt) and against the oracle with replayed
+dropout masks."""
+import re
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import mult_oracle as O  # noqa: E402
+from test_gpu_parity import MaskFeed, assert_rel  # noqa: E402
+
+
+def _build(G):
+    from mtb200.dynamic_models2 import DynamicMULTModel
+    hp = G["hp"]
+    m = DynamicMULTModel(origin_dimensions=list(hp["dims"]), dimension=hp["d"], num_heads=hp["H"], head_dim=hp["hd"],
+                         layers_single_attn=hp["layers_single"], layers_hybrid_attn=hp["layers_cross"],
+                         layers_self_attn=hp["layers_self"], attn_dropout=hp["attn_dropout"],
+                         relu_dropout=hp["relu_dropout"], res_dropout=hp["res_dropout"], out_dropout=hp["out_dropout"],
+                         embed_dropout=hp["embed_dropout"], attn_mask=True, output_dim=1, modality_set=hp["names"],
+                         all_steps=False, front_end="conv1d")
+    w = {re.sub(r"^proj\.(\d+)\.1\.weight$", r"proj.\1.weight", k): v for k, v in G["weights"].items()}
+    res = m.load_state_dict(w, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert all("_float_tensor" in k or k.startswith("translation") for k in res.missing_keys), res.missing_keys
+    return m.cuda()
+
+
+def _key(k):
+    return re.sub(r"^proj\.(\d+)\.weight$", r"proj.\1.1.weight", k)
+
+
+def _set(m, G, cfg):
+    hp = G["hp"]
+    m.set_active(active_self_attn_layer_num=2, active_single_attn_layer_num=cfg["single"],
+                 active_hybrid_attn_layer_num=2, active_dimension=hp["d"], active_head_num=hp["H"],
+                 active_head_dim=hp["hd"], active_modality=cfg["am"], active_cross=cfg["cross"],
+                 active_cross_output=cfg["outs"])
+
+
+def test_model_eval_matches_reference_golden():
+    import os
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "model.pt"), weights_only=False)
+    from mtb200 import ops
+    ops.set_gemm_mode("fp32")
+    m = _build(G)
+    xs = [x.cuda() for x in G["xs"]]
+    y = G["y"].cuda()
+    for c in G["cases"]:
+        cfg = c["cfg"]
+        if cfg["train"]:
+            continue
+        _set(m, G, cfg)
+        m.eval()
+        m.zero_grad()
+        pred, extra = m(xs)
+        assert extra == []
+        assert_rel(pred, c["pred"], 2e-5, f"{cfg['name']} pred")
+        loss = torch.nn.functional.l1_loss(pred, y)
+        loss.backward()
+        for k, p in m.named_parameters():
+            if k.startswith("translation"):
+                assert p.grad is None
+                continue
+            gold = c["grads"][_key(k)]
+            if gold is None:
+                # modules that did not run keep grad None so Adam skips them
+                assert p.grad is None, (cfg["name"], k)
+            elif float(gold.abs().max()) == 0.0:
+                assert p.grad is not None and float(p.grad.abs().max()) < 1e-7, (cfg["name"], k)
+            else:
+                assert p.grad is not None, (cfg["name"], k)
+                assert_rel(p.grad, gold, 1e-4, f"{cfg['name']} grad {k}")
+
+
+def test_model_train_dropout_matches_oracle():
+    import os
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "model.pt"), weights_only=False)
+    from mtb200 import ops
+    ops.set_gemm_mode("fp32")
+    m = _build(G)
+    hp = G["hp"]
+    xs = [x.cuda() for x in G["xs"]]
+    c = [c for c in G["cases"] if c["cfg"]["train"]][0]
+    cfg = c["cfg"]
+    _set(m, G, cfg)
+    m.train()
+    m.zero_grad()
+    with MaskFeed(ops) as mf:
+        pred, _ = m(xs)
+    loss = torch.nn.functional.l1_loss(pred, G["y"].cuda())
+    loss.backward()
+    w = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in G["weights"].items()}
+
+    def front(i, x):
+        return torch.einsum("bld,ed->lbe", x, w[f"proj.{i}.1.weight"][:, :, 0])
+    ref = O.model_forward(w, G["xs"], modality_list=hp["names"], d=hp["d"], H=hp["H"], hd=hp["hd"],
+                          layers_single=cfg["single"], layers_cross=2, layers_self=2, attn_dropout=hp["attn_dropout"],
+                          relu_dropout=hp["relu_dropout"], res_dropout=hp["res_dropout"], out_dropout=hp["out_dropout"],
+                          embed_dropout=hp["embed_dropout"], active_modality=cfg["am"], active_cross=cfg["cross"],
+                          active_cross_output=cfg["outs"], drop=mf.drop(), front_end=front, ffn=hp["d"])
+    assert_rel(pred, ref, 2e-5, "train pred")
+    torch.nn.functional.l1_loss(ref, G["y"]).backward()
+    for k, p in m.named_parameters():
+        if k.startswith("translation"):
+            continue
+        gr = w[_key(k)].grad
+        if gr is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+        elif float(gr.abs().max()) > 0:
+            assert_rel(p.grad, gr, 1e-4, f"train grad {k}")
+
+
+def test_train_step_runs_and_resamples():
+    from mtb200 import ops
+    from mtb200.dynamic_models2 import DynamicMULTModel
+    from mtb200.train import ALL_POOL_3, HypParams, train_step
+    torch.manual_seed(1111)
+    ops.manual_seed(1111)
+    lens = (6, 14, 14)
+    m = DynamicMULTModel(origin_dimensions=[12, 7, 5], dimension=40, num_heads=8, head_dim=5, layers_single_attn=2,
+                         layers_hybrid_attn=2, layers_self_attn=1, attn_dropout=[0.1, 0.1, 0.0, 0.0], relu_dropout=0.1,
+                         res_dropout=0.3, out_dropout=0.1, embed_dropout=0.3, attn_mask=True, output_dim=1,
+                         modality_set=["l", "a", "v"], all_steps=False, front_end="conv1d").cuda().train()
+    hyp = HypParams(["l", "a", "v"], ALL_POOL_3, 2, 1, 2, 40, 8, 5, seq_lens=lens)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    xs = [torch.randn(4, lens[i], d, device="cuda") for i, d in enumerate((12, 7, 5))]
+    y = torch.randn(4, 1, device="cuda")
+    losses = [float(train_step(m, opt, torch.nn.L1Loss(), xs, y, hyp)) for _ in range(12)]
+    assert all(torch.isfinite(torch.tensor(losses)))
