@@ -1,0 +1,84 @@
+"""Multi-GPU plumbing for the two places the path shards naturally:
+
+* data-parallel training: one process per GPU, every rank draws the IDENTICAL sub-network each
+  step (same seed, same CPU-generator consumption), gradients of the parameters that ran are
+  averaged with ONE flat NCCL all-reduce per bucket between backward and clipping
+  (src/train.py:179-181).  Parameters that did not run keep grad None on every rank alike.
+* EA population fitness: candidates are generated identically on every rank, rank r evaluates
+  candidates r, r+N, ...; only the fp32 scores are all-gathered.
+
+Works on any torch.distributed backend (NCCL on the B200 box, gloo in the CPU tests)."""
+from __future__ import annotations
+
+from typing import Callable, List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> tuple:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class GradSync:
+    """Flat-bucket gradient averaging over the active parameter set."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], bucket_bytes: int = 64 << 20, group=None):
+        self.params = list(params)
+        self.bucket_bytes = bucket_bytes
+        self.group = group
+        self.last_active = 0
+        self.last_bytes = 0
+
+    def buckets(self) -> List[List[torch.Tensor]]:
+        out, cur, size = [], [], 0
+        for p in self.params:
+            if p.grad is None:
+                continue
+            g = p.grad
+            if cur and (size + g.numel() * g.element_size() > self.bucket_bytes or g.dtype != cur[0].dtype):
+                out.append(cur)
+                cur, size = [], 0
+            cur.append(g)
+            size += g.numel() * g.element_size()
+        if cur:
+            out.append(cur)
+        return out
+
+    def __call__(self):
+        rank, n = world()
+        bks = self.buckets()
+        self.last_active = sum(len(b) for b in bks)
+        self.last_bytes = sum(g.numel() * g.element_size() for b in bks for g in b)
+        if n == 1:
+            return
+        works, flats = [], []
+        for b in bks:
+            flat = torch._utils._flatten_dense_tensors(b)
+            flat.div_(n)
+            works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            flats.append(flat)
+        for b, flat, w in zip(bks, flats, works):
+            w.wait()
+            for g, s in zip(b, torch._utils._unflatten_dense_tensors(flat, b)):
+                g.copy_(s)
+
+
+def shard_indices(n_items: int, rank: int, world_size: int) -> List[int]:
+    """Candidate r, r+N, r+2N, ... for rank r."""
+    return list(range(rank, n_items, world_size))
+
+
+def evaluate_population(candidates: Sequence, score_fn: Callable, device=None, group=None) -> List[float]:
+    """Rank r scores candidates r::N with ``score_fn(candidate) -> float``; scores are
+    all-gathered (sum of disjoint one-hot contributions) so every rank returns the full list in
+    candidate order.  Only population_size floats cross NVLink."""
+    rank, n = world()
+    scores = torch.zeros(len(candidates), dtype=torch.float32, device=device)
+    for i in shard_indices(len(candidates), rank, n):
+        scores[i] = float(score_fn(candidates[i]))
+    if n > 1:
+        dist.all_reduce(scores, op=dist.ReduceOp.SUM, group=group)
+    return scores.tolist()

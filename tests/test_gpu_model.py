@@ -116,7 +116,7 @@ def test_model_train_dropout_matches_oracle():
 def test_train_step_runs_and_resamples():
     from mtb200 import ops
     from mtb200.dynamic_models2 import DynamicMULTModel
-    from mtb200.train import ALL_POOL_3, HypParams, train_step
+    from mtb200.train import ALL_POOL_3, HypParams, sample_next_config, train_step
     torch.manual_seed(1111)
     ops.manual_seed(1111)
     lens = (6, 14, 14)
@@ -126,6 +126,7 @@ def test_train_step_runs_and_resamples():
                          modality_set=["l", "a", "v"], all_steps=False, front_end="conv1d").cuda().train()
     hyp = HypParams(["l", "a", "v"], ALL_POOL_3, 2, 1, 2, 40, 8, 5, seq_lens=lens)
     opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    sample_next_config(m, hyp)     # the constructor's default MulT wiring is not length-compatible for unaligned inputs
     xs = [torch.randn(4, lens[i], d, device="cuda") for i, d in enumerate((12, 7, 5))]
     y = torch.randn(4, 1, device="cuda")
     losses = [float(train_step(m, opt, torch.nn.L1Loss(), xs, y, hyp)) for _ in range(12)]
