@@ -302,7 +302,7 @@ def main():
 
 
 def tc_available():
-    return os.environ.get("MTB_TC_READY", "0") == "1"
+    return os.environ.get("MTB_TC_DISABLE", "0") != "1"
 
 
 def kernel_roofline(dev, args, mode):

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MTB_ABI_VERSION 3
+#define MTB_ABI_VERSION 4
 #define MTB_MAX_GROUP 24
 
 /* Dropout RNG: Philox4x32-10.  Element `i` of a dropout site is kept iff
@@ -147,6 +147,7 @@ typedef struct {
   float* dW; float* db;
   int M, N, K;
   int act; float p;
+  float* scratch;   /* [M*N] floats, required by the tensor-core engine when act == 1 (holds dY') */
 } mtb_linear_bwd_desc;
 int mtb_linear_bwd(const mtb_linear_bwd_desc* d, int n, void* stream);
 

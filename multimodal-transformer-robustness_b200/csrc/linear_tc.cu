@@ -1,9 +1,459 @@
-// linear_tc.cu -- tcgen05 / TMEM / TMA GEMM engine (placeholder until the tensor-core
-// kernels land: falls through to the fp32 engine so mode 1 stays functional).
+// linear_tc.cu -- tcgen05 / TMEM / TMA grouped GEMM engine behind mtb_linear_fwd / mtb_linear_bwd
+// (gemm mode 1).  modules/dynamic_multihead_attention.py:259-282, modules/dynamic_layers.py:15-25.
+//
+// One warp-specialised kernel (192 threads, 1 CTA / SM, one 128 x BJ output tile per CTA):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor loads of fp32 operand tiles into a 4-stage
+//              128B-swizzled shared-memory ring, completion on mbarriers
+//   warp 1   : TMEM allocator + MMA issuer -- one elected lane issues tcgen05.mma.kind::tf32
+//              (A and B straight from shared memory, fp32 accumulator in tensor memory) and
+//              tcgen05.commit to release ring slots / publish the accumulator
+//   warps 2-5: epilogue -- tcgen05.ld of the accumulator, bias / ReLU / Philox dropout /
+//              accumulate / atomic split-K, 128-bit stores
+// The same kernel serves forward (both operands K-major), dgrad (B MN-major) and wgrad (both
+// MN-major, split over the token axis) by switching the shared-memory matrix descriptors; fp32
+// data is consumed directly as TF32 (no conversion pass, no bf16 copies of weights in HBM).
+// Partial tiles (M % 128, N % BJ, K % 32 such as K = 200) rely on TMA zero fill.
 #include "common.cuh"
+#include <cuda.h>
+
 namespace mtb {
+
 int linear_fwd_simt(const mtb_linear_desc* d, int n, cudaStream_t st);
 int linear_bwd_simt(const mtb_linear_bwd_desc* d, int n, cudaStream_t st);
-int linear_fwd_tc(const mtb_linear_desc* d, int n, cudaStream_t st) { return linear_fwd_simt(d, n, st); }
-int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) { return linear_bwd_simt(d, n, st); }
+
+constexpr int TC_BI = 128;                 // UMMA M
+constexpr int TC_BR = 32;                  // reduction elements per stage (32 fp32 = one 128 B swizzle row)
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_BI * 128;    // 16 KB
+constexpr int TC_B_BYTES_MAX = 256 * 128;  // 32 KB
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES_MAX;
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024;
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 256;
+
+struct alignas(64) TcProblem {
+  CUtensorMap mapA, mapB;
+  float* C; int64_t ldc;
+  const float* bias;
+  int I, J, R;
+  int BJ;              // tile width along J (multiple of 16, <= 256)
+  int a_mn, b_mn;      // operand is MN-major in shared memory
+  int splits;          // split of the reduction range (epi == 2)
+  int epi;             // 0 store, 1 +=, 2 atomicAdd
+  int act; float p; mtb_rng rng;
+};
+
+struct TcGroup {
+  TcProblem d[MTB_MAX_GROUP];
+  int start[MTB_MAX_GROUP + 1];
+  int n;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must trap, never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (int it = 0; it < (1 << 22); ++it)
+    if (mbar_try_wait(bar, parity)) return;
+  printf("mtb gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), 128-byte swizzle:
+//   [0,14) start >> 4 | [16,30) LBO >> 4 | [32,46) SBO >> 4 | [46,48) version = 1 | [61,64) layout = 2
+//   K-major : SWIZZLE_128B (2); rows 128 B apart, 8-row groups SBO = 1024 B apart (LBO unused)
+//   MN-major: 32-bit operands only exist in the SWIZZLE_128B_BASE32B (1) layout (cutlass
+//             sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only available smem
+//             layout"): atom = 32 MN elements (128 B) x 4 reduction rows; MN atoms LBO = 4096 B apart
+//             (one 32 x 32 TMA box each), 4-row reduction groups SBO = 512 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, bool mn_major) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((mn_major ? 4096u : 16u) >> 4) << 16;
+  d |= (uint64_t)((mn_major ? 512u : 1024u) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(mn_major ? 1 : 2) << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcGroup g) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  int p = 0;
+  while (p + 1 < g.n && (int)blockIdx.x >= g.start[p + 1]) ++p;
+  const int local = blockIdx.x - g.start[p];
+  const TcProblem& P = g.d[p];
+  const int tj_n = (P.J + P.BJ - 1) / P.BJ, ti_n = (P.I + TC_BI - 1) / TC_BI;
+  const int split = local / (ti_n * tj_n);
+  const int tile = local - split * (ti_n * tj_n);
+  const int ti = tile / tj_n, tj = tile - ti * tj_n;
+  const int i0 = ti * TC_BI, j0 = tj * P.BJ;
+  const int nkb_total = (P.R + TC_BR - 1) / TC_BR;
+  const int per = (nkb_total + P.splits - 1) / P.splits;
+  const int kb0 = split * per;
+  const int kb1 = min(nkb_total, kb0 + per);
+  const int nkb = kb1 - kb0;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int b_boxes = P.b_mn ? (P.BJ + 31) / 32 : 1;
+  const uint32_t b_bytes = P.b_mn ? (uint32_t)b_boxes * 4096u : (uint32_t)P.BJ * 128u;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.mapB) : "memory");
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_slot;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        // ===== TMA producer =====
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int s = kb % TC_STAGES;
+          const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, (uint32_t)TC_A_BYTES + b_bytes);
+          const uint32_t sa = smem_base + (uint32_t)s * TC_STAGE_BYTES;
+          const uint32_t sb = sa + TC_A_BYTES;
+          const int r0 = (kb0 + kb) * TC_BR;
+          if (P.a_mn) {
+#pragma unroll
+            for (int b = 0; b < TC_BI / 32; ++b) tma_load_2d(sa + b * 4096, &P.mapA, fb, i0 + b * 32, r0);
+          } else {
+            tma_load_2d(sa, &P.mapA, fb, r0, i0);
+          }
+          if (P.b_mn) {
+            for (int b = 0; b < b_boxes; ++b) tma_load_2d(sb + b * 4096, &P.mapB, fb, j0 + b * 32, r0);
+          } else {
+            tma_load_2d(sb, &P.mapB, fb, r0, j0);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // ===== MMA issuer =====
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, majors, N >> 3, M >> 4
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.a_mn ? 1 : 0) << 15) |
+                               ((uint32_t)(P.b_mn ? 1 : 0) << 16) | ((uint32_t)(P.BJ >> 3) << 17) |
+                               ((uint32_t)(TC_BI >> 4) << 24);
+        const uint32_t a_step = P.a_mn ? 1024u : 32u;    // bytes per UMMA_K (8 tf32) step
+        const uint32_t b_step = P.b_mn ? 1024u : 32u;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int s = kb % TC_STAGES;
+          const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_base + (uint32_t)s * TC_STAGE_BYTES;
+          const uint32_t sb = sa + TC_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BR / 8; ++k) {
+            const uint64_t ad = make_desc(sa + k * a_step, P.a_mn);
+            const uint64_t bd = make_desc(sb + k * b_step, P.b_mn);
+            tcgen05_mma_tf32(tmem_d, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tcgen05_commit(smem_u32(&empty_bar[s]));        // frees the ring slot when these MMAs retire
+        }
+        tcgen05_commit(smem_u32(&tmem_full_bar));         // accumulator complete
+      }
+    } else {
+      // ===== epilogue warps: TMEM lane quadrant = warp_id % 4 =====
+      const int q = warp & 3;
+      const int row = i0 + q * 32 + lane;
+      mbar_wait(smem_u32(&tmem_full_bar), 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const DropCtx dc = make_drop(P.rng, P.p);
+      const bool vec_ok = ((P.ldc & 3) == 0) && ((((uintptr_t)P.C) & 15) == 0) && ((P.J & 3) == 0);
+      for (int c0 = 0; c0 < P.BJ; c0 += 32) {
+        if (j0 + c0 >= P.J) break;                        // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        if (row < P.I) {
+          float* crow = P.C + (int64_t)row * P.ldc;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const int j = j0 + c0 + c;
+            if (j >= P.J || c0 + c >= P.BJ) break;
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              o[e] = __uint_as_float(v[c + e]);
+              if (P.bias && j + e < P.J) o[e] += __ldg(P.bias + j + e);
+            }
+            if (P.act == 1) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+              if (dc.on) {
+                const uint64_t idx = (uint64_t)row * (uint64_t)P.J + (uint64_t)j;
+                if ((idx & 3) == 0) {
+                  const uint4 r = drop_rand4(dc, idx >> 2);
+                  o[0] = r.x >= dc.thr ? o[0] * dc.inv_keep : 0.f; o[1] = r.y >= dc.thr ? o[1] * dc.inv_keep : 0.f;
+                  o[2] = r.z >= dc.thr ? o[2] * dc.inv_keep : 0.f; o[3] = r.w >= dc.thr ? o[3] * dc.inv_keep : 0.f;
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) o[e] = drop_keep1(dc, idx + e) ? o[e] * dc.inv_keep : 0.f;
+                }
+              }
+            }
+            if (P.epi == 0 && vec_ok && j + 3 < P.J) {
+              *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (j + e >= P.J) break;
+                if (P.epi == 0) crow[j + e] = o[e];
+                else if (P.epi == 1) crow[j + e] += o[e];
+                else atomicAdd(crow + j + e, o[e]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ small helpers (backward)
+// scratch = dY * [Y > 0] * inv_keep      (ReLU + dropout backward applied once, feeds dgrad and wgrad)
+__global__ void actgrad_kernel(const float* __restrict__ dY, int64_t ldy, const float* __restrict__ Y, int64_t ldyy,
+                               float* __restrict__ out, int M, int N, float inv_keep) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = e / N;
+    const int n = (int)(e - m * N);
+    out[e] = Y[m * ldyy + n] > 0.f ? dY[m * ldy + n] * inv_keep : 0.f;
+  }
+}
+// db[n] += sum_m dY[m, n]
+__global__ void colsum_kernel(const float* __restrict__ dY, int64_t ldy, float* __restrict__ db, int M, int N, int rows_per_block) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  if (n >= N) return;
+  float s = 0.f;
+  for (int m = m0; m < m1; ++m) s += dY[(int64_t)m * ldy + n];
+  atomicAdd(db + n, s);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// row-major fp32 matrix [rows, cols] with leading dimension ld; box = bx (cols) x by (rows), 128 B swizzle
+static bool make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int bx, int by,
+                     bool mn_major = false) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)bx, (cuuint32_t)by};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static bool tma_ok(const float* p, int64_t ld) { return p != nullptr && ((((uintptr_t)p) & 15) == 0) && (ld % 4 == 0) && ld > 0; }
+
+static int pick_bj(int J) {
+  int best = 64, best_cost = 1 << 30;
+  const int cand[5] = {256, 224, 208, 128, 64};
+  for (int c : cand) {
+    const int tiles = (J + c - 1) / c;
+    const int cost = tiles * c;                  // padded columns computed
+    if (cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
+}
+static int round_bj_mn(int bj) { return ((bj + 31) / 32) * 32; }   // MN-major B tiles are loaded in 32-wide boxes
+
+static bool g_attr_done = false;
+static int launch_tc(const TcProblem* probs, int n, cudaStream_t st) {
+  if (n == 0) return 0;
+  if (!g_attr_done) {
+    MTB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    g_attr_done = true;
+  }
+  TcGroup g;
+  g.n = n;
+  int tot = 0;
+  for (int i = 0; i < n; ++i) {
+    g.d[i] = probs[i];
+    g.start[i] = tot;
+    tot += ((probs[i].I + TC_BI - 1) / TC_BI) * ((probs[i].J + probs[i].BJ - 1) / probs[i].BJ) * probs[i].splits;
+  }
+  g.start[n] = tot;
+  if (tot == 0) return 0;
+  gemm_tc_kernel<<<tot, TC_THREADS, TC_SMEM, st>>>(g);
+  mtb::note_launch();
+  MTB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int linear_fwd_tc(const mtb_linear_desc* d, int n, cudaStream_t st) {
+  TcProblem tc[MTB_MAX_GROUP];
+  mtb_linear_desc rest[MTB_MAX_GROUP];
+  int ntc = 0, nrest = 0;
+  for (int i = 0; i < n; ++i) {
+    const mtb_linear_desc& x = d[i];
+    bool ok = !x.row_idx && !x.col_idx && x.N >= 16 && x.K >= 8 && x.M >= 1 && tma_ok(x.X, x.ldx) && tma_ok(x.W, x.ldw);
+    TcProblem& q = tc[ntc];
+    if (ok) {
+      q = TcProblem{};
+      q.BJ = pick_bj(x.N);
+      ok = make_map(&q.mapA, x.X, x.M, x.K, x.ldx, TC_BR, TC_BI) && make_map(&q.mapB, x.W, x.N, x.K, x.ldw, TC_BR, q.BJ);
+    }
+    if (!ok) { rest[nrest++] = x; continue; }
+    q.C = x.Y; q.ldc = x.ldy; q.bias = x.bias;
+    q.I = x.M; q.J = x.N; q.R = x.K;
+    q.a_mn = 0; q.b_mn = 0; q.splits = 1; q.epi = 0;
+    q.act = x.act; q.p = x.p; q.rng = x.rng;
+    ++ntc;
+  }
+  int rc = launch_tc(tc, ntc, st);
+  if (rc) return rc;
+  if (nrest) return linear_fwd_simt(rest, nrest, st);
+  return 0;
+}
+
+int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
+  TcProblem dg[MTB_MAX_GROUP], wg[MTB_MAX_GROUP];
+  mtb_linear_bwd_desc rest[MTB_MAX_GROUP];
+  int ndg = 0, nwg = 0, nrest = 0;
+  for (int i = 0; i < n; ++i) {
+    const mtb_linear_bwd_desc& x = d[i];
+    bool ok = !x.row_idx && !x.col_idx && x.N >= 16 && x.K >= 16 && x.M >= 1 && tma_ok(x.dY, x.ldy) && tma_ok(x.W, x.ldw) &&
+              (!x.dX || tma_ok(x.dX, x.lddx)) && (!x.dW || tma_ok(x.X, x.ldx)) && (x.act == 0 || x.scratch != nullptr);
+    if (!ok) { rest[nrest++] = x; continue; }
+    const float* dYp = x.dY;
+    int64_t ldyp = x.ldy;
+    if (x.act == 1) {       // dY' = dY * [Y > 0] / (1 - p), materialised once for dgrad + wgrad + bias grad
+      const float inv_keep = x.p > 0.f ? 1.f / (1.f - x.p) : 1.f;
+      const int64_t total = (int64_t)x.M * x.N;
+      const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+      actgrad_kernel<<<blocks, 256, 0, st>>>(x.dY, x.ldy, x.Yact, x.ldyact, x.scratch, x.M, x.N, inv_keep);
+      mtb::note_launch();
+      MTB_CUDA(cudaGetLastError());
+      dYp = x.scratch; ldyp = x.N;
+    }
+    bool built = true;
+    TcProblem qd{}, qw{};
+    if (x.dX) {           // dX[M,K] = dY'[M,N] . W[N,K] : A K-major (reduction n contiguous), B MN-major (k_out contiguous)
+      qd.BJ = round_bj_mn(pick_bj(x.K));
+      if (qd.BJ > 256) qd.BJ = 256;
+      built = built && make_map(&qd.mapA, dYp, x.M, x.N, ldyp, TC_BR, TC_BI) && make_map(&qd.mapB, x.W, x.N, x.K, x.ldw, 32, TC_BR, true);
+      qd.C = x.dX; qd.ldc = x.lddx; qd.bias = nullptr;
+      qd.I = x.M; qd.J = x.K; qd.R = x.N;
+      qd.a_mn = 0; qd.b_mn = 1; qd.splits = 1; qd.epi = x.accumulate_dx ? 1 : 0;
+    }
+    if (x.dW) {           // dW[N,K] += dY'^T[N,M] . X[M,K] : both MN-major, reduction over tokens split across CTAs
+      qw.BJ = round_bj_mn(pick_bj(x.K));
+      if (qw.BJ > 256) qw.BJ = 256;
+      built = built && make_map(&qw.mapA, dYp, x.M, x.N, ldyp, 32, TC_BR, true) && make_map(&qw.mapB, x.X, x.M, x.K, x.ldx, 32, TC_BR, true);
+      qw.C = x.dW; qw.ldc = x.ldw; qw.bias = nullptr;
+      qw.I = x.N; qw.J = x.K; qw.R = x.M;
+      qw.a_mn = 1; qw.b_mn = 1; qw.epi = 2;
+      const int tiles = ((x.N + TC_BI - 1) / TC_BI) * ((x.K + qw.BJ - 1) / qw.BJ);
+      const int nkb = (x.M + TC_BR - 1) / TC_BR;
+      int s = (sm_count() + tiles - 1) / tiles;
+      if (s > nkb / 2) s = nkb / 2;
+      if (s < 1) s = 1;
+      qw.splits = s;
+    }
+    if (!built) { rest[nrest++] = x; continue; }
+    if (x.dX) dg[ndg++] = qd;
+    if (x.dW) wg[nwg++] = qw;
+    if (x.db) {
+      const int rows = 256;
+      dim3 grid((x.N + 127) / 128, (x.M + rows - 1) / rows);
+      colsum_kernel<<<grid, 128, 0, st>>>(dYp, ldyp, x.db, x.M, x.N, rows);
+      mtb::note_launch();
+      MTB_CUDA(cudaGetLastError());
+    }
+  }
+  int rc = launch_tc(dg, ndg, st);
+  if (rc) return rc;
+  rc = launch_tc(wg, nwg, st);
+  if (rc) return rc;
+  if (nrest) return linear_bwd_simt(rest, nrest, st);
+  return 0;
+}
+
+}  // namespace mtb

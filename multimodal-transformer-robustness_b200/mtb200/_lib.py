@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmultb200.so")
 
 MAX_GROUP = 24
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class MtbError(RuntimeError):
@@ -59,7 +59,7 @@ class LinearBwdDesc(C.Structure):
                 ("row_idx", C.c_void_p), ("col_idx", C.c_void_p),
                 ("dX", C.c_void_p), ("lddx", C.c_int64), ("accumulate_dx", C.c_int),
                 ("dW", C.c_void_p), ("db", C.c_void_p), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
-                ("act", C.c_int), ("p", C.c_float)]
+                ("act", C.c_int), ("p", C.c_float), ("scratch", C.c_void_p)]
 
 
 class AttnDesc(C.Structure):

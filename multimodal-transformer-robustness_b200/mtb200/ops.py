@@ -217,6 +217,9 @@ def res_drop(res: Tensor, a: Tensor, p: float, training: bool) -> Tensor:
 
 
 # ----------------------------------------------------------------------------- linear
+_keepalive: list = []     # scratch buffers referenced by in-flight launches of the current call
+
+
 def _lin_fwd_desc(x, W, b, row_idx, col_idx, row0, N, K, y, act, p, seed, off):
     ldw = W.stride(0)
     return LinearDesc(x.data_ptr(), x.stride(0), W.data_ptr() + 4 * row0 * ldw, ldw,
@@ -226,12 +229,16 @@ def _lin_fwd_desc(x, W, b, row_idx, col_idx, row0, N, K, y, act, p, seed, off):
 
 def _lin_bwd_desc(dy, yact, x, W, row_idx, col_idx, row0, N, K, dX, acc, dW, db, act, p):
     ldw = W.stride(0)
+    scratch = None
+    if act == 1 and lib.mtb_get_gemm_mode() == 1:
+        scratch = torch.empty((dy.shape[0], N), device=dy.device, dtype=torch.float32)
+        _keepalive.append(scratch)
     return LinearBwdDesc(dy.data_ptr(), dy.stride(0), _p(yact), yact.stride(0) if yact is not None else 0,
                          _p(x), x.stride(0) if x is not None else 0, W.data_ptr() + 4 * row0 * ldw, ldw,
                          _p(row_idx), _p(col_idx), _p(dX), dX.stride(0) if dX is not None else 0, int(acc),
                          (dW.data_ptr() + 4 * row0 * ldw) if dW is not None else None,
                          (db.data_ptr() + 4 * row0) if db is not None else None,
-                         dy.shape[0], N, K, act, p)
+                         dy.shape[0], N, K, act, p, _p(scratch))
 
 
 class _Linear(torch.autograd.Function):
@@ -258,6 +265,7 @@ class _Linear(torch.autograd.Function):
         db = torch.zeros_like(b) if (b is not None and ctx.needs_input_grad[2] and dW is not None) else None
         d = _lin_bwd_desc(dy, yact, x, W, row_idx, col_idx, row0, N, K, dX, False, dW, db, act, p)
         call_group(lib.mtb_linear_bwd, LinearBwdDesc, [d], _stream(), "mtb_linear_bwd")
+        _keepalive.clear()        # stream-ordered allocator: safe to release after the launches are enqueued
         return dX, dW, db, None, None, None, None, None, None, None, None
 
 

@@ -1,0 +1,94 @@
+"""GPU: the tcgen05 / TMEM / TMA GEMM engine (gemm mode 'tf32').  Tolerances: 3e-3 for a single
+GEMM against fp64 (TF32 keeps 10 mantissa bits; north_star allows 2e-2 for the reduced-precision
+training path), 2e-2 for logits/gradients of a whole encoder against the fp32 oracle."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import mult_oracle as O  # noqa: E402
+from test_gpu_parity import assert_rel  # noqa: E402
+
+
+@pytest.fixture()
+def tf32():
+    from mtb200 import ops
+    prev = ops.set_gemm_mode("tf32")
+    yield ops
+    ops.set_gemm_mode(prev)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 208, 32), (800, 600, 200), (8000, 200, 200), (130, 64, 40), (8000, 800, 200),
+                                   (16, 3000, 600), (300, 200, 800), (1, 256, 512), (257, 1536, 512)])
+def test_tc_linear_fwd_dgrad_wgrad(tf32, M, N, K):
+    ops = tf32
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).cuda().requires_grad_(True)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).cuda().requires_grad_(True)
+    b = torch.randn(N, generator=g).cuda().requires_grad_(True)
+    R = torch.randn(M, N, generator=g).cuda()
+    y = ops.linear(x, W, b, N=N, K=K)
+    (y * R).sum().backward()
+    xd, Wd, bd, Rd = x.detach().double(), W.detach().double(), b.detach().double(), R.double()
+    assert_rel(y, xd @ Wd.t() + bd, 3e-3, "fwd")
+    assert_rel(x.grad, Rd @ Wd, 3e-3, "dgrad")
+    assert_rel(W.grad, Rd.t() @ xd, 3e-3, "wgrad")
+    assert_rel(b.grad, Rd.sum(0), 1e-5, "bias grad")
+
+
+def test_tc_linear_relu_dropout_epilogue_matches_fp32_engine(tf32):
+    ops = tf32
+    M, N, K = 800, 200, 200
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    ops.manual_seed(5)
+    y_tc = ops.linear(x, W, b, N=N, K=K, act=1, p=0.2, training=True)
+    ops.set_gemm_mode("fp32")
+    ops.manual_seed(5)
+    y_ref = ops.linear(x, W, b, N=N, K=K, act=1, p=0.2, training=True)
+    ops.set_gemm_mode("tf32")
+    assert_rel(y_tc, y_ref, 3e-3, "relu+dropout epilogue")
+    # identical Philox mask: dropped positions coincide wherever the pre-activation is clearly positive
+    both = (y_ref > 1e-2)
+    assert bool((y_tc[both] > 0).all())
+
+
+def test_tc_views_and_fallbacks(tf32):
+    """Column-slice views (packed qkv), gathered operands (-> fp32 engine fallback) stay correct."""
+    ops = tf32
+    g = torch.Generator().manual_seed(2)
+    qkv = torch.randn(400, 600, generator=g).cuda()
+    W = (torch.randn(200, 200, generator=g) / 14).cuda()
+    y = ops.linear(qkv[:, 200:400], W, None, N=200, K=200)           # ld = 600, 16-byte aligned offset
+    assert_rel(y, qkv[:, 200:400].double() @ W.double().t(), 3e-3, "strided view")
+    idx = torch.arange(0, 200, 2, device="cuda", dtype=torch.int32)
+    y2 = ops.linear(qkv[:, :100].contiguous(), W, None, N=200, K=100, col_idx=idx)
+    assert_rel(y2, qkv[:, :100].double() @ W.double()[:, ::2].t(), 1e-5, "gather fallback (fp32 engine)")
+
+
+def test_tc_encoder_matches_oracle_within_reduced_precision_tolerance(tf32):
+    from modules.dynamic_transformer import DynamicTransformerEncoder
+    torch.manual_seed(0)
+    E, hd, H = 200, 25, 8
+    enc = DynamicTransformerEncoder(E, hd, H, 2, attn_mask=True)
+    w = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in enc.state_dict().items()}
+    enc = enc.cuda().eval()
+    enc.set_active(2, E, H, hd)
+    x, xk = torch.randn(40, 4, E), torch.randn(130, 4, E)
+    xc, xkc = x.cuda().requires_grad_(True), xk.cuda().requires_grad_(True)
+    out = enc(xc, xkc, xkc)
+    R = torch.randn(out.shape)
+    (out * R.cuda()).sum().backward()
+    xr, xkr = x.clone().requires_grad_(True), xk.clone().requires_grad_(True)
+    ref = O.encoder(w, "", xr, xkr, xkr, embed_dim=E, H=H, hd=hd, n_layers=2, ffn=E)
+    (ref * R).sum().backward()
+    assert_rel(out, ref, 2e-2, "encoder fwd (tf32)")
+    assert_rel(xc.grad, xr.grad, 2e-2, "dx")
+    assert_rel(xkc.grad, xkr.grad, 2e-2, "dxk")
+    for k, p in enc.named_parameters():
+        if w[k].grad is not None and float(w[k].grad.abs().max()) > 0:
+            assert_rel(p.grad, w[k].grad, 2e-2, k)
