@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MTB_ABI_VERSION 4
+#define MTB_ABI_VERSION 5
 #define MTB_MAX_GROUP 24
 
 /* Dropout RNG: Philox4x32-10.  Element `i` of a dropout site is kept iff
@@ -120,6 +120,13 @@ int mtb_resln_bwd(const mtb_resln_bwd_desc* d, int n, void* stream);
  * slicing of the out-projection are expressed as index arrays; plain prefix slices just
  * use a smaller N/K with the full ldw.
  * act: 0 = none, 1 = ReLU followed by dropout(p) (modules/dynamic_transformer.py:181-182). */
+/* Optional block structure of an index array: idx == concat_s [seg[s]*len, (seg[s]+1)*len), s < n.
+ * n == 0 means "unknown / not block structured".  The reference's active_mask gathers are unions
+ * of d-wide blocks (src/dynamic_models2.py:243-251); when the host states that structure the
+ * tensor-core engine addresses the blocks through TMA instead of falling back to the fp32 engine. */
+#define MTB_MAX_SEGS 16
+typedef struct { int32_t len; int32_t n; int32_t seg[MTB_MAX_SEGS]; } mtb_segs;
+
 typedef struct {
   const float* X; int64_t ldx;
   const float* W; int64_t ldw;
@@ -128,6 +135,7 @@ typedef struct {
   float* Y; int64_t ldy;
   int M, N, K;
   int act; float p; mtb_rng rng;
+  mtb_segs row_segs, col_segs;
 } mtb_linear_desc;
 int mtb_linear_fwd(const mtb_linear_desc* d, int n, void* stream);
 
@@ -148,6 +156,7 @@ typedef struct {
   int M, N, K;
   int act; float p;
   float* scratch;   /* [M*N] floats, required by the tensor-core engine when act == 1 (holds dY') */
+  mtb_segs row_segs, col_segs;
 } mtb_linear_bwd_desc;
 int mtb_linear_bwd(const mtb_linear_bwd_desc* d, int n, void* stream);
 

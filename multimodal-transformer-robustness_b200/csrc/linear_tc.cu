@@ -31,11 +31,22 @@ constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024;
 constexpr int TC_THREADS = 192;
 constexpr int TC_TMEM_COLS = 256;
 
+constexpr int TC_MAXSEG = 16;
+
+// Every logical axis (I rows of D, J cols of D, R reduction) may be SEGMENTED: the compact
+// axis is n_seg blocks of seg_len elements and block s lives at physical block index seg[s] of
+// the (larger) parameter tensor.  This is how the reference's active_mask gathers
+// (src/dynamic_models2.py:243-251: unions of d-wide column blocks) reach TMA: operands are 4-D
+// tensor maps {col_in_block, col_block, row_in_block, row_block}, tiles never straddle a block
+// and TMA zero-fills the tail of a partially covered block.  Unsegmented axes use one block.
 struct alignas(64) TcProblem {
   CUtensorMap mapA, mapB;
   float* C; int64_t ldc;
   const float* bias;
-  int I, J, R;
+  int I, J, R;         // compact sizes
+  int i_len, i_nseg, j_len, j_nseg, r_len, r_nseg;
+  uint8_t a_iseg[TC_MAXSEG], a_rseg[TC_MAXSEG], b_jseg[TC_MAXSEG], b_rseg[TC_MAXSEG];
+  uint8_t c_iseg[TC_MAXSEG], c_jseg[TC_MAXSEG], bias_seg[TC_MAXSEG];
   int BJ;              // tile width along J (multiple of 16, <= 256)
   int a_mn, b_mn;      // operand is MN-major in shared memory
   int splits;          // split of the reduction range (epi == 2)
@@ -77,6 +88,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tcgen05_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -129,12 +144,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   while (p + 1 < g.n && (int)blockIdx.x >= g.start[p + 1]) ++p;
   const int local = blockIdx.x - g.start[p];
   const TcProblem& P = g.d[p];
-  const int tj_n = (P.J + P.BJ - 1) / P.BJ, ti_n = (P.I + TC_BI - 1) / TC_BI;
+  const int tpi = (P.i_len + TC_BI - 1) / TC_BI, tpj = (P.j_len + P.BJ - 1) / P.BJ;   // tiles per block
+  const int ti_n = tpi * P.i_nseg, tj_n = tpj * P.j_nseg;
   const int split = local / (ti_n * tj_n);
   const int tile = local - split * (ti_n * tj_n);
   const int ti = tile / tj_n, tj = tile - ti * tj_n;
-  const int i0 = ti * TC_BI, j0 = tj * P.BJ;
-  const int nkb_total = (P.R + TC_BR - 1) / TC_BR;
+  const int is = ti / tpi, il0 = (ti - is * tpi) * TC_BI;        // block / offset inside block along I
+  const int js = tj / tpj, jl0 = (tj - js * tpj) * P.BJ;
+  const int kbps = (P.r_len + TC_BR - 1) / TC_BR;                // reduction slabs per block
+  const int nkb_total = kbps * P.r_nseg;
   const int per = (nkb_total + P.splits - 1) / P.splits;
   const int kb0 = split * per;
   const int kb1 = min(nkb_total, kb0 + per);
@@ -173,17 +191,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           mbar_expect_tx(fb, (uint32_t)TC_A_BYTES + b_bytes);
           const uint32_t sa = smem_base + (uint32_t)s * TC_STAGE_BYTES;
           const uint32_t sb = sa + TC_A_BYTES;
-          const int r0 = (kb0 + kb) * TC_BR;
+          const int rs = (kb0 + kb) / kbps;
+          const int rl0 = ((kb0 + kb) - rs * kbps) * TC_BR;
+          // 4-D coordinates {col_in_block, col_block, row_in_block, row_block}; K-major operands have the
+          // reduction on the (contiguous) column axis, MN-major operands on the row axis
           if (P.a_mn) {
 #pragma unroll
-            for (int b = 0; b < TC_BI / 32; ++b) tma_load_2d(sa + b * 4096, &P.mapA, fb, i0 + b * 32, r0);
+            for (int b = 0; b < TC_BI / 32; ++b)
+              tma_load_4d(sa + b * 4096, &P.mapA, fb, il0 + b * 32, P.a_iseg[is], rl0, P.a_rseg[rs]);
           } else {
-            tma_load_2d(sa, &P.mapA, fb, r0, i0);
+            tma_load_4d(sa, &P.mapA, fb, rl0, P.a_rseg[rs], il0, P.a_iseg[is]);
           }
           if (P.b_mn) {
-            for (int b = 0; b < b_boxes; ++b) tma_load_2d(sb + b * 4096, &P.mapB, fb, j0 + b * 32, r0);
+            for (int b = 0; b < b_boxes; ++b)
+              tma_load_4d(sb + b * 4096, &P.mapB, fb, jl0 + b * 32, P.b_jseg[js], rl0, P.b_rseg[rs]);
           } else {
-            tma_load_2d(sb, &P.mapB, fb, r0, j0);
+            tma_load_4d(sb, &P.mapB, fb, rl0, P.b_rseg[rs], jl0, P.b_jseg[js]);
           }
         }
       }
@@ -216,32 +239,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     } else {
       // ===== epilogue warps: TMEM lane quadrant = warp_id % 4 =====
       const int q = warp & 3;
-      const int row = i0 + q * 32 + lane;
+      const int il = il0 + q * 32 + lane;                 // row inside its block
+      const bool row_ok = il < P.i_len;
+      const int64_t row_c = (int64_t)is * P.i_len + il;   // compact row (dropout index)
       mbar_wait(smem_u32(&tmem_full_bar), 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const DropCtx dc = make_drop(P.rng, P.p);
-      const bool vec_ok = ((P.ldc & 3) == 0) && ((((uintptr_t)P.C) & 15) == 0) && ((P.J & 3) == 0);
+      float* crow = P.C + ((int64_t)P.c_iseg[is] * P.i_len + il) * P.ldc + (int64_t)P.c_jseg[js] * P.j_len;
+      const float* brow = P.bias ? P.bias + (int64_t)P.bias_seg[js] * P.j_len : nullptr;
+      const bool vec_ok = ((P.ldc & 3) == 0) && ((((uintptr_t)P.C) & 15) == 0) && ((P.j_len & 3) == 0);
       for (int c0 = 0; c0 < P.BJ; c0 += 32) {
-        if (j0 + c0 >= P.J) break;                        // warp-uniform
+        if (jl0 + c0 >= P.j_len) break;                   // warp-uniform
         uint32_t v[32];
         tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        if (row < P.I) {
-          float* crow = P.C + (int64_t)row * P.ldc;
+        if (row_ok) {
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
-            const int j = j0 + c0 + c;
-            if (j >= P.J || c0 + c >= P.BJ) break;
+            const int j = jl0 + c0 + c;                   // column inside its block
+            if (j >= P.j_len || c0 + c >= P.BJ) break;
             float o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               o[e] = __uint_as_float(v[c + e]);
-              if (P.bias && j + e < P.J) o[e] += __ldg(P.bias + j + e);
+              if (brow && j + e < P.j_len) o[e] += __ldg(brow + j + e);
             }
             if (P.act == 1) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
               if (dc.on) {
-                const uint64_t idx = (uint64_t)row * (uint64_t)P.J + (uint64_t)j;
+                const uint64_t idx = (uint64_t)row_c * (uint64_t)P.J + (uint64_t)((int64_t)js * P.j_len + j);
                 if ((idx & 3) == 0) {
                   const uint4 r = drop_rand4(dc, idx >> 2);
                   o[0] = r.x >= dc.thr ? o[0] * dc.inv_keep : 0.f; o[1] = r.y >= dc.thr ? o[1] * dc.inv_keep : 0.f;
@@ -252,12 +278,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                 }
               }
             }
-            if (P.epi == 0 && vec_ok && j + 3 < P.J) {
+            if (P.epi == 0 && vec_ok && j + 3 < P.j_len) {
               *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                if (j + e >= P.J) break;
+                if (j + e >= P.j_len) break;
                 if (P.epi == 0) crow[j + e] = o[e];
                 else if (P.epi == 1) crow[j + e] += o[e];
                 else atomicAdd(crow + j + e, o[e]);
@@ -286,14 +312,26 @@ __global__ void actgrad_kernel(const float* __restrict__ dY, int64_t ldy, const 
     out[e] = Y[m * ldyy + n] > 0.f ? dY[m * ldy + n] * inv_keep : 0.f;
   }
 }
-// db[n] += sum_m dY[m, n]
-__global__ void colsum_kernel(const float* __restrict__ dY, int64_t ldy, float* __restrict__ db, int M, int N, int rows_per_block) {
+// db[phys(n)] += sum_m dY[m, n]; one thread per column, 64 rows per block, 8 independent loads in flight
+constexpr int COLSUM_ROWS = 64;
+struct ColsumArgs {
+  const float* dY; int64_t ldy; float* db; int M, N, seg_len; uint8_t seg[TC_MAXSEG];
+};
+__global__ void __launch_bounds__(128) colsum_kernel(const ColsumArgs a) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
-  if (n >= N) return;
-  float s = 0.f;
-  for (int m = m0; m < m1; ++m) s += dY[(int64_t)m * ldy + n];
-  atomicAdd(db + n, s);
+  const int m0 = blockIdx.y * COLSUM_ROWS, m1 = min(a.M, m0 + COLSUM_ROWS);
+  if (n >= a.N) return;
+  const float* p = a.dY + n;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int m = m0;
+  for (; m + 8 <= m1; m += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s[u] += p[(int64_t)(m + u) * a.ldy];
+  }
+  for (; m < m1; ++m) s[0] += p[(int64_t)m * a.ldy];
+  const float t = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+  const int sgi = n / a.seg_len;
+  atomicAdd(a.db + (int64_t)a.seg[sgi] * a.seg_len + (n - sgi * a.seg_len), t);
 }
 
 // ------------------------------------------------------------------ host side
@@ -315,16 +353,18 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// row-major fp32 matrix [rows, cols] with leading dimension ld; box = bx (cols) x by (rows), 128 B swizzle
-static bool make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int bx, int by,
-                     bool mn_major = false) {
+// Row-major fp32 matrix with leading dimension ld seen as 4-D {col_in_block, col_block, row_in_block,
+// row_block}: column blocks of clen (ncb of them), row blocks of rlen (nrb of them); box = bx cols x by rows.
+static bool make_map(CUtensorMap* m, const float* ptr, int64_t ld, int64_t clen, int64_t ncb, int64_t rlen, int64_t nrb,
+                     int bx, int by, bool mn_major) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)bx, (cuuint32_t)by};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  if (ncb > 1 && (clen % 4) != 0) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)clen, (cuuint64_t)ncb, (cuuint64_t)rlen, (cuuint64_t)nrb};
+  cuuint64_t strides[3] = {(cuuint64_t)(ncb > 1 ? clen * 4 : ld * 4), (cuuint64_t)ld * 4, (cuuint64_t)rlen * ld * 4};
+  cuuint32_t box[4] = {(cuuint32_t)bx, 1, (cuuint32_t)by, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
@@ -344,6 +384,29 @@ static int pick_bj(int J) {
 }
 static int round_bj_mn(int bj) { return ((bj + 31) / 32) * 32; }   // MN-major B tiles are loaded in 32-wide boxes
 
+// axis description derived from the public descriptor
+struct Axis {
+  int len, n;                       // block length, number of compact blocks
+  uint8_t phys[TC_MAXSEG];          // physical block index of compact block s
+  int nphys;                        // physical blocks addressable (max + 1)
+};
+static bool make_axis(Axis& a, int total, const int32_t* idx, const mtb_segs& sg) {
+  if (idx == nullptr) {
+    a.len = total; a.n = 1; a.phys[0] = 0; a.nphys = 1;
+    return true;
+  }
+  if (sg.n <= 0 || sg.n > TC_MAXSEG || sg.len <= 0 || sg.len * sg.n != total || (sg.len % 4) != 0) return false;
+  a.len = sg.len; a.n = sg.n; a.nphys = 0;
+  for (int s = 0; s < sg.n; ++s) {
+    if (sg.seg[s] < 0 || sg.seg[s] > 255) return false;
+    a.phys[s] = (uint8_t)sg.seg[s];
+    if (sg.seg[s] + 1 > a.nphys) a.nphys = sg.seg[s] + 1;
+  }
+  return true;
+}
+static void ident(uint8_t* d, int n) { for (int s = 0; s < TC_MAXSEG; ++s) d[s] = (uint8_t)(s < n ? s : 0); }
+static void copy_phys(uint8_t* d, const Axis& a) { for (int s = 0; s < TC_MAXSEG; ++s) d[s] = s < a.n ? a.phys[s] : 0; }
+
 static bool g_attr_done = false;
 static int launch_tc(const TcProblem* probs, int n, cudaStream_t st) {
   if (n == 0) return 0;
@@ -355,9 +418,10 @@ static int launch_tc(const TcProblem* probs, int n, cudaStream_t st) {
   g.n = n;
   int tot = 0;
   for (int i = 0; i < n; ++i) {
-    g.d[i] = probs[i];
+    const TcProblem& q = probs[i];
+    g.d[i] = q;
     g.start[i] = tot;
-    tot += ((probs[i].I + TC_BI - 1) / TC_BI) * ((probs[i].J + probs[i].BJ - 1) / probs[i].BJ) * probs[i].splits;
+    tot += ((q.i_len + TC_BI - 1) / TC_BI) * q.i_nseg * ((q.j_len + q.BJ - 1) / q.BJ) * q.j_nseg * q.splits;
   }
   g.start[n] = tot;
   if (tot == 0) return 0;
@@ -373,16 +437,22 @@ int linear_fwd_tc(const mtb_linear_desc* d, int n, cudaStream_t st) {
   int ntc = 0, nrest = 0;
   for (int i = 0; i < n; ++i) {
     const mtb_linear_desc& x = d[i];
-    bool ok = !x.row_idx && !x.col_idx && x.N >= 16 && x.K >= 8 && x.M >= 1 && tma_ok(x.X, x.ldx) && tma_ok(x.W, x.ldw);
+    Axis an, ak;
+    bool ok = x.N >= 16 && x.K >= 8 && x.M >= 1 && tma_ok(x.X, x.ldx) && tma_ok(x.W, x.ldw) &&
+              make_axis(an, x.N, x.row_idx, x.row_segs) && make_axis(ak, x.K, x.col_idx, x.col_segs);
     TcProblem& q = tc[ntc];
     if (ok) {
       q = TcProblem{};
-      q.BJ = pick_bj(x.N);
-      ok = make_map(&q.mapA, x.X, x.M, x.K, x.ldx, TC_BR, TC_BI) && make_map(&q.mapB, x.W, x.N, x.K, x.ldw, TC_BR, q.BJ);
+      q.BJ = pick_bj(an.len);
+      ok = make_map(&q.mapA, x.X, x.ldx, ak.len, ak.n, x.M, 1, TC_BR, TC_BI, false) &&
+           make_map(&q.mapB, x.W, x.ldw, ak.len, ak.nphys, an.len, an.nphys, TC_BR, q.BJ, false);
     }
     if (!ok) { rest[nrest++] = x; continue; }
     q.C = x.Y; q.ldc = x.ldy; q.bias = x.bias;
     q.I = x.M; q.J = x.N; q.R = x.K;
+    q.i_len = x.M; q.i_nseg = 1; q.j_len = an.len; q.j_nseg = an.n; q.r_len = ak.len; q.r_nseg = ak.n;
+    ident(q.a_iseg, 1); ident(q.a_rseg, ak.n); copy_phys(q.b_jseg, an); copy_phys(q.b_rseg, ak);
+    ident(q.c_iseg, 1); ident(q.c_jseg, an.n); copy_phys(q.bias_seg, an);
     q.a_mn = 0; q.b_mn = 0; q.splits = 1; q.epi = 0;
     q.act = x.act; q.p = x.p; q.rng = x.rng;
     ++ntc;
@@ -399,38 +469,39 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
   int ndg = 0, nwg = 0, nrest = 0;
   for (int i = 0; i < n; ++i) {
     const mtb_linear_bwd_desc& x = d[i];
-    bool ok = !x.row_idx && !x.col_idx && x.N >= 16 && x.K >= 16 && x.M >= 1 && tma_ok(x.dY, x.ldy) && tma_ok(x.W, x.ldw) &&
-              (!x.dX || tma_ok(x.dX, x.lddx)) && (!x.dW || tma_ok(x.X, x.ldx)) && (x.act == 0 || x.scratch != nullptr);
+    Axis an, ak;
+    bool ok = x.N >= 16 && x.K >= 16 && x.M >= 1 && tma_ok(x.dY, x.ldy) && tma_ok(x.W, x.ldw) &&
+              (!x.dX || tma_ok(x.dX, x.lddx)) && (!x.dW || tma_ok(x.X, x.ldx)) && (x.act == 0 || x.scratch != nullptr) &&
+              make_axis(an, x.N, x.row_idx, x.row_segs) && make_axis(ak, x.K, x.col_idx, x.col_segs);
     if (!ok) { rest[nrest++] = x; continue; }
-    const float* dYp = x.dY;
-    int64_t ldyp = x.ldy;
-    if (x.act == 1) {       // dY' = dY * [Y > 0] / (1 - p), materialised once for dgrad + wgrad + bias grad
-      const float inv_keep = x.p > 0.f ? 1.f / (1.f - x.p) : 1.f;
-      const int64_t total = (int64_t)x.M * x.N;
-      const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-      actgrad_kernel<<<blocks, 256, 0, st>>>(x.dY, x.ldy, x.Yact, x.ldyact, x.scratch, x.M, x.N, inv_keep);
-      mtb::note_launch();
-      MTB_CUDA(cudaGetLastError());
-      dYp = x.scratch; ldyp = x.N;
-    }
     bool built = true;
     TcProblem qd{}, qw{};
-    if (x.dX) {           // dX[M,K] = dY'[M,N] . W[N,K] : A K-major (reduction n contiguous), B MN-major (k_out contiguous)
-      qd.BJ = round_bj_mn(pick_bj(x.K));
+    const float* dYp = x.act == 1 ? x.scratch : x.dY;
+    const int64_t ldyp = x.act == 1 ? x.N : x.ldy;
+    if (x.dX) {           // dX[M,K] = dY'[M,N] . W'[N,K] : A K-major (reduction n contiguous), B MN-major (k_out contiguous)
+      qd.BJ = round_bj_mn(pick_bj(ak.len));
       if (qd.BJ > 256) qd.BJ = 256;
-      built = built && make_map(&qd.mapA, dYp, x.M, x.N, ldyp, TC_BR, TC_BI) && make_map(&qd.mapB, x.W, x.N, x.K, x.ldw, 32, TC_BR, true);
+      built = built && make_map(&qd.mapA, dYp, ldyp, an.len, an.n, x.M, 1, TC_BR, TC_BI, false) &&
+              make_map(&qd.mapB, x.W, x.ldw, ak.len, ak.nphys, an.len, an.nphys, 32, TC_BR, true);
       qd.C = x.dX; qd.ldc = x.lddx; qd.bias = nullptr;
       qd.I = x.M; qd.J = x.K; qd.R = x.N;
+      qd.i_len = x.M; qd.i_nseg = 1; qd.j_len = ak.len; qd.j_nseg = ak.n; qd.r_len = an.len; qd.r_nseg = an.n;
+      ident(qd.a_iseg, 1); ident(qd.a_rseg, an.n); copy_phys(qd.b_jseg, ak); copy_phys(qd.b_rseg, an);
+      ident(qd.c_iseg, 1); ident(qd.c_jseg, ak.n); ident(qd.bias_seg, 1);
       qd.a_mn = 0; qd.b_mn = 1; qd.splits = 1; qd.epi = x.accumulate_dx ? 1 : 0;
     }
-    if (x.dW) {           // dW[N,K] += dY'^T[N,M] . X[M,K] : both MN-major, reduction over tokens split across CTAs
-      qw.BJ = round_bj_mn(pick_bj(x.K));
+    if (x.dW) {           // dW'[N,K] += dY'^T[N,M] . X[M,K] : both MN-major, reduction over tokens split across CTAs
+      qw.BJ = round_bj_mn(pick_bj(ak.len));
       if (qw.BJ > 256) qw.BJ = 256;
-      built = built && make_map(&qw.mapA, dYp, x.M, x.N, ldyp, 32, TC_BR, true) && make_map(&qw.mapB, x.X, x.M, x.K, x.ldx, 32, TC_BR, true);
+      built = built && make_map(&qw.mapA, dYp, ldyp, an.len, an.n, x.M, 1, 32, TC_BR, true) &&
+              make_map(&qw.mapB, x.X, x.ldx, ak.len, ak.n, x.M, 1, 32, TC_BR, true);
       qw.C = x.dW; qw.ldc = x.ldw; qw.bias = nullptr;
       qw.I = x.N; qw.J = x.K; qw.R = x.M;
+      qw.i_len = an.len; qw.i_nseg = an.n; qw.j_len = ak.len; qw.j_nseg = ak.n; qw.r_len = x.M; qw.r_nseg = 1;
+      ident(qw.a_iseg, an.n); ident(qw.a_rseg, 1); ident(qw.b_jseg, ak.n); ident(qw.b_rseg, 1);
+      copy_phys(qw.c_iseg, an); copy_phys(qw.c_jseg, ak); ident(qw.bias_seg, 1);
       qw.a_mn = 1; qw.b_mn = 1; qw.epi = 2;
-      const int tiles = ((x.N + TC_BI - 1) / TC_BI) * ((x.K + qw.BJ - 1) / qw.BJ);
+      const int tiles = ((an.len + TC_BI - 1) / TC_BI) * an.n * ((ak.len + qw.BJ - 1) / qw.BJ) * ak.n;
       const int nkb = (x.M + TC_BR - 1) / TC_BR;
       int s = (sm_count() + tiles - 1) / tiles;
       if (s > nkb / 2) s = nkb / 2;
@@ -438,12 +509,22 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
       qw.splits = s;
     }
     if (!built) { rest[nrest++] = x; continue; }
+    if (x.act == 1) {       // dY' = dY * [Y > 0] / (1 - p), materialised once for dgrad + wgrad + bias grad
+      const float inv_keep = x.p > 0.f ? 1.f / (1.f - x.p) : 1.f;
+      const int64_t total = (int64_t)x.M * x.N;
+      const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+      actgrad_kernel<<<blocks, 256, 0, st>>>(x.dY, x.ldy, x.Yact, x.ldyact, x.scratch, x.M, x.N, inv_keep);
+      mtb::note_launch();
+      MTB_CUDA(cudaGetLastError());
+    }
     if (x.dX) dg[ndg++] = qd;
     if (x.dW) wg[nwg++] = qw;
     if (x.db) {
-      const int rows = 256;
-      dim3 grid((x.N + 127) / 128, (x.M + rows - 1) / rows);
-      colsum_kernel<<<grid, 128, 0, st>>>(dYp, ldyp, x.db, x.M, x.N, rows);
+      ColsumArgs ca{};
+      ca.dY = dYp; ca.ldy = ldyp; ca.db = x.db; ca.M = x.M; ca.N = x.N; ca.seg_len = an.len;
+      for (int s = 0; s < TC_MAXSEG; ++s) ca.seg[s] = s < an.n ? an.phys[s] : 0;
+      dim3 grid((x.N + 127) / 128, (x.M + COLSUM_ROWS - 1) / COLSUM_ROWS);
+      colsum_kernel<<<grid, 128, 0, st>>>(ca);
       mtb::note_launch();
       MTB_CUDA(cudaGetLastError());
     }

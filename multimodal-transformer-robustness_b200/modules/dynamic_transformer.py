@@ -12,7 +12,7 @@ import torch
 from torch import nn
 
 from mtb200 import ops
-from mtb200.slicing import as_index, is_masked
+from mtb200.slicing import as_index, is_masked, mask_len
 from modules.position_embedding import SinusoidalPositionalEmbedding
 from modules.multihead_attention import MultiheadAttention, mha_forward  # noqa: F401
 from modules.dynamic_multihead_attention import DynamicMultiheadAttention
@@ -114,7 +114,7 @@ class DynamicTransformerEncoder(TransformerEncoder):
         """Static TransformerEncoder with copies of the active weights (reference :91-102)."""
         pe = self.embed_positions
         if is_masked(active_mask):
-            pe.embedding_dim = len(active_mask)
+            pe.embedding_dim = mask_len(active_mask)
         layers_nn = [l.get_active_subnet(active_dimension, active_head_num, active_head_dim, active_mask)
                      for l in self.layers[:active_layer_num]]
         ln = self.layer_norm.copy(active_mask=active_mask)
@@ -164,7 +164,7 @@ class DynamicTransformerEncoderLayer(TransformerEncoderLayer):
         """Stand-alone layer forward (reference :159-188); the encoder uses the fused schedule."""
         masked = is_masked(active_mask)
         if masked:
-            assert len(active_mask) == x.size()[-1]
+            assert mask_len(active_mask) == x.size()[-1]
         assert self.attn_mask, "the reference's attention requires attn_mask=True"
         idx = as_index(active_mask, x.device) if masked else None
         tr = self.training

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmultb200.so")
 
 MAX_GROUP = 24
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class MtbError(RuntimeError):
@@ -21,6 +21,13 @@ class MtbError(RuntimeError):
 
 class Rng(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("offset", C.c_uint64), ("dev", C.c_void_p)]
+
+
+MAX_SEGS = 16
+
+
+class Segs(C.Structure):
+    _fields_ = [("len", C.c_int32), ("n", C.c_int32), ("seg", C.c_int32 * MAX_SEGS)]
 
 
 class EmbedDesc(C.Structure):
@@ -50,7 +57,7 @@ class LinearDesc(C.Structure):
     _fields_ = [("X", C.c_void_p), ("ldx", C.c_int64), ("W", C.c_void_p), ("ldw", C.c_int64),
                 ("bias", C.c_void_p), ("row_idx", C.c_void_p), ("col_idx", C.c_void_p),
                 ("Y", C.c_void_p), ("ldy", C.c_int64), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
-                ("act", C.c_int), ("p", C.c_float), ("rng", Rng)]
+                ("act", C.c_int), ("p", C.c_float), ("rng", Rng), ("row_segs", Segs), ("col_segs", Segs)]
 
 
 class LinearBwdDesc(C.Structure):
@@ -59,7 +66,7 @@ class LinearBwdDesc(C.Structure):
                 ("row_idx", C.c_void_p), ("col_idx", C.c_void_p),
                 ("dX", C.c_void_p), ("lddx", C.c_int64), ("accumulate_dx", C.c_int),
                 ("dW", C.c_void_p), ("db", C.c_void_p), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
-                ("act", C.c_int), ("p", C.c_float), ("scratch", C.c_void_p)]
+                ("act", C.c_int), ("p", C.c_float), ("scratch", C.c_void_p), ("row_segs", Segs), ("col_segs", Segs)]
 
 
 class AttnDesc(C.Structure):

@@ -24,6 +24,7 @@ from modules.dynamic_layers import DynamicLinear
 from modules.dynamic_transformer import DynamicTransformerEncoder
 from . import ops
 from .models2 import AmnSum, ModalityStr, gen_subnet
+from .slicing import make_mask
 
 __all__ = ["DynamicMULTModel", "Transpose", "RNN_Header", "Conv1x1FrontEnd"]
 
@@ -188,7 +189,7 @@ class DynamicMULTModel(nn.Module):
                 k = self.modality_index_list[i][name]
                 mask.extend(range(k * d, (k + 1) * d))
                 out_index.extend(range(d * slot * i + k * d, d * slot * i + (k + 1) * d))
-            mask_t = torch.tensor(mask, dtype=torch.int32, device=dev)
+            mask_t = make_mask(mask, dev)          # cached: no per-step host->device copy
             h = self.trans_mems['mems' + self.modality_list[i]](h, active_mask=mask_t)
             if self.all_steps:
                 hs.append(h)
@@ -198,7 +199,7 @@ class DynamicMULTModel(nn.Module):
             out = torch.cat(hs, dim=2).permute(1, 0, 2)
         else:
             out = torch.cat(last_hs, dim=1)
-        idx = torch.tensor(out_index, dtype=torch.int32, device=dev)
+        idx = make_mask(out_index, dev)
         lead = out.shape[:-1]
         o2 = out.reshape(-1, out.shape[-1])
         C = idx.numel()

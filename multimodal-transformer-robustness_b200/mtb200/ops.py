@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import (AttnBwdDesc, AttnDesc, EmbedDesc, LinearBwdDesc, LinearDesc, ResLnBwdDesc,
-                   ResLnDesc, Rng, call_group, lib)
+                   ResLnDesc, Rng, Segs, call_group, lib)
 
 Tensor = torch.Tensor
 
@@ -76,12 +76,27 @@ def _mat(t: Tensor, name: str) -> Tensor:
     return t
 
 
-def _idx(t: Optional[Tensor]) -> Optional[Tensor]:
+def _idx(t) -> Optional[Tensor]:
+    """index tensor of a Mask / tensor / None"""
     if t is None:
         return None
+    t = getattr(t, "idx", t)
     if t.dtype != torch.int32 or not t.is_contiguous():
         t = t.to(torch.int32).contiguous()
     return t
+
+
+_NO_SEGS = Segs(0, 0)
+
+
+def _segs(m) -> Segs:
+    """block structure of a Mask (empty for bare tensors / None)"""
+    if m is None or getattr(m, "segs", None) is None:
+        return _NO_SEGS
+    s = Segs(m.seg_len, len(m.segs))
+    for i, v in enumerate(m.segs):
+        s.seg[i] = v
+    return s
 
 
 def _p(t: Optional[Tensor]):
@@ -220,14 +235,14 @@ def res_drop(res: Tensor, a: Tensor, p: float, training: bool) -> Tensor:
 _keepalive: list = []     # scratch buffers referenced by in-flight launches of the current call
 
 
-def _lin_fwd_desc(x, W, b, row_idx, col_idx, row0, N, K, y, act, p, seed, off):
+def _lin_fwd_desc(x, W, b, row_idx, col_idx, row0, N, K, y, act, p, seed, off, rsegs=_NO_SEGS, csegs=_NO_SEGS):
     ldw = W.stride(0)
     return LinearDesc(x.data_ptr(), x.stride(0), W.data_ptr() + 4 * row0 * ldw, ldw,
                       (b.data_ptr() + 4 * row0) if b is not None else None, _p(row_idx), _p(col_idx),
-                      y.data_ptr(), y.stride(0), x.shape[0], N, K, act, p, _rng_struct(seed, off))
+                      y.data_ptr(), y.stride(0), x.shape[0], N, K, act, p, _rng_struct(seed, off), rsegs, csegs)
 
 
-def _lin_bwd_desc(dy, yact, x, W, row_idx, col_idx, row0, N, K, dX, acc, dW, db, act, p):
+def _lin_bwd_desc(dy, yact, x, W, row_idx, col_idx, row0, N, K, dX, acc, dW, db, act, p, rsegs=_NO_SEGS, csegs=_NO_SEGS):
     ldw = W.stride(0)
     scratch = None
     if act == 1 and lib.mtb_get_gemm_mode() == 1:
@@ -238,35 +253,35 @@ def _lin_bwd_desc(dy, yact, x, W, row_idx, col_idx, row0, N, K, dX, acc, dW, db,
                          _p(row_idx), _p(col_idx), _p(dX), dX.stride(0) if dX is not None else 0, int(acc),
                          (dW.data_ptr() + 4 * row0 * ldw) if dW is not None else None,
                          (db.data_ptr() + 4 * row0) if db is not None else None,
-                         dy.shape[0], N, K, act, p, _p(scratch))
+                         dy.shape[0], N, K, act, p, _p(scratch), rsegs, csegs)
 
 
 class _Linear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, W, b, row_idx, col_idx, row0, N, K, act, p, training):
+    def forward(ctx, x, W, b, row_idx, col_idx, row0, N, K, act, p, training, rsegs, csegs):
         M = x.shape[0]
         assert x.shape[1] == K, (x.shape, K)
         y = torch.empty((M, N), device=x.device, dtype=torch.float32)
         p = float(p) if (training and act == 1) else 0.0
         seed, off = rng.site(M * N, p) if p > 0 else (0, 0)
-        d = _lin_fwd_desc(x, W, b, row_idx, col_idx, row0, N, K, y, act, p, seed, off)
+        d = _lin_fwd_desc(x, W, b, row_idx, col_idx, row0, N, K, y, act, p, seed, off, rsegs, csegs)
         call_group(lib.mtb_linear_fwd, LinearDesc, [d], _stream(), "mtb_linear_fwd")
         ctx.save_for_backward(x, W, b, row_idx, col_idx, y if act == 1 else None)
-        ctx.cfg = (row0, N, K, act, p)
+        ctx.cfg = (row0, N, K, act, p, rsegs, csegs)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, W, b, row_idx, col_idx, yact = ctx.saved_tensors
-        row0, N, K, act, p = ctx.cfg
+        row0, N, K, act, p, rsegs, csegs = ctx.cfg
         dy = _mat(dy, "dy")
         dX = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dW = torch.zeros_like(W) if ctx.needs_input_grad[1] else None
         db = torch.zeros_like(b) if (b is not None and ctx.needs_input_grad[2] and dW is not None) else None
-        d = _lin_bwd_desc(dy, yact, x, W, row_idx, col_idx, row0, N, K, dX, False, dW, db, act, p)
+        d = _lin_bwd_desc(dy, yact, x, W, row_idx, col_idx, row0, N, K, dX, False, dW, db, act, p, rsegs, csegs)
         call_group(lib.mtb_linear_bwd, LinearBwdDesc, [d], _stream(), "mtb_linear_bwd")
         _keepalive.clear()        # stream-ordered allocator: safe to release after the launches are enqueued
-        return dX, dW, db, None, None, None, None, None, None, None, None
+        return dX, dW, db, None, None, None, None, None, None, None, None, None, None
 
 
 def linear(x: Tensor, W: Tensor, b: Optional[Tensor], *, N: int, K: int, row0: int = 0,
@@ -277,7 +292,7 @@ def linear(x: Tensor, W: Tensor, b: Optional[Tensor], *, N: int, K: int, row0: i
     _chk(W, "weight")
     assert W.is_contiguous()
     return _Linear.apply(_mat(x, "x"), W, b, _idx(row_idx), _idx(col_idx), int(row0), int(N), int(K), int(act), p,
-                         training)
+                         training, _segs(row_idx), _segs(col_idx))
 
 
 class _InProjCross(torch.autograd.Function):

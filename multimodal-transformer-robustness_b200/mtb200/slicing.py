@@ -7,7 +7,7 @@ rows are contiguous and a plain row offset is used instead of an index array."""
 from __future__ import annotations
 
 import functools
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 
@@ -35,17 +35,68 @@ def out_proj_cols(H: int, hd: int, aH: int, ahd: int, device) -> Optional[torch.
     return _head_index(H, hd, aH, ahd, 0, 1, str(device))
 
 
-def as_index(mask, device) -> Optional[torch.Tensor]:
-    """Reference-style ``active_mask`` ([None] sentinel, list, or Int tensor) -> int32 device tensor."""
+class Mask:
+    """An ``active_mask``: int32 device index tensor plus (when the indices are a union of
+    equally sized, aligned blocks -- the only kind the model produces, src/dynamic_models2.py:243-251)
+    the block structure, which lets the tensor-core GEMM address the blocks through TMA."""
+    __slots__ = ("idx", "seg_len", "segs")
+
+    def __init__(self, idx: torch.Tensor, seg_len: int = 0, segs=None):
+        self.idx, self.seg_len, self.segs = idx, seg_len, segs
+
+    def numel(self) -> int:
+        return self.idx.numel()
+
+    def long(self) -> torch.Tensor:
+        return self.idx.long()
+
+
+def _block_structure(ix: Sequence[int]):
+    """(block_len, [block ids]) if ix is a concatenation of aligned blocks of equal length."""
+    n = len(ix)
+    if n == 0:
+        return 0, None
+    run = 1
+    while run < n and ix[run] == ix[run - 1] + 1:
+        run += 1
+    if run < 4 or n % run != 0 or n // run > 16:
+        return 0, None
+    segs = []
+    for s in range(0, n, run):
+        if ix[s] % run != 0 or any(ix[s + t] != ix[s] + t for t in range(run)):
+            return 0, None
+        segs.append(ix[s] // run)
+    return run, segs
+
+
+_mask_cache: dict = {}
+
+
+def make_mask(indices: Sequence[int], device) -> Mask:
+    """Cached Mask from a Python index list (no device synchronisation)."""
+    key = (tuple(indices), str(device))
+    m = _mask_cache.get(key)
+    if m is None:
+        ln, segs = _block_structure(key[0])
+        m = Mask(torch.tensor(key[0], dtype=torch.int32, device=device), ln, segs)
+        if len(_mask_cache) > 4096:
+            _mask_cache.clear()
+        _mask_cache[key] = m
+    return m
+
+
+def as_index(mask, device) -> Optional[Mask]:
+    """Reference-style ``active_mask`` ([None] sentinel, list, Int tensor or Mask) -> Mask.
+    A bare tensor has to be read back once to learn its block structure (one small D2H copy)."""
     if mask is None:
         return None
+    if isinstance(mask, Mask):
+        return mask
     if isinstance(mask, (list, tuple)):
         if len(mask) == 0 or mask[0] is None:
             return None
-        return torch.tensor(mask, dtype=torch.int32, device=device)
-    if mask.device != torch.device(device) or mask.dtype != torch.int32:
-        mask = mask.to(device=device, dtype=torch.int32)
-    return mask.contiguous()
+        return make_mask(mask, device)
+    return make_mask(mask.detach().cpu().tolist(), device)
 
 
 def is_masked(mask) -> bool:
@@ -54,3 +105,7 @@ def is_masked(mask) -> bool:
     if isinstance(mask, (list, tuple)):
         return len(mask) > 0 and mask[0] is not None
     return True
+
+
+def mask_len(mask) -> int:
+    return mask.numel() if isinstance(mask, (Mask, torch.Tensor)) else len(mask)
