@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MTB_ABI_VERSION 5
+#define MTB_ABI_VERSION 6
 #define MTB_MAX_GROUP 24
 
 /* Dropout RNG: Philox4x32-10.  Element `i` of a dropout site is kept iff
@@ -73,6 +73,16 @@ typedef struct {
 int mtb_embed_fwd(const mtb_embed_desc* d, int n, void* stream);
 /* dx[L*B, E] (contiguous) = scale * keep/(1-p) * dy ; d->x = dy, d->y = dx */
 int mtb_embed_bwd(const mtb_embed_desc* d, int n, void* stream);
+
+/* ---- strided sum / copy: dst[T,E] = (accumulate ? dst : 0) + sum_i src_i[T,E], n_src in 1..3 ------
+ * The fusion DAG's glue (src/dynamic_models2.py:242 torch.cat, :257 h[-1], and the gradient fan-in
+ * of a branch output consumed by several later branches) without materialising concatenations. */
+typedef struct {
+  const float* src[3]; int64_t ld_src[3]; int n_src;
+  float* dst; int64_t ld_dst;
+  int T, E; int accumulate;
+} mtb_addn_desc;
+int mtb_addn(const mtb_addn_desc* d, int n, void* stream);
 
 /* ---- (a3,a10) dropout + residual + LayerNorm ------------------------------------------
  * modules/dynamic_transformer.py:163,169-170,173-178,185-187,87 + modules/dynamic_layers.py:61-67.

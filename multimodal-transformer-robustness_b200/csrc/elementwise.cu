@@ -117,6 +117,43 @@ static int launch_embed(const mtb_embed_desc* d, int n, cudaStream_t st) {
   return 0;
 }
 
+__global__ void __launch_bounds__(EW_THREADS) addn_kernel(const __grid_constant__ Group<mtb_addn_desc> g) {
+  int local;
+  const int pi = find_problem(g, blockIdx.x, local);
+  const mtb_addn_desc& d = g.d[pi];
+  const int E = d.E;
+  const int64_t total = (int64_t)d.T * E;
+  const bool vec = (E & 3) == 0 && (d.ld_dst & 3) == 0 && ((((uintptr_t)d.dst) & 15) == 0) &&
+                   (d.ld_src[0] & 3) == 0 && ((((uintptr_t)d.src[0]) & 15) == 0) &&
+                   (d.n_src < 2 || ((d.ld_src[1] & 3) == 0 && ((((uintptr_t)d.src[1]) & 15) == 0))) &&
+                   (d.n_src < 3 || ((d.ld_src[2] & 3) == 0 && ((((uintptr_t)d.src[2]) & 15) == 0)));
+  if (vec) {
+    const int64_t nvec = total >> 2;
+    const int ev = E >> 2;
+    for (int u = 0; u < EW_VEC_PER_THREAD; ++u) {
+      const int64_t v = (int64_t)local * (EW_THREADS * EW_VEC_PER_THREAD) + threadIdx.x + (int64_t)u * EW_THREADS;
+      if (v >= nvec) break;
+      const int64_t t = v / ev;
+      const int c = (int)(v - t * ev) << 2;
+      float4 acc = d.accumulate ? *reinterpret_cast<const float4*>(d.dst + t * d.ld_dst + c) : make_float4(0, 0, 0, 0);
+      for (int i = 0; i < d.n_src; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(d.src[i] + t * d.ld_src[i] + c);
+        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+      }
+      *reinterpret_cast<float4*>(d.dst + t * d.ld_dst + c) = acc;
+    }
+  } else {
+    const int64_t base = (int64_t)local * (EW_THREADS * EW_VEC_PER_THREAD * 4);
+    for (int64_t e = base + threadIdx.x; e < base + EW_THREADS * EW_VEC_PER_THREAD * 4 && e < total; e += EW_THREADS) {
+      const int64_t t = e / E;
+      const int c = (int)(e - t * E);
+      float acc = d.accumulate ? d.dst[t * d.ld_dst + c] : 0.f;
+      for (int i = 0; i < d.n_src; ++i) acc += d.src[i][t * d.ld_src[i] + c];
+      d.dst[t * d.ld_dst + c] = acc;
+    }
+  }
+}
+
 __global__ void mask_kernel(mtb_rng rng, float p, int64_t n, uint8_t* keep) {
   const DropCtx dc = make_drop(rng, p);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -133,6 +170,27 @@ int mtb_embed_fwd(const mtb_embed_desc* d, int n, void* stream) {
 }
 int mtb_embed_bwd(const mtb_embed_desc* d, int n, void* stream) {
   return mtb::launch_embed<true>(d, n, (cudaStream_t)stream);
+}
+int mtb_addn(const mtb_addn_desc* d, int n, void* stream) {
+  using namespace mtb;
+  MTB_CHECK(n >= 1 && n <= MTB_MAX_GROUP, "addn: group size %d out of range", n);
+  Group<mtb_addn_desc> g;
+  g.n = n;
+  int tot = 0;
+  for (int i = 0; i < n; ++i) {
+    MTB_CHECK(d[i].n_src >= 1 && d[i].n_src <= 3 && d[i].dst && d[i].src[0], "addn: bad problem %d", i);
+    g.d[i] = d[i];
+    g.start[i] = tot;
+    const int64_t total = (int64_t)d[i].T * d[i].E;
+    const int64_t per = (int64_t)EW_THREADS * EW_VEC_PER_THREAD * 4;
+    tot += (int)((total + per - 1) / per);
+  }
+  g.start[n] = tot;
+  if (tot == 0) return 0;
+  addn_kernel<<<tot, EW_THREADS, 0, (cudaStream_t)stream>>>(g);
+  mtb::note_launch();
+  MTB_CUDA(cudaGetLastError());
+  return 0;
 }
 int mtb_dropout_mask(mtb_rng rng, float p, int64_t n, uint8_t* keep, void* stream) {
   if (n <= 0) return 0;

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmultb200.so")
 
 MAX_GROUP = 24
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class MtbError(RuntimeError):
@@ -34,6 +34,11 @@ class EmbedDesc(C.Structure):
     _fields_ = [("x", C.c_void_p), ("sl", C.c_int64), ("sb", C.c_int64), ("se", C.c_int64),
                 ("y", C.c_void_p), ("L", C.c_int), ("B", C.c_int), ("E", C.c_int),
                 ("scale", C.c_float), ("p", C.c_float), ("rng", Rng)]
+
+
+class AddNDesc(C.Structure):
+    _fields_ = [("src", C.c_void_p * 3), ("ld_src", C.c_int64 * 3), ("n_src", C.c_int),
+                ("dst", C.c_void_p), ("ld_dst", C.c_int64), ("T", C.c_int), ("E", C.c_int), ("accumulate", C.c_int)]
 
 
 class ResLnDesc(C.Structure):
@@ -97,6 +102,7 @@ SYMBOLS = {
     "mtb_rng_advance": ([C.c_void_p, C.c_uint64, C.c_void_p], C.c_int),
     "mtb_embed_fwd": ([C.POINTER(EmbedDesc), C.c_int, C.c_void_p], C.c_int),
     "mtb_embed_bwd": ([C.POINTER(EmbedDesc), C.c_int, C.c_void_p], C.c_int),
+    "mtb_addn": ([C.POINTER(AddNDesc), C.c_int, C.c_void_p], C.c_int),
     "mtb_resln_fwd": ([C.POINTER(ResLnDesc), C.c_int, C.c_void_p], C.c_int),
     "mtb_resln_bwd": ([C.POINTER(ResLnBwdDesc), C.c_int, C.c_void_p], C.c_int),
     "mtb_linear_fwd": ([C.POINTER(LinearDesc), C.c_int, C.c_void_p], C.c_int),

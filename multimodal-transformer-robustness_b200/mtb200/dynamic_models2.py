@@ -79,7 +79,7 @@ class DynamicMULTModel(nn.Module):
     def __init__(self, origin_dimensions: list, dimension, num_heads, head_dim, layers_single_attn,
                  layers_hybrid_attn, layers_self_attn, attn_dropout: list, relu_dropout, res_dropout, out_dropout,
                  embed_dropout, attn_mask, output_dim, modality_set, all_steps, stride=0, padding=0, kernel_size=0,
-                 experiment_type="random_sample", front_end="gru", prune_dead_branches=True):
+                 experiment_type="random_sample", front_end="gru", prune_dead_branches=True, use_engine=True):
         super().__init__()
         self.orig_dimensions = origin_dimensions
         self.d = dimension
@@ -103,6 +103,8 @@ class DynamicMULTModel(nn.Module):
         self.modality_num = len(self.orig_dimensions)
         self.combined_dim = AmnSum(self.modality_num) * self.d
         self.prune_dead_branches = prune_dead_branches
+        self.use_engine = use_engine          # plan executor (mtb200.engine); False = per-op autograd path
+        self._engine = None
 
         # front-ends (construction order = RNG order of the reference, :134-149)
         proj = []
@@ -164,9 +166,44 @@ class DynamicMULTModel(nn.Module):
                 need.update(name)
         return need
 
+    # ------------------------------------------------------------------ plan-executor path
+    def reset_engine(self):
+        self._engine = None
+
+    def engine(self):
+        if self._engine is None:
+            from .engine import Engine
+            seed = ops.rng.seed if ops.rng.seed is not None else torch.initial_seed()
+            self._engine = Engine(self, next(self.parameters()).device, seed=seed)
+        return self._engine
+
+    def _engine_ok(self, x) -> bool:
+        if not self.use_engine or self.all_steps or not x[0].is_cuda or self.d % 4 != 0:
+            return False
+        sa = self.trans_mems0['mems0' + self.modality_list[0]].layers
+        for encs in (self.trans_mems0, self.trans, self.trans_mems):
+            for enc in encs.values():
+                for l in enc.layers[:enc.active_layer_num]:
+                    a = l.self_attn
+                    if a.active_num_heads != a.num_heads or a.active_head_dim != a.head_dim or a.head_dim > 64:
+                        return False
+        return True
+
+    def _forward_engine(self, x):
+        need = self._needed_modalities() if self.prune_dead_branches else set(self.modality_list)
+        px = []
+        for i, ch in enumerate(self.modality_list):
+            if ch in need:
+                px.append(self.proj[i](x[i]).permute(2, 0, 1))
+            else:      # not consumed in this step: only its (L, B) is needed for the plan key
+                px.append(x[i].new_empty((x[i].shape[1], x[i].shape[0], 0)))
+        return self.engine().forward(px), []
+
     def forward(self, x):
         """x: list of per-modality inputs.  Returns (prediction, []) like the reference (:222-291)."""
         assert len(x) == self.modality_num
+        if self._engine_ok(x):
+            return self._forward_engine(x)
         need = self._needed_modalities() if self.prune_dead_branches else set(self.modality_list)
         dev = next(self.parameters()).device
         h_ = {}

@@ -49,7 +49,8 @@ class Drop:
       mode="torch"   F.dropout(training=True) on the global torch generator, i.e.
                      exactly what the reference does on CPU (bit-identical masks
                      when called in the same order under the same seed)
-      mode="inject"  keep-masks supplied by the caller through ``fn(tag, shape, p)``
+      mode="inject"  keep-masks supplied by the caller through ``fn(tag, shape, p)`` (tag is the
+                     fully qualified site name, e.g. 'trans.crossla.layers.0.attn')
                      -> bool/float tensor of ``shape`` (1 = keep); used to feed the
                      masks the CUDA kernels generate (Philox) into the oracle.
     """
@@ -162,7 +163,7 @@ def _sliced_in_proj(W: Tensor, b: Tensor, H: int, hd: int, aH: int, ahd: int,
 
 def attention(w: Weights, pre: str, q_in: Tensor, k_in: Tensor, v_in: Tensor,
               H: int, hd: int, aH: int, ahd: int, p_attn: float = 0.0,
-              mask=None, drop: Drop = NO_DROP, self_attn: Optional[bool] = None) -> Tensor:
+              mask=None, drop: Drop = NO_DROP, self_attn: Optional[bool] = None, drop_tag: str = "attn") -> Tensor:
     """Weight-sliced multi-head attention on seq-first tensors [L, B, E].
     ``pre`` is the key prefix (e.g. 'layers.0.self_attn.').  Uses the first ``aH``
     heads and first ``ahd`` dims per head; optional column gather ``mask`` (self
@@ -188,7 +189,7 @@ def attention(w: Weights, pre: str, q_in: Tensor, k_in: Tensor, v_in: Tensor,
     Lk = k.shape[1]
     s = torch.bmm(q, k.transpose(1, 2)) + future_mask(Lq, Lk, q.dtype).unsqueeze(0)
     pr = F.softmax(s.float() if s.dtype != torch.float64 else s, dim=-1).type_as(s)
-    pr = drop(pr, p_attn, "attn")
+    pr = drop(pr, p_attn, drop_tag)
     o = torch.bmm(pr, v)
     o = o.transpose(0, 1).contiguous().view(Lq, B, aH * ahd)
     E_out = Wo.shape[0]
@@ -209,18 +210,18 @@ def encoder_layer(w: Weights, pre: str, x: Tensor, x_k=None, x_v=None, *, H: int
     res = x
     xn = dyn_layernorm(x, ln0g, ln0b, mask)
     if x_k is None and x_v is None:
-        a = attention(w, pre + "self_attn.", xn, xn, xn, H, hd, aH, ahd, p_attn, mask, drop, True)
+        a = attention(w, pre + "self_attn.", xn, xn, xn, H, hd, aH, ahd, p_attn, mask, drop, True, pre + "attn")
     else:
         kn = dyn_layernorm(x_k, ln0g, ln0b)
         vn = dyn_layernorm(x_v, ln0g, ln0b)
-        a = attention(w, pre + "self_attn.", xn, kn, vn, H, hd, aH, ahd, p_attn, None, drop, False)
-    x = res + drop(a, p_res, "res0")
+        a = attention(w, pre + "self_attn.", xn, kn, vn, H, hd, aH, ahd, p_attn, None, drop, False, pre + "attn")
+    x = res + drop(a, p_res, pre + "res0")
     res = x
     xn = dyn_layernorm(x, ln1g, ln1b, mask)
     h = dyn_linear(xn, w[pre + "fc1.l.weight"], w[pre + "fc1.l.bias"], dim_out=ffn, mask_in=mask)
-    h = drop(F.relu(h), p_relu, "relu")
+    h = drop(F.relu(h), p_relu, pre + "relu")
     y = dyn_linear(h, w[pre + "fc2.l.weight"], w[pre + "fc2.l.bias"], dim_in=ffn, mask_out=mask)
-    return res + drop(y, p_res, "res1")
+    return res + drop(y, p_res, pre + "res1")
 
 
 # --------------------------------------------------------------------------- a2: encoder
@@ -242,12 +243,12 @@ def encoder(w: Weights, pre: str, x_in: Tensor, x_in_k=None, x_in_v=None, *, emb
     ffn = 4 * H * hd if ffn is None else ffn
     scale = math.sqrt(embed_dim)
     E_pos = mask.numel() if mask is not None else embed_dim
-    x = drop(_embed(x_in, scale, E_pos), p_embed, "embed_q")
+    x = drop(_embed(x_in, scale, E_pos), p_embed, pre + "embed_q")
     cross = x_in_k is not None and x_in_v is not None
     if cross:
         assert mask is None
-        x_k = drop(_embed(x_in_k, scale, E_pos), p_embed, "embed_k")
-        x_v = drop(_embed(x_in_v, scale, E_pos), p_embed, "embed_v")
+        x_k = drop(_embed(x_in_k, scale, E_pos), p_embed, pre + "embed_k")
+        x_v = drop(_embed(x_in_v, scale, E_pos), p_embed, pre + "embed_v")
     for i in range(n_layers):
         lp = f"{pre}layers.{i}."
         if cross:
@@ -397,6 +398,6 @@ def model_forward(w: Weights, xs: Sequence[Tensor], *, modality_list: Sequence[s
     out = torch.cat(hs, dim=2).permute(1, 0, 2) if all_steps else torch.cat(last, dim=1)
     oi = torch.tensor(out_idx, dtype=torch.int64)
     z = dyn_linear(out, w["proj1.l.weight"], w["proj1.l.bias"], mask_in=oi)
-    z = drop(F.relu(z), out_dropout, "out")
+    z = drop(F.relu(z), out_dropout, "head.out")
     z = dyn_linear(z, w["proj2.l.weight"], w["proj2.l.bias"], mask_out=oi) + out
     return dyn_linear(z, w["out_layer.l.weight"], w["out_layer.l.bias"], mask_in=oi)

@@ -28,7 +28,7 @@ def test_descriptor_layouts_match_header_sizes():
     import subprocess
     import tempfile
     from mtb200 import _lib
-    names = {"mtb_rng": _lib.Rng, "mtb_embed_desc": _lib.EmbedDesc, "mtb_resln_desc": _lib.ResLnDesc,
+    names = {"mtb_rng": _lib.Rng, "mtb_embed_desc": _lib.EmbedDesc, "mtb_resln_desc": _lib.ResLnDesc, "mtb_addn_desc": _lib.AddNDesc, "mtb_segs": _lib.Segs,
              "mtb_resln_bwd_desc": _lib.ResLnBwdDesc, "mtb_linear_desc": _lib.LinearDesc,
              "mtb_linear_bwd_desc": _lib.LinearBwdDesc, "mtb_attn_desc": _lib.AttnDesc,
              "mtb_attn_bwd_desc": _lib.AttnBwdDesc}

@@ -1,0 +1,173 @@
+"""GPU: the plan executor (mtb200.engine) -- stage-batched grouped launches over a static arena,
+manual backward, CUDA-graph replay -- against the UNMODIFIED reference's outputs (golden) and the
+oracle with replayed Philox masks."""
+import math
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import mult_oracle as O  # noqa: E402
+from test_gpu_model import _build, _key, _set  # noqa: E402
+from test_gpu_parity import assert_rel  # noqa: E402
+
+
+def _golden():
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "model.pt"), weights_only=False)
+
+
+def _check_grads(m, gold_grads, name, tol=1e-4):
+    for k, p in m.named_parameters():
+        if k.startswith("translation"):
+            assert p.grad is None
+            continue
+        gold = gold_grads[_key(k)]
+        if gold is None:
+            assert p.grad is None, (name, k)
+        elif float(gold.abs().max()) == 0.0:
+            assert p.grad is not None and float(p.grad.abs().max()) < 1e-7, (name, k)
+        else:
+            assert p.grad is not None, (name, k)
+            assert_rel(p.grad, gold, tol, f"{name} grad {k}")
+
+
+def test_engine_eval_matches_reference_golden_and_graph_replay():
+    from mtb200 import ops
+    ops.set_gemm_mode("fp32")
+    G = _golden()
+    m = _build(G, use_engine=True)
+    xs = [x.cuda() for x in G["xs"]]
+    y = G["y"].cuda()
+    for rep in range(3):                       # rep 0: plan build + eager run; rep >= 2: CUDA-graph replay
+        for c in G["cases"]:
+            cfg = c["cfg"]
+            if cfg["train"]:
+                continue
+            _set(m, G, cfg)
+            m.eval()
+            m.zero_grad()
+            pred, extra = m(xs)
+            assert extra == []
+            assert_rel(pred, c["pred"], 2e-5, f"{cfg['name']} pred (rep {rep})")
+            torch.nn.functional.l1_loss(pred, y).backward()
+            _check_grads(m, c["grads"], f"{cfg['name']} rep {rep}")
+    eng = m.engine()
+    assert eng.stats["graph_replays"] > 0, eng.stats
+    assert eng.stats["plans"] == 4
+
+
+def test_engine_train_dropout_matches_oracle():
+    from mtb200 import ops
+    ops.set_gemm_mode("fp32")
+    ops.manual_seed(99)
+    G = _golden()
+    m = _build(G, use_engine=True)
+    hp = G["hp"]
+    xs = [x.cuda() for x in G["xs"]]
+    c = [c for c in G["cases"] if c["cfg"]["train"]][0]
+    cfg = c["cfg"]
+    _set(m, G, cfg)
+    m.train()
+    for rep in range(3):                       # the third pass is a graph replay with fresh masks
+        m.zero_grad()
+        pred, _ = m(xs)
+        torch.nn.functional.l1_loss(pred, G["y"].cuda()).backward()
+        eng = m.engine()
+        plan = eng.last_plan
+        base = eng.step_offset
+
+        def provider(tag, shape, p, plan=plan, base=base, eng=eng):
+            off, n, pp = plan.sites[tag]
+            assert abs(pp - p) < 1e-7, (tag, pp, p)
+            if tag.endswith("attn"):
+                BH, Lq, Lk = shape
+                Lk4 = (Lk + 3) // 4 * 4
+                assert n == BH * Lq * Lk4
+                return ops.dropout_mask(eng.seed, base + off, p, n, "cuda").view(BH, Lq, Lk4)[:, :, :Lk].cpu()
+            assert n == math.prod(shape), (tag, n, shape)
+            return ops.dropout_mask(eng.seed, base + off, p, n, "cuda").view(shape).cpu()
+        w = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in G["weights"].items()}
+
+        def front(i, x):
+            return torch.einsum("bld,ed->lbe", x, w[f"proj.{i}.1.weight"][:, :, 0])
+        ref = O.model_forward(w, G["xs"], modality_list=hp["names"], d=hp["d"], H=hp["H"], hd=hp["hd"],
+                              layers_single=cfg["single"], layers_cross=2, layers_self=2, attn_dropout=hp["attn_dropout"],
+                              relu_dropout=hp["relu_dropout"], res_dropout=hp["res_dropout"], out_dropout=hp["out_dropout"],
+                              embed_dropout=hp["embed_dropout"], active_modality=cfg["am"], active_cross=cfg["cross"],
+                              active_cross_output=cfg["outs"], drop=O.Drop("inject", provider), front_end=front, ffn=hp["d"])
+        assert_rel(pred, ref, 2e-5, f"train pred (rep {rep})")
+        torch.nn.functional.l1_loss(ref, G["y"]).backward()
+        gold = {k: v.grad for k, v in w.items()}
+        for k, p in m.named_parameters():
+            if k.startswith("translation"):
+                continue
+            gr = gold[_key(k)]
+            if gr is None:
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            elif float(gr.abs().max()) > 0:
+                assert_rel(p.grad, gr, 1e-4, f"train grad {k} (rep {rep})")
+    assert m.engine().stats["graph_replays"] > 0
+
+
+def test_engine_matches_per_op_path_at_real_dims_unaligned():
+    """d=200, 8 heads x 25, unaligned lengths, a two-level fusion config: plan executor vs the
+    per-op autograd path (same kernels, different orchestration), eval mode, both GEMM engines."""
+    from mtb200 import ops
+    from mtb200.dynamic_models2 import DynamicMULTModel
+    torch.manual_seed(0)
+    kw = dict(origin_dimensions=[300, 74, 35], dimension=200, num_heads=8, head_dim=25, layers_single_attn=2,
+              layers_hybrid_attn=2, layers_self_attn=1, attn_dropout=[0.1, 0.1, 0.0, 0.0], relu_dropout=0.1, res_dropout=0.3,
+              out_dropout=0.1, embed_dropout=0.3, attn_mask=True, output_dim=1, modality_set=["l", "a", "v"], all_steps=False,
+              front_end="conv1d")
+    m = DynamicMULTModel(**kw).cuda().eval()
+    lens = (20, 70, 70)
+    xs = [torch.randn(4, lens[i], dd, device="cuda") for i, dd in enumerate((300, 74, 35))]
+    xs[1][0, 40:] = 0
+    y = torch.randn(4, 1, device="cuda")
+    m.set_active(active_self_attn_layer_num=1, active_single_attn_layer_num=[2, 1, 0], active_hybrid_attn_layer_num=2,
+                 active_dimension=200, active_head_num=8, active_head_dim=25, active_modality=[0, 1, 2],
+                 active_cross=[["la", "lv", "lav"], ["av"], ["va"]], active_cross_output=[["la", "lav"], ["a", "av"], ["va"]])
+    for mode, tol in (("fp32", 2e-5), ("tf32", 3e-3)):
+        ops.set_gemm_mode(mode)
+        res = {}
+        for use in (False, True):
+            m.use_engine = use
+            m.zero_grad()
+            pred, _ = m(xs)
+            torch.nn.functional.l1_loss(pred, y).backward()
+            res[use] = (pred.detach().clone(), {k: (None if p.grad is None else p.grad.detach().clone()) for k, p in m.named_parameters()})
+        assert_rel(res[True][0], res[False][0], tol, f"pred {mode}")
+        for k in res[True][1]:
+            a, b = res[True][1][k], res[False][1][k]
+            assert (a is None) == (b is None), k
+            if a is not None and float(b.abs().max()) > 0:
+                if mode == "fp32":
+                    assert_rel(a, b, 1e-4, f"{mode} {k}")
+                else:
+                    assert float((a - b).norm() / b.norm()) < 2e-2, (mode, k)
+    ops.set_gemm_mode("fp32")
+
+
+def test_engine_random_sample_training_steps():
+    from mtb200 import ops
+    from mtb200.dynamic_models2 import DynamicMULTModel
+    from mtb200.train import ALL_POOL_3, HypParams, sample_next_config, train_step
+    torch.manual_seed(1111)
+    ops.manual_seed(1111)
+    ops.set_gemm_mode("tf32")
+    lens = (6, 14, 14)
+    m = DynamicMULTModel(origin_dimensions=[12, 7, 5], dimension=40, num_heads=8, head_dim=5, layers_single_attn=2,
+                         layers_hybrid_attn=2, layers_self_attn=1, attn_dropout=[0.1, 0.1, 0.0, 0.0], relu_dropout=0.1,
+                         res_dropout=0.3, out_dropout=0.1, embed_dropout=0.3, attn_mask=True, output_dim=1,
+                         modality_set=["l", "a", "v"], all_steps=False, front_end="conv1d").cuda().train()
+    hyp = HypParams(["l", "a", "v"], ALL_POOL_3, 2, 1, 2, 40, 8, 5, seq_lens=lens)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    sample_next_config(m, hyp)
+    xs = [torch.randn(4, lens[i], d, device="cuda") for i, d in enumerate((12, 7, 5))]
+    y = torch.randn(4, 1, device="cuda")
+    losses = [float(train_step(m, opt, torch.nn.L1Loss(), xs, y, hyp)) for _ in range(40)]
+    assert all(math.isfinite(v) for v in losses)
+    assert m.engine().stats["plans"] >= 5
+    ops.set_gemm_mode("fp32")

@@ -12,7 +12,7 @@ from oracle import mult_oracle as O  # noqa: E402
 from test_gpu_parity import MaskFeed, assert_rel  # noqa: E402
 
 
-def _build(G):
+def _build(G, use_engine=False):
     from mtb200.dynamic_models2 import DynamicMULTModel
     hp = G["hp"]
     m = DynamicMULTModel(origin_dimensions=list(hp["dims"]), dimension=hp["d"], num_heads=hp["H"], head_dim=hp["hd"],
@@ -20,7 +20,7 @@ def _build(G):
                          layers_self_attn=hp["layers_self"], attn_dropout=hp["attn_dropout"],
                          relu_dropout=hp["relu_dropout"], res_dropout=hp["res_dropout"], out_dropout=hp["out_dropout"],
                          embed_dropout=hp["embed_dropout"], attn_mask=True, output_dim=1, modality_set=hp["names"],
-                         all_steps=False, front_end="conv1d")
+                         all_steps=False, front_end="conv1d", use_engine=use_engine)
     w = {re.sub(r"^proj\.(\d+)\.1\.weight$", r"proj.\1.weight", k): v for k, v in G["weights"].items()}
     res = m.load_state_dict(w, strict=False)
     assert not res.unexpected_keys, res.unexpected_keys
@@ -123,7 +123,7 @@ def test_train_step_runs_and_resamples():
     m = DynamicMULTModel(origin_dimensions=[12, 7, 5], dimension=40, num_heads=8, head_dim=5, layers_single_attn=2,
                          layers_hybrid_attn=2, layers_self_attn=1, attn_dropout=[0.1, 0.1, 0.0, 0.0], relu_dropout=0.1,
                          res_dropout=0.3, out_dropout=0.1, embed_dropout=0.3, attn_mask=True, output_dim=1,
-                         modality_set=["l", "a", "v"], all_steps=False, front_end="conv1d").cuda().train()
+                         modality_set=["l", "a", "v"], all_steps=False, front_end="conv1d", use_engine=False).cuda().train()
     hyp = HypParams(["l", "a", "v"], ALL_POOL_3, 2, 1, 2, 40, 8, 5, seq_lens=lens)
     opt = torch.optim.Adam(m.parameters(), lr=1e-3)
     sample_next_config(m, hyp)     # the constructor's default MulT wiring is not length-compatible for unaligned inputs

@@ -55,7 +55,7 @@ class MaskFeed:
         def fn(tag, shape, p):
             off, n, pp = next(it)
             assert abs(pp - p) < 1e-7, (tag, pp, p)
-            if tag == "attn":
+            if tag.endswith("attn"):
                 BH, Lq, Lk = shape
                 Lk4 = (Lk + 3) // 4 * 4
                 assert n == BH * Lq * Lk4, (tag, n, shape)
