@@ -226,7 +226,7 @@ def main():
 
     model = build_model().to(dev).train()              # identical init on every rank (same seed)
     hyp = make_hyp(args.seq)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)   # torch's fused multi-tensor Adam (optimizer is outside the hot path)
     crit = torch.nn.L1Loss()
     sync = GradSync(list(model.parameters())) if world > 1 else None
     ops.manual_seed(SEED + 7919 * rank)                # dropout differs per rank; the sampler stream does not

@@ -45,8 +45,8 @@ typedef struct {
 int mtb_abi_version(void);
 const char* mtb_last_error(void);
 int mtb_sm_count(void);
-/* which GEMM engine mtb_linear_* uses: 0 = fp32 CUDA-core (parity mode, 1e-5),
- * 1 = tcgen05 TF32 tensor-core (TMA + TMEM).  Returns the previous mode. */
+/* which math engine mtb_linear_* and mtb_attn_* use: 0 = fp32 CUDA-core (parity mode, 1e-5),
+ * 1 = tcgen05 TF32 tensor-core (TMA + TMEM GEMMs, tcgen05 flash attention).  Returns the previous mode. */
 int mtb_set_gemm_mode(int mode);
 int mtb_get_gemm_mode(void);
 /* number of kernels this library has launched so far in this process (bench bookkeeping) */

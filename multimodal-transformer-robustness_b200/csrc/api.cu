@@ -35,6 +35,8 @@ int linear_fwd_tc(const mtb_linear_desc* d, int n, cudaStream_t st);
 int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st);
 int attn_fwd_simt(const mtb_attn_desc* d, int n, cudaStream_t st);
 int attn_bwd_simt(const mtb_attn_bwd_desc* d, int n, cudaStream_t st);
+int attn_fwd_tc(const mtb_attn_desc* d, int n, cudaStream_t st);
+int attn_bwd_tc(const mtb_attn_bwd_desc* d, int n, cudaStream_t st);
 
 }  // namespace mtb
 
@@ -79,6 +81,7 @@ int mtb_attn_fwd(const mtb_attn_desc* d, int n, void* stream) {
   for (int i = 0; i < n; ++i)
     MTB_CHECK(d[i].q && d[i].k && d[i].v && d[i].o && d[i].Lq > 0 && d[i].Lk > 0 && d[i].hd > 0,
               "attn_fwd: bad problem %d", i);
+  if (mtb::g_gemm_mode == 1) return mtb::attn_fwd_tc(d, n, (cudaStream_t)stream);
   return mtb::attn_fwd_simt(d, n, (cudaStream_t)stream);
 }
 
@@ -87,6 +90,7 @@ int mtb_attn_bwd(const mtb_attn_bwd_desc* d, int n, void* stream) {
   for (int i = 0; i < n; ++i)
     MTB_CHECK(d[i].q && d[i].k && d[i].v && d[i].o && d[i].d_o && d[i].lse && d[i].delta && d[i].dq && d[i].dk && d[i].dv,
               "attn_bwd: null operand in problem %d", i);
+  if (mtb::g_gemm_mode == 1) return mtb::attn_bwd_tc(d, n, (cudaStream_t)stream);
   return mtb::attn_bwd_simt(d, n, (cudaStream_t)stream);
 }
 

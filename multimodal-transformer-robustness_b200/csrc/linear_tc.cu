@@ -23,11 +23,10 @@ int linear_bwd_simt(const mtb_linear_bwd_desc* d, int n, cudaStream_t st);
 
 constexpr int TC_BI = 128;                 // UMMA M
 constexpr int TC_BR = 32;                  // reduction elements per stage (32 fp32 = one 128 B swizzle row)
-constexpr int TC_STAGES = 4;
+constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BI * 128;    // 16 KB
-constexpr int TC_B_BYTES_MAX = 256 * 128;  // 32 KB
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES_MAX;
-constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024;
+constexpr int TC_SMEM_BUDGET = 110 * 1024; // <= half an SM's shared memory: two CTAs per SM overlap
+                                           // one tile's epilogue with the other's main loop
 constexpr int TC_THREADS = 192;
 constexpr int TC_TMEM_COLS = 256;
 
@@ -48,6 +47,7 @@ struct alignas(64) TcProblem {
   uint8_t a_iseg[TC_MAXSEG], a_rseg[TC_MAXSEG], b_jseg[TC_MAXSEG], b_rseg[TC_MAXSEG];
   uint8_t c_iseg[TC_MAXSEG], c_jseg[TC_MAXSEG], bias_seg[TC_MAXSEG];
   int BJ;              // tile width along J (multiple of 16, <= 256)
+  int stages;          // shared-memory ring depth (2..4), stage = 16 KB (A) + BJ * 128 B (B)
   int a_mn, b_mn;      // operand is MN-major in shared memory
   int splits;          // split of the reduction range (epi == 2)
   int epi;             // 0 store, 1 +=, 2 atomicAdd
@@ -133,10 +133,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, bool mn_major) {
   return d;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcGroup g) {
+__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ TcGroup g) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
+  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_slot;
 
@@ -162,11 +162,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_boxes = P.b_mn ? (P.BJ + 31) / 32 : 1;
   const uint32_t b_bytes = P.b_mn ? (uint32_t)b_boxes * 4096u : (uint32_t)P.BJ * 128u;
+  const int TC_STAGES = P.stages;
+  const uint32_t TC_STAGE_BYTES = (uint32_t)TC_A_BYTES + (((uint32_t)P.BJ * 128u + 1023u) & ~1023u);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.mapB) : "memory");
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     mbar_init(smem_u32(&tmem_full_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -411,21 +413,27 @@ static bool g_attr_done = false;
 static int launch_tc(const TcProblem* probs, int n, cudaStream_t st) {
   if (n == 0) return 0;
   if (!g_attr_done) {
-    MTB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    MTB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048));
     g_attr_done = true;
   }
   TcGroup g;
   g.n = n;
   int tot = 0;
+  size_t smem = 0;
   for (int i = 0; i < n; ++i) {
-    const TcProblem& q = probs[i];
+    TcProblem q = probs[i];
+    const size_t stage = (size_t)TC_A_BYTES + (((size_t)(q.b_mn ? ((q.BJ + 31) / 32) * 32 : q.BJ) * 128 + 1023) & ~(size_t)1023);
+    int stages = (int)(TC_SMEM_BUDGET / stage);
+    stages = stages > TC_MAX_STAGES ? TC_MAX_STAGES : (stages < 2 ? 2 : stages);
+    q.stages = stages;
+    if (stage * stages + 1024 > smem) smem = stage * stages + 1024;
     g.d[i] = q;
     g.start[i] = tot;
     tot += ((q.i_len + TC_BI - 1) / TC_BI) * q.i_nseg * ((q.j_len + q.BJ - 1) / q.BJ) * q.j_nseg * q.splits;
   }
   g.start[n] = tot;
   if (tot == 0) return 0;
-  gemm_tc_kernel<<<tot, TC_THREADS, TC_SMEM, st>>>(g);
+  gemm_tc_kernel<<<tot, TC_THREADS, smem, st>>>(g);
   mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
   return 0;

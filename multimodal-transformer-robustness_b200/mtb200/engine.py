@@ -616,7 +616,7 @@ def _run(ops, stream: int):
 class Engine:
     """Owns the arenas and the plan cache of one DynamicMULTModel on one device."""
 
-    def __init__(self, model, device, seed: int = 0, graph_after: int = 1):
+    def __init__(self, model, device, seed: int = 0, graph_after: int = 3):
         self.model = model
         self.device = torch.device(device)
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF

@@ -38,6 +38,7 @@ def test_engine_eval_matches_reference_golden_and_graph_replay():
     ops.set_gemm_mode("fp32")
     G = _golden()
     m = _build(G, use_engine=True)
+    m.engine().graph_after = 1
     xs = [x.cuda() for x in G["xs"]]
     y = G["y"].cuda()
     for rep in range(3):                       # rep 0: plan build + eager run; rep >= 2: CUDA-graph replay
@@ -70,6 +71,7 @@ def test_engine_train_dropout_matches_oracle():
     cfg = c["cfg"]
     _set(m, G, cfg)
     m.train()
+    m.engine().graph_after = 1
     for rep in range(3):                       # the third pass is a graph replay with fresh masks
         m.zero_grad()
         pred, _ = m(xs)
