@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MTB_ABI_VERSION 6
+#define MTB_ABI_VERSION 7
 #define MTB_MAX_GROUP 24
 
 /* Dropout RNG: Philox4x32-10.  Element `i` of a dropout site is kept iff
@@ -45,10 +45,14 @@ typedef struct {
 int mtb_abi_version(void);
 const char* mtb_last_error(void);
 int mtb_sm_count(void);
-/* which math engine mtb_linear_* and mtb_attn_* use: 0 = fp32 CUDA-core (parity mode, 1e-5),
- * 1 = tcgen05 TF32 tensor-core (TMA + TMEM GEMMs, tcgen05 flash attention).  Returns the previous mode. */
+/* which GEMM engine mtb_linear_* uses: 0 = fp32 CUDA-core (parity mode, 1e-5),
+ * 1 = tcgen05 TF32 tensor-core (TMA + TMEM).  Returns the previous mode. */
 int mtb_set_gemm_mode(int mode);
 int mtb_get_gemm_mode(void);
+/* which attention core mtb_attn_* uses: 0 = fp32 CUDA-core flash kernels (default: at head_dim 25
+ * the op is softmax-bound, not MMA-bound, and this kernel is the faster one), 1 = tcgen05 / TMEM
+ * flash kernels (TF32 QK^T and PV on the tensor core). */
+int mtb_set_attn_mode(int mode);
 /* number of kernels this library has launched so far in this process (bench bookkeeping) */
 uint64_t mtb_launch_count(void);
 

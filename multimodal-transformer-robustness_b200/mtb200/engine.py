@@ -616,7 +616,11 @@ def _run(ops, stream: int):
 class Engine:
     """Owns the arenas and the plan cache of one DynamicMULTModel on one device."""
 
-    def __init__(self, model, device, seed: int = 0, graph_after: int = 3):
+    def __init__(self, model, device, seed: int = 0, graph_after: int = -1):
+        # graph_after: capture a plan into CUDA graphs once it has been hit more than this many times
+        # (-1 = never).  Off by default: under `random_sample` almost every step draws a new
+        # sub-network, and a capture costs far more than the eager run of a cached plan; fixed-config
+        # workloads (test_single training, EA fitness evaluation) switch it on.
         self.model = model
         self.device = torch.device(device)
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -928,6 +932,7 @@ class Engine:
             return
         if self.graph_after >= 0 and plan.hits > self.graph_after and not torch.cuda.is_current_stream_capturing():
             try:
+                torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     _run(ops, torch.cuda.current_stream().cuda_stream)

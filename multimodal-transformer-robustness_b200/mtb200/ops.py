@@ -117,6 +117,12 @@ def set_gemm_mode(mode: str) -> str:
     return "tf32" if prev else "fp32"
 
 
+def set_attn_mode(mode: str) -> str:
+    """'simt' = fp32 CUDA-core flash attention (default), 'tc' = tcgen05 / TMEM flash attention (TF32)."""
+    prev = lib.mtb_set_attn_mode({"simt": 0, "tc": 1}[mode])
+    return "tc" if prev else "simt"
+
+
 def get_gemm_mode() -> str:
     return "tf32" if lib.mtb_get_gemm_mode() else "fp32"
 

@@ -78,7 +78,7 @@ def test_tc_encoder_matches_oracle_within_reduced_precision_tolerance(tf32):
     w = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in enc.state_dict().items()}
     enc = enc.cuda().eval()
     enc.set_active(2, E, H, hd)
-    x, xk = torch.randn(40, 4, E), torch.randn(130, 4, E)
+    x, xk = torch.randn(150, 8, E), torch.randn(260, 8, E)     # 1200 / 2080 tokens: realistic token counts
     xc, xkc = x.cuda().requires_grad_(True), xk.cuda().requires_grad_(True)
     out = enc(xc, xkc, xkc)
     R = torch.randn(out.shape)
@@ -157,6 +157,14 @@ def test_tc_attention_matches_oracle(tf32, Lq, Lk, B, H, hd, p):
     kernel's own Philox dropout masks replayed."""
     ops = tf32
     from test_gpu_parity import MaskFeed, _attn_ref
+    ops.set_attn_mode("tc")
+    try:
+        _tc_attention_case(ops, MaskFeed, _attn_ref, Lq, Lk, B, H, hd, p)
+    finally:
+        ops.set_attn_mode("simt")
+
+
+def _tc_attention_case(ops, MaskFeed, _attn_ref, Lq, Lk, B, H, hd, p):
     g = torch.Generator().manual_seed(Lq * 131 + Lk)
     D = H * hd
     q, k, v = (torch.randn(L * B, D, generator=g) for L in (Lq, Lk, Lk))
