@@ -224,6 +224,7 @@ def main():
         mode = "fp32"
     ops.set_gemm_mode(mode)
 
+    ops.preload()                                      # force-load every kernel (CUDA loads modules lazily)
     model = build_model().to(dev).train()              # identical init on every rank (same seed)
     hyp = make_hyp(args.seq)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)   # torch's fused multi-tensor Adam (optimizer is outside the hot path)
@@ -236,9 +237,14 @@ def main():
     resident = [([x.to(dev) for x in xs], y.to(dev)) for xs, y in host]
     h2d = sum(x.numel() * 4 for x in host[0][0]) + host[0][1].numel() * 4
 
+    dbg = os.environ.get("MTB_BENCH_DEBUG") == "1"
+
     def run(n, e2e):
         losses = []
         for it in range(n):
+            if dbg:
+                torch.cuda.synchronize()
+                t_dbg = time.perf_counter()
             if e2e:
                 xs_h, y_h = host[it % n_host]
                 xs = [x.to(dev, non_blocking=True) for x in xs_h]
@@ -248,6 +254,10 @@ def main():
             loss = train_step(model, opt, crit, xs, y, hyp, grad_sync=sync)
             if e2e:
                 losses.append(loss.item())             # device->host read of the step's result
+            if dbg:
+                torch.cuda.synchronize()
+                print(f"[dbg] e2e={e2e} it={it} {1e3 * (time.perf_counter() - t_dbg):.2f} ms cfg={model.active_modality} {model.active_cross_output}",
+                      file=sys.stderr, flush=True)
         return losses
 
     def timed(n, e2e):

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MTB_ABI_VERSION 7
+#define MTB_ABI_VERSION 8
 #define MTB_MAX_GROUP 24
 
 /* Dropout RNG: Philox4x32-10.  Element `i` of a dropout site is kept iff
@@ -53,6 +53,9 @@ int mtb_get_gemm_mode(void);
  * the op is softmax-bound, not MMA-bound, and this kernel is the faster one), 1 = tcgen05 / TMEM
  * flash kernels (TF32 QK^T and PV on the tensor core). */
 int mtb_set_attn_mode(int mode);
+/* force-load every kernel of the library into the current CUDA context (CUDA loads modules lazily;
+ * without this the first use of each kernel variant stalls a training step by milliseconds) */
+int mtb_preload(void);
 /* number of kernels this library has launched so far in this process (bench bookkeeping) */
 uint64_t mtb_launch_count(void);
 

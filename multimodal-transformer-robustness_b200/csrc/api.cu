@@ -37,6 +37,12 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st);
 int attn_fwd_simt(const mtb_attn_desc* d, int n, cudaStream_t st);
 int attn_bwd_simt(const mtb_attn_bwd_desc* d, int n, cudaStream_t st);
 int attn_fwd_tc(const mtb_attn_desc* d, int n, cudaStream_t st);
+int preload_elementwise();
+int preload_layernorm();
+int preload_linear_simt();
+int preload_linear_tc();
+int preload_attention_simt();
+int preload_attention_tc();
 int attn_bwd_tc(const mtb_attn_bwd_desc* d, int n, cudaStream_t st);
 
 }  // namespace mtb
@@ -52,6 +58,12 @@ int mtb_set_gemm_mode(int mode) {
   return prev;
 }
 int mtb_get_gemm_mode(void) { return mtb::g_gemm_mode; }
+int mtb_preload(void) {
+  const int bad = mtb::preload_elementwise() + mtb::preload_layernorm() + mtb::preload_linear_simt() + mtb::preload_linear_tc() +
+                  mtb::preload_attention_simt() + mtb::preload_attention_tc();
+  MTB_CHECK(bad == 0, "preload: %d kernels failed to load (%s)", bad, cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
 int mtb_set_attn_mode(int mode) {
   const int prev = mtb::g_attn_mode;
   mtb::g_attn_mode = mode ? 1 : 0;

@@ -439,3 +439,16 @@ int attn_bwd_simt(const mtb_attn_bwd_desc* d, int n, cudaStream_t st) {
 }
 
 }  // namespace mtb
+
+namespace mtb {
+int preload_attention_simt() {
+  int bad = 0;
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_fwd_kernel<32>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_fwd_kernel<64>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_bwd_dq_kernel<32>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_bwd_dq_kernel<64>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_bwd_dkv_kernel<32>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_bwd_dkv_kernel<64>) != cudaSuccess) ++bad; }
+  return bad;
+}
+}  // namespace mtb

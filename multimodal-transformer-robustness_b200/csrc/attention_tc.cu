@@ -616,3 +616,13 @@ int attn_bwd_tc(const mtb_attn_bwd_desc* d, int n, cudaStream_t st) {
 }
 
 }  // namespace mtb
+
+namespace mtb {
+int preload_attention_tc() {
+  int bad = 0;
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_fwd_tc_kernel) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_bwd_dq_tc_kernel) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_bwd_dkv_tc_kernel) != cudaSuccess) ++bad; }
+  return bad;
+}
+}  // namespace mtb

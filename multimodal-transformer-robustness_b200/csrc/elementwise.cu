@@ -164,6 +164,18 @@ __global__ void rng_advance_kernel(uint64_t* st, uint64_t delta) { st[1] += delt
 
 }  // namespace mtb
 
+namespace mtb {
+int preload_elementwise() {
+  int bad = 0;
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, embed_kernel<false>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, embed_kernel<true>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, addn_kernel) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, mask_kernel) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, rng_advance_kernel) != cudaSuccess) ++bad; }
+  return bad;
+}
+}  // namespace mtb
+
 extern "C" {
 int mtb_embed_fwd(const mtb_embed_desc* d, int n, void* stream) {
   return mtb::launch_embed<false>(d, n, (cudaStream_t)stream);

@@ -257,6 +257,21 @@ static bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 }  // namespace mtb
 
+namespace mtb {
+int preload_layernorm() {
+  int bad = 0;
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_fwd_kernel<2>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_fwd_kernel<8>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_fwd_generic) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_bwd_kernel<2, true>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_bwd_kernel<2, false>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_bwd_kernel<8, true>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_bwd_kernel<8, false>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_bwd_generic) != cudaSuccess) ++bad; }
+  return bad;
+}
+}  // namespace mtb
+
 extern "C" {
 
 int mtb_resln_fwd(const mtb_resln_desc* d, int n, void* stream) {

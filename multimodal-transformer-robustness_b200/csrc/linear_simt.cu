@@ -218,3 +218,11 @@ int linear_bwd_simt(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
 }
 
 }  // namespace mtb
+
+namespace mtb {
+int preload_linear_simt() {
+  int bad = 0;
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, gemm_simt_kernel) != cudaSuccess) ++bad; }
+  return bad;
+}
+}  // namespace mtb

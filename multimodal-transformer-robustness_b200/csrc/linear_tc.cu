@@ -546,3 +546,13 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
 }
 
 }  // namespace mtb
+
+namespace mtb {
+int preload_linear_tc() {
+  int bad = 0;
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, gemm_tc_kernel) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, actgrad_kernel) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, colsum_kernel) != cudaSuccess) ++bad; }
+  return bad;
+}
+}  // namespace mtb

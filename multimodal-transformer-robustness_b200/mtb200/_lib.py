@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmultb200.so")
 
 MAX_GROUP = 24
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class MtbError(RuntimeError):
@@ -99,6 +99,7 @@ SYMBOLS = {
     "mtb_get_gemm_mode": ([], C.c_int),
     "mtb_set_attn_mode": ([C.c_int], C.c_int),
     "mtb_launch_count": ([], C.c_uint64),
+    "mtb_preload": ([], C.c_int),
     "mtb_dropout_mask": ([Rng, C.c_float, C.c_int64, C.c_void_p, C.c_void_p], C.c_int),
     "mtb_rng_advance": ([C.c_void_p, C.c_uint64, C.c_void_p], C.c_int),
     "mtb_embed_fwd": ([C.POINTER(EmbedDesc), C.c_int, C.c_void_p], C.c_int),

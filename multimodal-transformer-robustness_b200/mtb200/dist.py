@@ -33,8 +33,11 @@ class GradSync:
         self.last_bytes = 0
 
     def buckets(self) -> List[List[torch.Tensor]]:
+        return self._buckets_of(self.params)
+
+    def _buckets_of(self, params) -> List[List[torch.Tensor]]:
         out, cur, size = [], [], 0
-        for p in self.params:
+        for p in params:
             if p.grad is None:
                 continue
             g = p.grad
@@ -47,9 +50,31 @@ class GradSync:
             out.append(cur)
         return out
 
-    def __call__(self):
+    def flat_ranges(self, engine):
+        """Plan-executor path: gradients are views of ONE flat arena, so the active set is a few
+        large contiguous ranges that are all-reduced in place (no flatten / unflatten copies)."""
         rank, n = world()
-        bks = self.buckets()
+        rs = engine.active_ranges()
+        self.last_active = len(engine.last_plan.active_params) if engine.last_plan else 0
+        self.last_bytes = sum(hi - lo for lo, hi in rs) * 4
+        if n == 1:
+            return
+        works = []
+        for lo, hi in rs:
+            t = engine.grad_arena[lo:hi]
+            t.div_(n)
+            works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for w in works:
+            w.wait()
+
+    def __call__(self, engine=None):
+        if engine is not None and engine.last_plan is not None and getattr(engine, "_grads_live", False):
+            extra = [p for p in engine.model._outside_engine_params() if p.grad is not None]
+            self.flat_ranges(engine)
+            if not extra:
+                return
+        rank, n = world()
+        bks = self.buckets() if engine is None else self._buckets_of(extra)
         self.last_active = sum(len(b) for b in bks)
         self.last_bytes = sum(g.numel() * g.element_size() for b in bks for g in b)
         if n == 1:

@@ -177,6 +177,26 @@ class DynamicMULTModel(nn.Module):
             self._engine = Engine(self, next(self.parameters()).device, seed=seed)
         return self._engine
 
+    def zero_grad(self, set_to_none: bool = True):
+        """Same semantics as nn.Module.zero_grad (grads -> None); when the plan executor produced
+        the gradients only the parameters that actually ran are visited."""
+        eng = self._engine
+        if set_to_none and eng is not None and eng.last_plan is not None and getattr(eng, "_grads_live", False):
+            for p in eng.last_plan.active_params:
+                p.grad = None
+            for p in self._outside_engine_params():
+                p.grad = None
+            eng._grads_live = False
+            return
+        super().zero_grad(set_to_none=set_to_none)
+
+    def _outside_engine_params(self):
+        ps = getattr(self, "_outside_cache", None)
+        if ps is None:
+            ps = [p for p in self.proj.parameters()]
+            self._outside_cache = ps
+        return ps
+
     def _engine_ok(self, x) -> bool:
         if not self.use_engine or self.all_steps or not x[0].is_cuda or self.d % 4 != 0:
             return False

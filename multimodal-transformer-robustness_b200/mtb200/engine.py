@@ -623,6 +623,9 @@ class Engine:
         # workloads (test_single training, EA fitness evaluation) switch it on.
         self.model = model
         self.device = torch.device(device)
+        from . import ops as _ops
+        with torch.cuda.device(self.device):
+            _ops.preload()
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.graph_after = graph_after
         self.plans: Dict[tuple, Plan] = {}
@@ -646,6 +649,40 @@ class Engine:
 
     def grad_ptr(self, p) -> int:
         return self.grad_arena.data_ptr() + F4 * self._grad_off[id(p)]
+
+    def active_ranges(self, max_gap: int = 1 << 18) -> List[Tuple[int, int]]:
+        """Element ranges [lo, hi) of the gradient arena covered by the parameters that ran in the
+        last backward, with small gaps merged (the gaps hold zeros).  Used by the flat
+        all-reduce / clip paths: a handful of large contiguous ranges instead of hundreds of tensors."""
+        plan = self.last_plan
+        if plan is None:
+            return []
+        spans = sorted((self._grad_off[id(p)], self._grad_off[id(p)] + p.numel()) for p in plan.active_params)
+        out: List[Tuple[int, int]] = []
+        for lo, hi in spans:
+            if out and lo - out[-1][1] <= max_gap:
+                out[-1] = (out[-1][0], max(out[-1][1], hi))
+            else:
+                out.append((lo, hi))
+        return out
+
+    def clip_grad_norm_(self, max_norm: float, extra: Sequence[torch.Tensor] = ()) -> torch.Tensor:
+        """torch.nn.utils.clip_grad_norm_ over the active set, computed on the flat arena (inactive
+        regions are exactly zero, so the norm over the merged ranges equals the norm over the
+        active parameters).  No host synchronisation."""
+        rs = self.active_ranges()
+        flats = [self.grad_arena[lo:hi] for lo, hi in rs] + [g.reshape(-1) for g in extra]   # extra: grads living outside the arena
+        if not flats:
+            return torch.zeros((), device=self.device)
+        sq = None
+        for t in flats:
+            v = torch.dot(t, t)
+            sq = v if sq is None else sq + v
+        total = sq.sqrt()
+        coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+        for t in flats:
+            t.mul_(coef)
+        return total
 
     def manual_seed(self, seed: int):
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -988,6 +1025,7 @@ class _EngineFn(torch.autograd.Function):
         for p in plan.active_params:
             g = eng.grad_views[id(p)]
             p.grad = g if p.grad is None else p.grad + g
+        eng._grads_live = True
         outs = []
         for i, shp in enumerate(ctx.shapes):
             ch = m.modality_list[i]

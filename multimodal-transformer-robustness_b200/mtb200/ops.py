@@ -111,6 +111,17 @@ def dropout_mask(seed: int, offset: int, p: float, n: int, device) -> Tensor:
     return out
 
 
+_preloaded = False
+
+
+def preload():
+    """Load every libmultb200 kernel into the current CUDA context (idempotent)."""
+    global _preloaded
+    if not _preloaded:
+        _lib.check(lib.mtb_preload(), "mtb_preload")
+        _preloaded = True
+
+
 def set_gemm_mode(mode: str) -> str:
     """'fp32' = CUDA-core parity engine, 'tf32' = tcgen05 tensor-core engine."""
     prev = lib.mtb_set_gemm_mode({"fp32": 0, "tf32": 1}[mode])

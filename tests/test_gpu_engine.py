@@ -173,3 +173,32 @@ def test_engine_random_sample_training_steps():
     assert all(math.isfinite(v) for v in losses)
     assert m.engine().stats["plans"] >= 5
     ops.set_gemm_mode("fp32")
+
+
+def test_flat_clip_equals_torch_clip():
+    """engine.clip_grad_norm_ (flat arena) == torch.nn.utils.clip_grad_norm_ over the same grads."""
+    from mtb200 import ops
+    ops.set_gemm_mode("fp32")
+    G = _golden()
+    m = _build(G, use_engine=True)
+    xs = [x.cuda() for x in G["xs"]]
+    cfg = G["cases"][0]["cfg"]
+    _set(m, G, cfg)
+    m.eval()
+    res = {}
+    for which in ("torch", "flat"):
+        m.zero_grad()
+        pred, _ = m(xs)
+        (pred.sum() * 50.0).backward()
+        if which == "torch":
+            n = torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+        else:
+            n = m.engine().clip_grad_norm_(1.0, [p.grad for p in m._outside_engine_params() if p.grad is not None])
+        res[which] = (float(n), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+    assert abs(res["torch"][0] - res["flat"][0]) / res["torch"][0] < 1e-5
+    assert res["torch"][1].keys() == res["flat"][1].keys()
+    for k in res["torch"][1]:
+        assert_rel(res["flat"][1][k], res["torch"][1][k], 1e-5, k)
+    # zero_grad fast path leaves every grad None
+    m.zero_grad()
+    assert all(p.grad is None for p in m.parameters())
