@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MTB_ABI_VERSION 8
+#define MTB_ABI_VERSION 9
 #define MTB_MAX_GROUP 24
 
 /* Dropout RNG: Philox4x32-10.  Element `i` of a dropout site is kept iff
@@ -113,7 +113,7 @@ int mtb_resln_fwd(const mtb_resln_desc* d, int n, void* stream);
  *   g    = d_xnew (may be NULL) + LayerNorm_backward(dy; x_new, mean, rstd, gamma[idx])
  *   d_res = g ;  d_a = g * keep/(1-p)   (d_a may be NULL)
  *   dgamma/dbeta (may be NULL: masked LayerNorm gets no gradient) are
- *   ACCUMULATED (+=) at [idx]. */
+ *   ACCUMULATED (+=) at [idx]; so is the optional dbias (column sums of d_a). */
 typedef struct {
   const float* dy;     int64_t ld_dy;
   const float* d_xnew; int64_t ld_dx;
@@ -125,6 +125,8 @@ typedef struct {
   float* dgamma; float* dbeta;
   int T, E;
   float p; mtb_rng rng;
+  float* dbias;    /* optional: dbias[idx[c]] += sum_t d_a[t, c] -- the bias gradient of the linear layer that
+                      produced `a` (out-projection / fc2), fused here so no separate column-sum pass is needed */
 } mtb_resln_bwd_desc;
 int mtb_resln_bwd(const mtb_resln_bwd_desc* d, int n, void* stream);
 

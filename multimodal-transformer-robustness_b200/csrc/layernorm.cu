@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(LN_THREADS) resln_fwd_generic(const __grid_con
 template <int MAXV, bool AFFINE_GRAD>
 __global__ void __launch_bounds__(LN_THREADS) resln_bwd_kernel(const __grid_constant__ Group<mtb_resln_bwd_desc> g,
                                                                int rows_per_cta) {
-  extern __shared__ float sred[];   // [2][E] when AFFINE_GRAD
+  extern __shared__ float sred[];   // [3][E] when AFFINE_GRAD: dgamma, dbeta, dbias partials
   int local;
   const int pi = find_problem(g, blockIdx.x, local);
   const mtb_resln_bwd_desc& d = g.d[pi];
@@ -134,11 +134,12 @@ __global__ void __launch_bounds__(LN_THREADS) resln_bwd_kernel(const __grid_cons
   const DropCtx dc = make_drop(d.rng, d.p);
   const bool has_ln = d.dy != nullptr;
   const bool agrad = AFFINE_GRAD && d.dgamma != nullptr && has_ln;
-  float4 dg[AFFINE_GRAD ? MAXV : 1], db[AFFINE_GRAD ? MAXV : 1];
+  const bool bgrad = AFFINE_GRAD && d.dbias != nullptr && d.d_a != nullptr;
+  float4 dg[AFFINE_GRAD ? MAXV : 1], db[AFFINE_GRAD ? MAXV : 1], dba[AFFINE_GRAD ? MAXV : 1];
   if (AFFINE_GRAD) {
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) { dg[i] = make_float4(0, 0, 0, 0); db[i] = make_float4(0, 0, 0, 0); }
-    for (int c = threadIdx.x; c < 2 * E; c += LN_THREADS) sred[c] = 0.f;
+    for (int i = 0; i < MAXV; ++i) { dg[i] = make_float4(0, 0, 0, 0); db[i] = make_float4(0, 0, 0, 0); dba[i] = make_float4(0, 0, 0, 0); }
+    for (int c = threadIdx.x; c < 3 * E; c += LN_THREADS) sred[c] = 0.f;
     __syncthreads();
   }
   const int row0 = local * rows_per_cta;
@@ -183,7 +184,9 @@ __global__ void __launch_bounds__(LN_THREADS) resln_bwd_kernel(const __grid_cons
         if (d.d_res) st4(d.d_res + (int64_t)t * d.ld_dres + c, gx);
         if (d.d_a) {
           const float4 k = keep4(dc, ((uint64_t)t * E + c) >> 2);
-          st4(d.d_a + (int64_t)t * d.ld_da + c, make_float4(gx.x * k.x, gx.y * k.y, gx.z * k.z, gx.w * k.w));
+          const float4 da = make_float4(gx.x * k.x, gx.y * k.y, gx.z * k.z, gx.w * k.w);
+          st4(d.d_a + (int64_t)t * d.ld_da + c, da);
+          if (AFFINE_GRAD && bgrad) { dba[i].x += da.x; dba[i].y += da.y; dba[i].z += da.z; dba[i].w += da.w; }
         }
       }
     }
@@ -202,12 +205,26 @@ __global__ void __launch_bounds__(LN_THREADS) resln_bwd_kernel(const __grid_cons
         }
       }
     }
+    if (bgrad) {
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nv) {
+          const int c = v << 2;
+          atomicAdd(&sred[2 * E + c], dba[i].x); atomicAdd(&sred[2 * E + c + 1], dba[i].y);
+          atomicAdd(&sred[2 * E + c + 2], dba[i].z); atomicAdd(&sred[2 * E + c + 3], dba[i].w);
+        }
+      }
+    }
     __syncthreads();
-    if (agrad) {
+    if (agrad || bgrad) {
       for (int c = threadIdx.x; c < E; c += LN_THREADS) {
         const int ic = d.idx ? d.idx[c] : c;
-        atomicAdd(&d.dgamma[ic], sred[c]);
-        if (d.dbeta) atomicAdd(&d.dbeta[ic], sred[E + c]);
+        if (agrad) {
+          atomicAdd(&d.dgamma[ic], sred[c]);
+          if (d.dbeta) atomicAdd(&d.dbeta[ic], sred[E + c]);
+        }
+        if (bgrad) atomicAdd(&d.dbias[ic], sred[2 * E + c]);
       }
     }
   }
@@ -249,6 +266,7 @@ __global__ void __launch_bounds__(LN_THREADS) resln_bwd_generic(const __grid_con
     if (d.d_a) {
       const float k = dc.on ? (drop_keep1(dc, (uint64_t)t * E + c) ? dc.inv_keep : 0.f) : 1.f;
       d.d_a[(int64_t)t * d.ld_da + c] = gx * k;
+      if (d.dbias) atomicAdd(&d.dbias[d.idx ? d.idx[c] : c], gx * k);
     }
   }
 }
@@ -316,7 +334,7 @@ int mtb_resln_bwd(const mtb_resln_bwd_desc* d, int n, void* stream) {
     MTB_CHECK(x.dy || x.d_xnew, "resln_bwd: problem %d has no incoming gradient", i);
     maxE = x.E > maxE ? x.E : maxE;
     maxT = x.T > maxT ? x.T : maxT;
-    affine = affine || (x.dgamma != nullptr);
+    affine = affine || (x.dgamma != nullptr) || (x.dbias != nullptr);
     vec = vec && (x.E % 4 == 0) && (!x.dy || (aligned16(x.dy) && x.ld_dy % 4 == 0 && aligned16(x.x_new) && x.ld_x % 4 == 0)) &&
           (!x.d_xnew || (aligned16(x.d_xnew) && x.ld_dx % 4 == 0)) && (!x.d_res || (aligned16(x.d_res) && x.ld_dres % 4 == 0)) &&
           (!x.d_a || (aligned16(x.d_a) && x.ld_da % 4 == 0)) && (!x.dy || x.idx || aligned16(x.gamma));
@@ -331,7 +349,7 @@ int mtb_resln_bwd(const mtb_resln_bwd_desc* d, int n, void* stream) {
     for (int i = 0; i < n; ++i) { g.d[i] = d[i]; g.start[i] = tot; tot += (d[i].T + rows - 1) / rows; }
     g.start[n] = tot;
     if (tot == 0) return 0;
-    const size_t smem = affine ? 2 * (size_t)maxE * sizeof(float) : 0;
+    const size_t smem = affine ? 3 * (size_t)maxE * sizeof(float) : 0;
     if (maxE <= 256) {
       if (affine) resln_bwd_kernel<2, true><<<tot, LN_THREADS, smem, st>>>(g, rows);
       else resln_bwd_kernel<2, false><<<tot, LN_THREADS, 0, st>>>(g, rows);

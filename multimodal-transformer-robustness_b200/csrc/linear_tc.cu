@@ -25,7 +25,7 @@ constexpr int TC_BI = 128;                 // UMMA M
 constexpr int TC_BR = 32;                  // reduction elements per stage (32 fp32 = one 128 B swizzle row)
 constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BI * 128;    // 16 KB
-constexpr int TC_SMEM_BUDGET = 110 * 1024; // <= half an SM's shared memory: two CTAs per SM overlap
+constexpr int TC_SMEM_BUDGET = 92 * 1024;  // <= half an SM's shared memory: two CTAs per SM overlap
                                            // one tile's epilogue with the other's main loop
 constexpr int TC_THREADS = 192;
 constexpr int TC_TMEM_COLS = 256;
@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
   __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float epi_tile[4][32 * 33];        // per-epilogue-warp transpose tile (padded: conflict free)
 
   int p = 0;
   while (p + 1 < g.n && (int)blockIdx.x >= g.start[p + 1]) ++p;
@@ -240,59 +241,70 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
       }
     } else {
       // ===== epilogue warps: TMEM lane quadrant = warp_id % 4 =====
+      // tcgen05.ld hands every thread one accumulator ROW; storing that directly would make each
+      // warp-wide store touch 32 different cache lines.  Each 32 x 32 chunk is therefore transposed
+      // through a padded shared-memory tile so that one store instruction writes 32 consecutive
+      // floats of a single row (fully coalesced 128 B), for plain, accumulate and atomic epilogues.
       const int q = warp & 3;
-      const int il = il0 + q * 32 + lane;                 // row inside its block
+      float* tp = &epi_tile[q][0];
+      const int il_w = il0 + q * 32;                      // first row of this warp inside the block
+      const int il = il_w + lane;
       const bool row_ok = il < P.i_len;
       const int64_t row_c = (int64_t)is * P.i_len + il;   // compact row (dropout index)
       mbar_wait(smem_u32(&tmem_full_bar), 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const DropCtx dc = make_drop(P.rng, P.p);
-      float* crow = P.C + ((int64_t)P.c_iseg[is] * P.i_len + il) * P.ldc + (int64_t)P.c_jseg[js] * P.j_len;
+      float* cbase = P.C + ((int64_t)P.c_iseg[is] * P.i_len + il_w) * P.ldc + (int64_t)P.c_jseg[js] * P.j_len;
       const float* brow = P.bias ? P.bias + (int64_t)P.bias_seg[js] * P.j_len : nullptr;
-      const bool vec_ok = ((P.ldc & 3) == 0) && ((((uintptr_t)P.C) & 15) == 0) && ((P.j_len & 3) == 0);
+      const int rows_here = min(32, P.i_len - il_w);      // warp-uniform; <= 0 when the whole warp is out of range
       for (int c0 = 0; c0 < P.BJ; c0 += 32) {
         if (jl0 + c0 >= P.j_len) break;                   // warp-uniform
         uint32_t v[32];
         tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        if (row_ok) {
+        if (rows_here <= 0) continue;
+        if (P.act == 1 && row_ok) {                       // bias + ReLU + dropout need the row-major view (Philox groups of 4 columns)
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
-            const int j = jl0 + c0 + c;                   // column inside its block
-            if (j >= P.j_len || c0 + c >= P.BJ) break;
+            const int j = jl0 + c0 + c;
             float o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               o[e] = __uint_as_float(v[c + e]);
               if (brow && j + e < P.j_len) o[e] += __ldg(brow + j + e);
+              o[e] = fmaxf(o[e], 0.f);
             }
-            if (P.act == 1) {
+            if (dc.on && j < P.j_len) {
+              const uint64_t idx = (uint64_t)row_c * (uint64_t)P.J + (uint64_t)((int64_t)js * P.j_len + j);
+              if ((idx & 3) == 0) {
+                const uint4 r = drop_rand4(dc, idx >> 2);
+                o[0] = r.x >= dc.thr ? o[0] * dc.inv_keep : 0.f; o[1] = r.y >= dc.thr ? o[1] * dc.inv_keep : 0.f;
+                o[2] = r.z >= dc.thr ? o[2] * dc.inv_keep : 0.f; o[3] = r.w >= dc.thr ? o[3] * dc.inv_keep : 0.f;
+              } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
-              if (dc.on) {
-                const uint64_t idx = (uint64_t)row_c * (uint64_t)P.J + (uint64_t)((int64_t)js * P.j_len + j);
-                if ((idx & 3) == 0) {
-                  const uint4 r = drop_rand4(dc, idx >> 2);
-                  o[0] = r.x >= dc.thr ? o[0] * dc.inv_keep : 0.f; o[1] = r.y >= dc.thr ? o[1] * dc.inv_keep : 0.f;
-                  o[2] = r.z >= dc.thr ? o[2] * dc.inv_keep : 0.f; o[3] = r.w >= dc.thr ? o[3] * dc.inv_keep : 0.f;
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) o[e] = drop_keep1(dc, idx + e) ? o[e] * dc.inv_keep : 0.f;
-                }
+                for (int e = 0; e < 4; ++e) o[e] = drop_keep1(dc, idx + e) ? o[e] * dc.inv_keep : 0.f;
               }
             }
-            if (P.epi == 0 && vec_ok && j + 3 < P.j_len) {
-              *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
-            } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (j + e >= P.j_len) break;
-                if (P.epi == 0) crow[j + e] = o[e];
-                else if (P.epi == 1) crow[j + e] += o[e];
-                else atomicAdd(crow + j + e, o[e]);
-              }
-            }
+            for (int e = 0; e < 4; ++e) v[c + e] = __float_as_uint(o[e]);
           }
         }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) tp[lane * 33 + c] = __uint_as_float(v[c]);   // bank (lane + c) % 32: conflict free
+        __syncwarp();
+        const int j = jl0 + c0 + lane;                    // my column in the transposed view
+        const bool col_ok = (j < P.j_len) && (c0 + lane < P.BJ);
+        const float bj = (P.act != 1 && brow && col_ok) ? __ldg(brow + j) : 0.f;
+        if (col_ok) {
+          float* cp = cbase + j;
+#pragma unroll 4
+          for (int r = 0; r < rows_here; ++r) {
+            const float val = tp[r * 33 + lane] + bj;
+            if (P.epi == 0) cp[(int64_t)r * P.ldc] = val;
+            else if (P.epi == 1) cp[(int64_t)r * P.ldc] += val;
+            else atomicAdd(cp + (int64_t)r * P.ldc, val);
+          }
+        }
+        __syncwarp();
       }
     }
   }
@@ -304,14 +316,26 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------ small helpers (backward)
-// scratch = dY * [Y > 0] * inv_keep      (ReLU + dropout backward applied once, feeds dgrad and wgrad)
-__global__ void actgrad_kernel(const float* __restrict__ dY, int64_t ldy, const float* __restrict__ Y, int64_t ldyy,
-                               float* __restrict__ out, int M, int N, float inv_keep) {
-  const int64_t total = (int64_t)M * N;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = e / N;
-    const int n = (int)(e - m * N);
-    out[e] = Y[m * ldyy + n] > 0.f ? dY[m * ldy + n] * inv_keep : 0.f;
+// scratch = dY * [Y > 0] * inv_keep  (ReLU + dropout backward applied once, feeds dgrad and wgrad) and, fused,
+// db[phys(n)] += sum_m scratch[m, n]: one thread per column, 64 rows per block, coalesced along n.
+struct ActgradArgs {
+  const float* dY; int64_t ldy; const float* Y; int64_t ldyy; float* out; float* db;
+  int M, N, seg_len; float inv_keep; uint8_t seg[TC_MAXSEG];
+};
+__global__ void __launch_bounds__(128) actgrad_kernel(const ActgradArgs a) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m0 = blockIdx.y * 64, m1 = min(a.M, m0 + 64);
+  if (n >= a.N) return;
+  float s = 0.f;
+#pragma unroll 4
+  for (int m = m0; m < m1; ++m) {
+    const float v = a.Y[(int64_t)m * a.ldyy + n] > 0.f ? a.dY[(int64_t)m * a.ldy + n] * a.inv_keep : 0.f;
+    a.out[(int64_t)m * a.N + n] = v;
+    s += v;
+  }
+  if (a.db) {
+    const int sgi = n / a.seg_len;
+    atomicAdd(a.db + (int64_t)a.seg[sgi] * a.seg_len + (n - sgi * a.seg_len), s);
   }
 }
 // db[phys(n)] += sum_m dY[m, n]; one thread per column, 64 rows per block, 8 independent loads in flight
@@ -517,17 +541,19 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
       qw.splits = s;
     }
     if (!built) { rest[nrest++] = x; continue; }
-    if (x.act == 1) {       // dY' = dY * [Y > 0] / (1 - p), materialised once for dgrad + wgrad + bias grad
-      const float inv_keep = x.p > 0.f ? 1.f / (1.f - x.p) : 1.f;
-      const int64_t total = (int64_t)x.M * x.N;
-      const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-      actgrad_kernel<<<blocks, 256, 0, st>>>(x.dY, x.ldy, x.Yact, x.ldyact, x.scratch, x.M, x.N, inv_keep);
+    if (x.act == 1) {       // dY' = dY * [Y > 0] / (1 - p), materialised once for dgrad + wgrad; bias grad fused
+      ActgradArgs aa{};
+      aa.dY = x.dY; aa.ldy = x.ldy; aa.Y = x.Yact; aa.ldyy = x.ldyact; aa.out = x.scratch; aa.db = x.db;
+      aa.M = x.M; aa.N = x.N; aa.seg_len = an.len; aa.inv_keep = x.p > 0.f ? 1.f / (1.f - x.p) : 1.f;
+      for (int s2 = 0; s2 < TC_MAXSEG; ++s2) aa.seg[s2] = s2 < an.n ? an.phys[s2] : 0;
+      dim3 grid((x.N + 127) / 128, (x.M + 63) / 64);
+      actgrad_kernel<<<grid, 128, 0, st>>>(aa);
       mtb::note_launch();
       MTB_CUDA(cudaGetLastError());
     }
     if (x.dX) dg[ndg++] = qd;
     if (x.dW) wg[nwg++] = qw;
-    if (x.db) {
+    if (x.db && x.act != 1) {
       ColsumArgs ca{};
       ca.dY = dYp; ca.ldy = ldyp; ca.db = x.db; ca.M = x.M; ca.N = x.N; ca.seg_len = an.len;
       for (int s = 0; s < TC_MAXSEG; ++s) ca.seg[s] = s < an.n ? an.phys[s] : 0;

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmultb200.so")
 
 MAX_GROUP = 24
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class MtbError(RuntimeError):
@@ -55,7 +55,7 @@ class ResLnBwdDesc(C.Structure):
                 ("gamma", C.c_void_p), ("idx", C.c_void_p),
                 ("d_res", C.c_void_p), ("ld_dres", C.c_int64), ("d_a", C.c_void_p), ("ld_da", C.c_int64),
                 ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("T", C.c_int), ("E", C.c_int),
-                ("p", C.c_float), ("rng", Rng)]
+                ("p", C.c_float), ("rng", Rng), ("dbias", C.c_void_p)]
 
 
 class LinearDesc(C.Structure):

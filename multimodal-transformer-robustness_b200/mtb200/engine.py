@@ -398,7 +398,7 @@ class PlanBuilder:
                                           S["st2"][0], S["st2"][1], ln.weight.data_ptr(), e.mask.idx.data_ptr() if masked else None,
                                           g_x1r.ptr, g_x1r.ld, g_y.ptr, g_y.ld,
                                           None if masked else self.grad_ptr(ln.weight), None if masked else self.grad_ptr(ln.bias),
-                                          Tq, e.E, pr, r))
+                                          Tq, e.E, pr, r, self.grad_ptr(e.enc.layers[i].fc2.l.bias)))      # fc2 bias grad = colsum(g_y), fused
             self.emit(self.bwd, lib.mtb_resln_bwd, ResLnBwdDesc, descs, f"res_ln2_bwd[{i}]")
             # g'. fc2 backward, f'. fc1 backward
             d2, d1 = [], []
@@ -412,7 +412,7 @@ class PlanBuilder:
                 scratch = A.alloc(Tq * Fa)
                 S["g_xn1"] = g_xn1
                 d2.append(LinearBwdDesc(S["g_y"].ptr, S["g_y"].ld, None, 0, S["h"].ptr, S["h"].ld, W2.data_ptr(), W2.stride(0), midx, None,
-                                        g_h.ptr, g_h.ld, 0, self.grad_ptr(W2), self.grad_ptr(b2), Tq, e.E, Fa, 0, 0.0, None,
+                                        g_h.ptr, g_h.ld, 0, self.grad_ptr(W2), None, Tq, e.E, Fa, 0, 0.0, None,
                                         _segs(e.mask), Segs(0, 0)))
                 d1.append(LinearBwdDesc(g_h.ptr, g_h.ld, S["h"].ptr, S["h"].ld, S["xn1"].ptr, S["xn1"].ld, W1.data_ptr(), W1.stride(0), None, midx,
                                         g_xn1.ptr, g_xn1.ld, 0, self.grad_ptr(W1), self.grad_ptr(b1), Tq, Fa, e.E, 1, S["p_relu"], scratch,
@@ -435,7 +435,7 @@ class PlanBuilder:
                                           S["st1"][0], S["st1"][1], ln.weight.data_ptr(), e.mask.idx.data_ptr() if masked else None,
                                           g_xr.ptr, g_xr.ld, g_a.ptr, g_a.ld,
                                           None if masked else self.grad_ptr(ln.weight), None if masked else self.grad_ptr(ln.bias),
-                                          Tq, e.E, pr, r))
+                                          Tq, e.E, pr, r, self.grad_ptr(layer.self_attn.out_proj.bias)))   # out-proj bias grad, fused
             self.emit(self.bwd, lib.mtb_resln_bwd, ResLnBwdDesc, descs, f"res_ln1_bwd[{i}]")
             # d'. out-projection backward
             descs = []
@@ -449,7 +449,7 @@ class PlanBuilder:
                 g_o = A.mat(Tq, D)
                 S["g_o"] = g_o
                 descs.append(LinearBwdDesc(S["g_a"].ptr, S["g_a"].ld, None, 0, S["o"].ptr, S["o"].ld, Wo.data_ptr(), Wo.stride(0), ridx, None,
-                                           g_o.ptr, g_o.ld, 0, self.grad_ptr(Wo), self.grad_ptr(bo), Tq, e.E, D, 0, 0.0, None,
+                                           g_o.ptr, g_o.ld, 0, self.grad_ptr(Wo), None, Tq, e.E, D, 0, 0.0, None,
                                            _segs(e.mask), Segs(0, 0)))
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, descs, f"out_proj_bwd[{i}]")
             # c'. attention backward
@@ -517,7 +517,7 @@ class PlanBuilder:
                     gy = S["g_" + nm + "n"]
                     descs.append(ResLnBwdDesc(gy.ptr, gy.ld, None if first else acc.ptr, 0 if first else acc.ld, e.saved["x" + nm].ptr, e.E,
                                               st[0], st[1], ln.weight.data_ptr(), None, acc.ptr, acc.ld, None, 0,
-                                              self.grad_ptr(ln.weight), self.grad_ptr(ln.bias), Tk, e.E, 0.0, none_rng))
+                                              self.grad_ptr(ln.weight), self.grad_ptr(ln.bias), Tk, e.E, 0.0, none_rng, None))
             self.emit(self.bwd, lib.mtb_resln_bwd, ResLnBwdDesc, descs, f"ln0_kv_bwd[{i}]")
         # first LayerNorm backward -> g_x0
         descs = []
@@ -531,7 +531,7 @@ class PlanBuilder:
             descs.append(ResLnBwdDesc(gxn.ptr, gxn.ld, gx.ptr if gx else None, gx.ld if gx else 0, e.saved["x0"].ptr, e.E, st[0], st[1],
                                       ln.weight.data_ptr(), e.mask.idx.data_ptr() if masked else None, g_x0.ptr, g_x0.ld, None, 0,
                                       None if masked else self.grad_ptr(ln.weight), None if masked else self.grad_ptr(ln.bias),
-                                      Tq, e.E, 0.0, none_rng))
+                                      Tq, e.E, 0.0, none_rng, None))
         self.emit(self.bwd, lib.mtb_resln_bwd, ResLnBwdDesc, descs, "ln_first_bwd")
         # embed backward -> gradients wrt the encoder inputs (contiguous [L, B, E])
         descs = []

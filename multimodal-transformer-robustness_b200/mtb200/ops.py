@@ -226,7 +226,7 @@ class _ResLn(torch.autograd.Function):
                          _p(d_xnew), d_xnew.stride(0) if d_xnew is not None else 0,
                          _p(xs) if use_ln else None, xs.stride(0) if use_ln else 0, _p(mean) if use_ln else None,
                          _p(rstd) if use_ln else None, _p(gamma) if use_ln else None, _p(idx) if use_ln else None,
-                         _p(d_res), E, _p(d_a), E, _p(dgamma), _p(dbeta), T, E, p, _rng_struct(seed, off))
+                         _p(d_res), E, _p(d_a), E, _p(dgamma), _p(dbeta), T, E, p, _rng_struct(seed, off), None)
         call_group(lib.mtb_resln_bwd, ResLnBwdDesc, [d], _stream(), "mtb_resln_bwd")
         return (d_res if has_res else None, d_a, dgamma, dbeta, None, None, None, None, None)
 
