@@ -437,7 +437,7 @@ static bool g_attr_done = false;
 static int launch_tc(const TcProblem* probs, int n, cudaStream_t st) {
   if (n == 0) return 0;
   if (!g_attr_done) {
-    MTB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048));
+    MTB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (TC_A_BYTES + 256 * 128) + 2048));
     g_attr_done = true;
   }
   TcGroup g;

@@ -219,26 +219,41 @@ class DynamicMULTModel(nn.Module):
                 px.append(x[i].new_empty((x[i].shape[1], x[i].shape[0], 0)))
         return self.engine().forward(px), []
 
-    def forward(self, x):
-        """x: list of per-modality inputs.  Returns (prediction, []) like the reference (:222-291)."""
+    def forward(self, x, branch_cache: dict = None):
+        """x: list of per-modality inputs.  Returns (prediction, []) like the reference (:222-291).
+        ``branch_cache`` (inference only): dict reused across calls on the SAME inputs and weights;
+        outputs of `mems0` stacks and cross-modal branches are memoised by name, so evaluating many
+        candidate sub-networks (EA.py fitness) only recomputes the per-candidate `mems` stacks + head."""
         assert len(x) == self.modality_num
-        if self._engine_ok(x):
+        if branch_cache is not None:
+            assert not self.training and not torch.is_grad_enabled(), "branch_cache is for no-grad evaluation"
+        elif self._engine_ok(x):
             return self._forward_engine(x)
         need = self._needed_modalities() if self.prune_dead_branches else set(self.modality_list)
         dev = next(self.parameters()).device
         h_ = {}
+        memo = branch_cache if branch_cache is not None else None
+
+        def cached(key, fn):
+            if memo is None:
+                return fn()
+            if key not in memo:
+                memo[key] = fn()
+            return memo[key]
         for i, ch in enumerate(self.modality_list):
             if ch in need:
-                px = self.proj[i](x[i]).permute(2, 0, 1)          # [L, B, d] view
-                h_[ch] = self.trans_mems0['mems0' + ch](px)
+                enc0 = self.trans_mems0['mems0' + ch]
+                h_[ch] = cached(("mems0", ch, enc0.active_layer_num),
+                                lambda i=i, enc0=enc0: enc0(self.proj[i](x[i]).permute(2, 0, 1)))
         last_hs, hs, out_index = [], [], []
         d = self.d
         for i in self.active_modality:
             if self.active_cross_output[i] == []:
                 continue
             for name in self.active_cross[i]:
-                src = h_[name[:-1]]
-                h_[name] = self.trans['cross' + name](h_[name[-1]], src, src)
+                encx = self.trans['cross' + name]
+                h_[name] = cached(("cross", name, encx.active_layer_num),
+                                  lambda name=name, encx=encx: encx(h_[name[-1]], h_[name[:-1]], h_[name[:-1]]))
             h = torch.cat([h_[name] for name in self.active_cross_output[i]], dim=2)
             slot = len(self.modality_index_list[i])
             mask = []

@@ -249,11 +249,52 @@ def gen_sampler(m):
                os.path.join(OUT, "sampler.pt"))
 
 
+# ----------------------------------------------------------------------------- 6. EA search trace
+def gen_ea(m):
+    """Run the reference's EvolutionSearch.search (class source exec'd from EA.py up to its CLI block,
+    which needs datasets) with a deterministic stand-in fitness.  The stand-in keeps the one RNG side
+    effect of the real eval_model: creating a DataLoader iterator (EA.py:157)."""
+    import random
+    import types
+    import numpy as np
+    from torch.utils.data import DataLoader, TensorDataset
+    ref_root = ref_shims.find_reference()
+    src = open(os.path.join(ref_root, "EA.py")).read().split("import sys\nimport torch\nimport argparse")[0]
+    ns = {}
+    exec(compile(src, "EA_class", "exec"), ns)
+    Ref = ns["EvolutionSearch"]
+    loader = DataLoader(TensorDataset(torch.zeros(4, 1)), batch_size=4, shuffle=False)
+    trace = []
+
+    def fitness(sample):
+        key = repr(sample)
+        return (sum(ord(c) * (i % 7 + 1) for i, c in enumerate(key)) % 1000) / 1000.0
+
+    class Traced(Ref):
+        def get_acc(self, sample):
+            iter(loader)                       # same global-generator draw as the real evaluation
+            trace.append(copy.deepcopy(sample))
+            return fitness(sample)
+
+        def eval_model(self, test=False):
+            return 0.0
+    import copy
+    hp = types.SimpleNamespace(mutate_prob=0.5, population_size=12, max_time_budget=4, parent_ratio=0.5, mutation_ratio=0.5,
+                               subnet_prob=0.5, active_modality=[0, 1, 2], criterion=None, modality_list=["l", "a", "v"])
+    torch.manual_seed(1111); random.seed(1111); np.random.seed(1111)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        best_valids, best_info = Traced(m, hp, loader, loader).search()
+    torch.save(dict(hp=vars(hp), trace=trace, best_valids=best_valids, best_info=best_info),
+               os.path.join(OUT, "ea_trace.pt"))
+
+
 if __name__ == "__main__":
     gen_pe_mask()
     gen_attention()
     gen_encoder()
     mm = gen_model()
     gen_sampler(mm)
+    gen_ea(mm)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -103,3 +103,36 @@ def test_encoder_constructor_rng_order(golden):
     for k, v in G["ctor"]["weights"].items():
         assert torch.equal(enc.state_dict()[k], v), k
     assert torch.equal(after, G["ctor"]["after"])
+
+
+def _fake_fitness(sample):
+    key = repr(sample)
+    return (sum(ord(c) * (i % 7 + 1) for i, c in enumerate(key)) % 1000) / 1000.0
+
+
+def test_ea_search_visits_the_reference_candidates(golden):
+    """mtb200.ea.EvolutionSearch under the same three seeds evaluates exactly the candidates the
+    reference's EA.py search evaluates (recorded trace), in the same order, and returns the same best."""
+    import random
+    import types
+    import numpy as np
+    from mtb200.ea import EvolutionSearch
+    G = golden("ea_trace.pt")
+    m = _small_model()
+    hp = types.SimpleNamespace(**G["hp"])
+    seen = []
+
+    class Fake(EvolutionSearch):
+        def get_acc(self, sample):
+            seen.append([[list(x) for x in sample[0]], [list(x) for x in sample[1]]])
+            return _fake_fitness(sample)
+
+        def score_many(self, samples):
+            return [self.get_acc(s) for s in samples]
+    torch.manual_seed(1111); random.seed(1111); np.random.seed(1111)
+    best_valids, best_info = Fake(m, hp, [], []).search()
+    ref = [[[list(x) for x in s[0]], [list(x) for x in s[1]]] for s in G["trace"]]
+    assert len(seen) == len(ref)
+    assert seen == ref
+    assert best_valids == G["best_valids"]
+    assert best_info[0] == G["best_info"][0]

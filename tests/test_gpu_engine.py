@@ -202,3 +202,25 @@ def test_flat_clip_equals_torch_clip():
     # zero_grad fast path leaves every grad None
     m.zero_grad()
     assert all(p.grad is None for p in m.parameters())
+
+
+def test_ea_branch_memoisation_is_results_identical():
+    """EA fitness evaluation with memoised mems0 / cross-branch outputs == plain evaluation."""
+    import types
+    from mtb200 import ops
+    from mtb200.ea import EvolutionSearch
+    ops.set_gemm_mode("fp32")
+    G = _golden()
+    m = _build(G, use_engine=False).eval()
+    xs = [x.cuda() for x in G["xs"]]
+    y = G["y"].cuda()
+    hp = types.SimpleNamespace(mutate_prob=0.5, population_size=6, max_time_budget=2, parent_ratio=0.5, mutation_ratio=0.5,
+                               active_modality=[0, 1, 2])
+    torch.manual_seed(7)
+    cands = [list(m.gen_active_cross([0, 1, 2])) for _ in range(6)]
+    preds = {}
+    for memo in (False, True):
+        ea = EvolutionSearch(m, hp, [(xs, y)], memoize=memo, metric=lambda r, t: float(r.sum()))
+        preds[memo] = [ea.get_acc(c) for c in cands]
+    for a, b in zip(preds[False], preds[True]):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(a)), (a, b)
