@@ -166,6 +166,14 @@ class DynamicMULTModel(nn.Module):
                 need.update(name)
         return need
 
+    def __getstate__(self):
+        """whole-object pickling (src/train.py:508-511 does torch.save(model)): the plan executor holds raw
+        device pointers and is rebuilt lazily after loading"""
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        state.pop("_outside_cache", None)
+        return state
+
     # ------------------------------------------------------------------ plan-executor path
     def reset_engine(self):
         self._engine = None

@@ -77,7 +77,8 @@ def install(ref_root: str | None = None, use_product_modules: bool = False) -> s
     else:
         sys.path.insert(0, ref_root)
     # src is a namespace package upstream (no __init__.py); stub the two broken members
-    _stub("src.dataset")
+    _stub("src.dataset", **{n: object for n in ("MOSEI_Datasets", "avMNIST_Datasets", "GentlePush_Datasets",
+                                                 "Enrico_Datasets", "EEG2a_Datasets")})
     _stub("src.models")
     return ref_root
 
