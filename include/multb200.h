@@ -29,7 +29,7 @@ extern "C" {
 #define MTB_ABI_VERSION 9
 #define MTB_MAX_GROUP 24
 
-/* Dropout RNG: Philox4x32-10.  Element `i` of a dropout site is kept iff
+/* Dropout RNG: Philox4x32-7.  Element `i` of a dropout site is kept iff
  * philox(key = seed, counter = offset + i/4)[i % 4] >= (uint32)(p * 2^32).
  * If `dev` is non-null it points to two device uint64 {seed_add, offset_add} that are
  * added to seed/offset at run time (lets a captured CUDA graph draw fresh masks on every
@@ -49,9 +49,8 @@ int mtb_sm_count(void);
  * 1 = tcgen05 TF32 tensor-core (TMA + TMEM).  Returns the previous mode. */
 int mtb_set_gemm_mode(int mode);
 int mtb_get_gemm_mode(void);
-/* which attention core mtb_attn_* uses: 0 = fp32 CUDA-core flash kernels (default: at head_dim 25
- * the op is softmax-bound, not MMA-bound, and this kernel is the faster one), 1 = tcgen05 / TMEM
- * flash kernels (TF32 QK^T and PV on the tensor core). */
+/* which attention core mtb_attn_* uses: 0 = fp32 CUDA-core flash kernels, 1 = tcgen05 / TMEM flash
+ * kernels (TF32 QK^T, PV, dP, dQ, dK, dV on the tensor core), -1 (default) = follow the GEMM engine. */
 int mtb_set_attn_mode(int mode);
 /* force-load every kernel of the library into the current CUDA context (CUDA loads modules lazily;
  * without this the first use of each kernel variant stalls a training step by milliseconds) */

@@ -7,7 +7,7 @@ namespace mtb {
 
 static thread_local char g_err[512] = "";
 int g_gemm_mode = 0;
-int g_attn_mode = 0;
+int g_attn_mode = -1;   // -1 = follow the GEMM engine (tensor-core attention in tensor-core mode)
 static unsigned long long g_launches = 0;
 void note_launch() { ++g_launches; }
 unsigned long long launches() { return g_launches; }
@@ -66,7 +66,7 @@ int mtb_preload(void) {
 }
 int mtb_set_attn_mode(int mode) {
   const int prev = mtb::g_attn_mode;
-  mtb::g_attn_mode = mode ? 1 : 0;
+  mtb::g_attn_mode = mode < 0 ? -1 : (mode ? 1 : 0);
   return prev;
 }
 uint64_t mtb_launch_count(void) { return mtb::launches(); }
@@ -99,7 +99,7 @@ int mtb_attn_fwd(const mtb_attn_desc* d, int n, void* stream) {
   for (int i = 0; i < n; ++i)
     MTB_CHECK(d[i].q && d[i].k && d[i].v && d[i].o && d[i].Lq > 0 && d[i].Lk > 0 && d[i].hd > 0,
               "attn_fwd: bad problem %d", i);
-  if (mtb::g_attn_mode == 1) return mtb::attn_fwd_tc(d, n, (cudaStream_t)stream);
+  if (mtb::g_attn_mode == 1 || (mtb::g_attn_mode < 0 && mtb::g_gemm_mode == 1)) return mtb::attn_fwd_tc(d, n, (cudaStream_t)stream);
   return mtb::attn_fwd_simt(d, n, (cudaStream_t)stream);
 }
 
@@ -108,7 +108,7 @@ int mtb_attn_bwd(const mtb_attn_bwd_desc* d, int n, void* stream) {
   for (int i = 0; i < n; ++i)
     MTB_CHECK(d[i].q && d[i].k && d[i].v && d[i].o && d[i].d_o && d[i].lse && d[i].delta && d[i].dq && d[i].dk && d[i].dv,
               "attn_bwd: null operand in problem %d", i);
-  if (mtb::g_attn_mode == 1) return mtb::attn_bwd_tc(d, n, (cudaStream_t)stream);
+  if (mtb::g_attn_mode == 1 || (mtb::g_attn_mode < 0 && mtb::g_gemm_mode == 1)) return mtb::attn_bwd_tc(d, n, (cudaStream_t)stream);
   return mtb::attn_bwd_simt(d, n, (cudaStream_t)stream);
 }
 

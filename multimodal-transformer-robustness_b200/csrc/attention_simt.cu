@@ -8,6 +8,11 @@
 
 namespace mtb {
 
+extern int g_gemm_mode;
+// exp in the softmax: accurate expf in fp32 parity mode, ex2.approx-based __expf when the run is in
+// reduced-precision (tensor-core) mode anyway
+template <bool FAST> __device__ __forceinline__ float attn_exp(float x) { return FAST ? __expf(x) : expf(x); }
+
 constexpr int AT = 64;          // q-tile and k-tile edge
 constexpr int AP = AT + 4;      // padded smem row (floats), keeps float4 alignment
 constexpr int A_THREADS = 256;
@@ -59,24 +64,34 @@ __device__ __forceinline__ void mini_pv(const float* __restrict__ P, const float
 template <int HDP>
 __device__ __forceinline__ void load_tile_T(float* T, const float* base, int64_t ld, int B, int b, int h, int hd,
                                             int l0, int L) {
+  // 4-byte cp.async with zero-fill: every copy of the tile is in flight at once (one L2 latency per
+  // tile) instead of a dependent load -> store chain per element; completed by tile_wait()
+  const uint32_t tb = (uint32_t)__cvta_generic_to_shared(T);
   for (int e = threadIdx.x; e < AT * HDP; e += A_THREADS) {
     const int r = e / HDP, dd = e - r * HDP;
-    float v = 0.f;
     const int l = l0 + r;
-    if (l < L && dd < hd) v = base[((int64_t)l * B + b) * ld + h * hd + dd];
-    T[dd * AP + r] = v;
+    const bool ok = (l < L) && (dd < hd);
+    const float* src = ok ? base + ((int64_t)l * B + b) * ld + h * hd + dd : base;
+    const int nbytes = ok ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(tb + (uint32_t)(dd * AP + r) * 4u), "l"(src), "r"(nbytes) : "memory");
   }
+}
+__device__ __forceinline__ void tile_wait() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 // -> natural tile N[l - l0][d] (zero padded), row stride HDP+2
 template <int HDP>
 __device__ __forceinline__ void load_tile_N(float* N, const float* base, int64_t ld, int B, int b, int h, int hd,
                                             int l0, int L) {
+  const uint32_t tb = (uint32_t)__cvta_generic_to_shared(N);
   for (int e = threadIdx.x; e < AT * HDP; e += A_THREADS) {
     const int r = e / HDP, dd = e - r * HDP;
-    float v = 0.f;
     const int l = l0 + r;
-    if (l < L && dd < hd) v = base[((int64_t)l * B + b) * ld + h * hd + dd];
-    N[r * (HDP + 2) + dd] = v;
+    const bool ok = (l < L) && (dd < hd);
+    const float* src = ok ? base + ((int64_t)l * B + b) * ld + h * hd + dd : base;
+    const int nbytes = ok ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(tb + (uint32_t)(r * (HDP + 2) + dd) * 4u), "l"(src), "r"(nbytes) : "memory");
   }
 }
 
@@ -94,7 +109,7 @@ __device__ __forceinline__ void attn_keep4(const DropCtx& dc, int64_t bh, int Lq
 }
 
 // ------------------------------------------------------------------------------ forward
-template <int HDP>
+template <int HDP, bool FAST>
 __global__ void __launch_bounds__(A_THREADS) attn_fwd_kernel(const __grid_constant__ Group<mtb_attn_desc> g) {
   extern __shared__ __align__(16) float smem[];
   float* Qt = smem;                    // [HDP][AP]
@@ -128,6 +143,7 @@ __global__ void __launch_bounds__(A_THREADS) attn_fwd_kernel(const __grid_consta
     __syncthreads();                                   // previous tile's Ps / Vn / Kt consumed
     load_tile_T<HDP>(Kt, d.k, d.ldk, d.B, b, h, d.hd, j0, d.Lk);
     load_tile_N<HDP>(Vn, d.v, d.ldv, d.B, b, h, d.hd, j0, d.Lk);
+    tile_wait();
     __syncthreads();
     float s[4][4];
 #pragma unroll
@@ -149,13 +165,13 @@ __global__ void __launch_bounds__(A_THREADS) attn_fwd_kernel(const __grid_consta
 #pragma unroll
       for (int sh = 8; sh > 0; sh >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sh));
       const float m_new = fmaxf(m[u], mx);
-      const float corr = (m_new == -CUDART_INF_F) ? 1.f : expf(m[u] - m_new);
+      const float corr = (m_new == -CUDART_INF_F) ? 1.f : attn_exp<FAST>(m[u] - m_new);
       float keep[4];
       attn_keep4(dc, bh, d.Lq, Lk4, min(i, d.Lq - 1), j0 + tx * 4, keep);
       float rs = 0.f, pk[4];
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        const float p = (s[u][v] == -CUDART_INF_F) ? 0.f : expf(s[u][v] - m_new);
+        const float p = (s[u][v] == -CUDART_INF_F) ? 0.f : attn_exp<FAST>(s[u][v] - m_new);
         rs += p;
         pk[v] = p * keep[v];
       }
@@ -186,7 +202,7 @@ __global__ void __launch_bounds__(A_THREADS) attn_fwd_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------ backward: dQ (+ delta)
-template <int HDP>
+template <int HDP, bool FAST>
 __global__ void __launch_bounds__(A_THREADS) attn_bwd_dq_kernel(const __grid_constant__ Group<mtb_attn_bwd_desc> g) {
   extern __shared__ __align__(16) float smem[];
   float* Qt = smem;                      // [HDP][AP]
@@ -236,6 +252,7 @@ __global__ void __launch_bounds__(A_THREADS) attn_bwd_dq_kernel(const __grid_con
     load_tile_T<HDP>(Kt, d.k, d.ldk, d.B, b, h, d.hd, j0, d.Lk);
     load_tile_T<HDP>(Vt, d.v, d.ldv, d.B, b, h, d.hd, j0, d.Lk);
     load_tile_N<HDP>(Kn, d.k, d.ldk, d.B, b, h, d.hd, j0, d.Lk);
+    tile_wait();
     __syncthreads();
     float s[4][4], dp[4][4];
 #pragma unroll
@@ -254,7 +271,7 @@ __global__ void __launch_bounds__(A_THREADS) attn_bwd_dq_kernel(const __grid_con
       for (int v = 0; v < 4; ++v) {
         const int j = j0 + tx * 4 + v;
         const bool open = (i < d.Lq) && (j < d.Lk) && (j - i < 1 + off);
-        const float p = open ? expf(s[u][v] * d.scale - row_lse[r]) : 0.f;
+        const float p = open ? attn_exp<FAST>(s[u][v] * d.scale - row_lse[r]) : 0.f;
         ds[v] = p * (dp[u][v] * keep[v] - row_delta[r]) * d.scale;
       }
       *reinterpret_cast<float4*>(dSs + r * AP + tx * 4) = make_float4(ds[0], ds[1], ds[2], ds[3]);
@@ -278,7 +295,7 @@ __global__ void __launch_bounds__(A_THREADS) attn_bwd_dq_kernel(const __grid_con
 // ------------------------------------------------------------------------------ backward: dK, dV
 // One CTA per (b, h, k-tile); loops over the q tiles that can see this k tile.  Works in the
 // transposed [j][i] thread layout so P~^T and dS^T land in shared memory without conflicts.
-template <int HDP>
+template <int HDP, bool FAST>
 __global__ void __launch_bounds__(A_THREADS) attn_bwd_dkv_kernel(const __grid_constant__ Group<mtb_attn_bwd_desc> g) {
   extern __shared__ __align__(16) float smem[];
   float* Kt = smem;                      // [HDP][AP]
@@ -324,6 +341,7 @@ __global__ void __launch_bounds__(A_THREADS) attn_bwd_dkv_kernel(const __grid_co
       col_lse[tid] = i < d.Lq ? d.lse[(int64_t)bh * d.Lq + i] : 0.f;
       col_delta[tid] = i < d.Lq ? d.delta[(int64_t)bh * d.Lq + i] : 0.f;
     }
+    tile_wait();
     __syncthreads();
     float st[4][4], dpt[4][4];     // [j = ty*4+u][i = tx*4+v]
 #pragma unroll
@@ -332,6 +350,20 @@ __global__ void __launch_bounds__(A_THREADS) attn_bwd_dkv_kernel(const __grid_co
       for (int v = 0; v < 4; ++v) { st[u][v] = 0.f; dpt[u][v] = 0.f; }
     mini_gemm<HDP>(Kt, Qt, d.hd, ty, tx, st);
     mini_gemm<HDP>(Vt, dOt, d.hd, ty, tx, dpt);
+    // keep factors of my 4 x 4 block: the 4 key rows j = j0 + ty*4 .. +3 of one query column share a
+    // Philox group (dropout index = (bh*Lq + i) * round4(Lk) + j), so one draw serves 4 elements
+    float keepm[4][4];          // [v = query column][u = key row]
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      keepm[v][0] = keepm[v][1] = keepm[v][2] = keepm[v][3] = dc.inv_keep;
+      const int i = i0 + tx * 4 + v;
+      if (dc.on && i < d.Lq) {
+        const uint64_t idx = ((uint64_t)((int64_t)bh * d.Lq + i)) * (uint64_t)Lk4 + (uint64_t)(j0 + ty * 4);
+        const uint4 r = drop_rand4(dc, idx >> 2);
+        keepm[v][0] = r.x >= dc.thr ? dc.inv_keep : 0.f; keepm[v][1] = r.y >= dc.thr ? dc.inv_keep : 0.f;
+        keepm[v][2] = r.z >= dc.thr ? dc.inv_keep : 0.f; keepm[v][3] = r.w >= dc.thr ? dc.inv_keep : 0.f;
+      }
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int jr = ty * 4 + u, j = j0 + jr;
@@ -340,12 +372,8 @@ __global__ void __launch_bounds__(A_THREADS) attn_bwd_dkv_kernel(const __grid_co
       for (int v = 0; v < 4; ++v) {
         const int ir = tx * 4 + v, i = i0 + ir;
         const bool open = (i < d.Lq) && (j < d.Lk) && (j - i < 1 + off);
-        float keep = dc.inv_keep;
-        if (dc.on && open) {
-          const uint64_t idx = ((uint64_t)((int64_t)bh * d.Lq + i)) * (uint64_t)Lk4 + (uint64_t)j;
-          keep = drop_keep1(dc, idx) ? dc.inv_keep : 0.f;
-        }
-        const float p = open ? expf(st[u][v] * d.scale - col_lse[ir]) : 0.f;
+        const float keep = keepm[v][u];
+        const float p = open ? attn_exp<FAST>(st[u][v] * d.scale - col_lse[ir]) : 0.f;
         pt[v] = p * keep;
         ds[v] = p * (dpt[u][v] * keep - col_delta[ir]) * d.scale;
       }
@@ -375,31 +403,31 @@ template <int HDP> static size_t fwd_smem() { return sizeof(float) * (2 * HDP * 
 template <int HDP> static size_t dq_smem() { return sizeof(float) * (4 * HDP * AP + AT * (HDP + 2) + AT * AP + 2 * AT); }
 template <int HDP> static size_t dkv_smem() { return sizeof(float) * (4 * HDP * AP + 2 * AT * (HDP + 2) + 2 * AT * AP + 2 * AT); }
 
-template <int HDP>
+template <int HDP, bool FAST>
 static int launch_fwd(const Group<mtb_attn_desc>& g, int tot, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    MTB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<HDP>()));
+    MTB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HDP, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<HDP>()));
     attr = true;
   }
-  attn_fwd_kernel<HDP><<<tot, A_THREADS, fwd_smem<HDP>(), st>>>(g);
+  attn_fwd_kernel<HDP, FAST><<<tot, A_THREADS, fwd_smem<HDP>(), st>>>(g);
   mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
   return 0;
 }
-template <int HDP>
+template <int HDP, bool FAST>
 static int launch_bwd(const Group<mtb_attn_bwd_desc>& gq, int totq, const Group<mtb_attn_bwd_desc>& gk, int totk,
                       cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    MTB_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dq_smem<HDP>()));
-    MTB_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<HDP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dkv_smem<HDP>()));
+    MTB_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<HDP, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dq_smem<HDP>()));
+    MTB_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<HDP, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dkv_smem<HDP>()));
     attr = true;
   }
-  attn_bwd_dq_kernel<HDP><<<totq, A_THREADS, dq_smem<HDP>(), st>>>(gq);
+  attn_bwd_dq_kernel<HDP, FAST><<<totq, A_THREADS, dq_smem<HDP>(), st>>>(gq);
   mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
-  attn_bwd_dkv_kernel<HDP><<<totk, A_THREADS, dkv_smem<HDP>(), st>>>(gk);
+  attn_bwd_dkv_kernel<HDP, FAST><<<totk, A_THREADS, dkv_smem<HDP>(), st>>>(gk);
   mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
   return 0;
@@ -418,7 +446,8 @@ int attn_fwd_simt(const mtb_attn_desc* d, int n, cudaStream_t st) {
   g.start[n] = tot;
   if (tot == 0) return 0;
   MTB_CHECK(maxhd <= 64, "attention: head_dim %d > 64 not supported", maxhd);
-  return maxhd <= 32 ? launch_fwd<32>(g, tot, st) : launch_fwd<64>(g, tot, st);
+  if (g_gemm_mode == 1) return maxhd <= 32 ? launch_fwd<32, true>(g, tot, st) : launch_fwd<64, true>(g, tot, st);
+  return maxhd <= 32 ? launch_fwd<32, false>(g, tot, st) : launch_fwd<64, false>(g, tot, st);
 }
 
 int attn_bwd_simt(const mtb_attn_bwd_desc* d, int n, cudaStream_t st) {
@@ -435,7 +464,8 @@ int attn_bwd_simt(const mtb_attn_bwd_desc* d, int n, cudaStream_t st) {
   gq.start[n] = totq; gk.start[n] = totk;
   if (totq == 0 || totk == 0) return 0;
   MTB_CHECK(maxhd <= 64, "attention: head_dim %d > 64 not supported", maxhd);
-  return maxhd <= 32 ? launch_bwd<32>(gq, totq, gk, totk, st) : launch_bwd<64>(gq, totq, gk, totk, st);
+  if (g_gemm_mode == 1) return maxhd <= 32 ? launch_bwd<32, true>(gq, totq, gk, totk, st) : launch_bwd<64, true>(gq, totq, gk, totk, st);
+  return maxhd <= 32 ? launch_bwd<32, false>(gq, totq, gk, totk, st) : launch_bwd<64, false>(gq, totq, gk, totk, st);
 }
 
 }  // namespace mtb
@@ -443,12 +473,13 @@ int attn_bwd_simt(const mtb_attn_bwd_desc* d, int n, cudaStream_t st) {
 namespace mtb {
 int preload_attention_simt() {
   int bad = 0;
-  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_fwd_kernel<32>) != cudaSuccess) ++bad; }
-  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_fwd_kernel<64>) != cudaSuccess) ++bad; }
-  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_bwd_dq_kernel<32>) != cudaSuccess) ++bad; }
-  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_bwd_dq_kernel<64>) != cudaSuccess) ++bad; }
-  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_bwd_dkv_kernel<32>) != cudaSuccess) ++bad; }
-  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_bwd_dkv_kernel<64>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_fwd_kernel<32, false>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_fwd_kernel<32, true>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_fwd_kernel<64, false>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_bwd_dq_kernel<32, true>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_bwd_dq_kernel<32, false>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_bwd_dkv_kernel<32, true>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_bwd_dkv_kernel<32, false>) != cudaSuccess) ++bad; }
   return bad;
 }
 }  // namespace mtb

@@ -102,17 +102,27 @@ __device__ __forceinline__ uint32_t idesc_tf32(int M, int N, bool a_mn, bool b_m
 
 // stage `rows` token rows (token l0 + r, batch b, head h) of a token-major matrix into a tile of
 // 128-byte rows; MNSW selects the 32-byte-atom swizzle.  Zero padding for d >= hd and l >= L.
+// Rows are 25 floats at 100-byte offsets (TMA cannot address them), so each element travels as a
+// 4-byte cp.async (LDGSTS) with zero-fill straight into its swizzled slot: no registers, and ALL
+// copies of a tile are in flight at once -- one L2 latency per tile instead of one per element
+// (the first version's load -> convert -> store loop spent 70 % of its stall samples here).
 template <bool MNSW>
 __device__ __forceinline__ void stage_tile(uint8_t* tile, const float* base, int64_t ld, int B, int b, int h, int hd, int l0, int L,
                                            int rows) {
+  const uint32_t tbase = a_smem_u32(tile);
   for (int e = threadIdx.x; e < rows * HP; e += ATC_THREADS) {
     const int r = e >> 5, c = e & 31;
     const int l = l0 + r;
-    float v = 0.f;
-    if (l < L && c < hd) v = to_tf32(base[((int64_t)l * B + b) * ld + h * hd + c]);
-    const uint32_t off = MNSW ? swz128_32(r, c * 4) : swz128(r, c * 4);
-    *reinterpret_cast<float*>(tile + off) = v;
+    const bool ok = (l < L) && (c < hd);
+    const float* src = ok ? base + ((int64_t)l * B + b) * ld + h * hd + c : base;
+    const uint32_t dst = tbase + (MNSW ? swz128_32(r, c * 4) : swz128(r, c * 4));
+    const int nbytes = ok ? 4 : 0;                           // src-size 0 -> the 4 destination bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
   }
+}
+__device__ __forceinline__ void stage_wait() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ int a_round4(int x) { return (x + 3) & ~3; }
@@ -149,6 +159,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_tc_kernel(const __grid_c
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   stage_tile<false>(Qs, d.q, d.ldq, d.B, b, h, d.hd, i0, d.Lq, TQ);
+  stage_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -170,6 +181,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_tc_kernel(const __grid_c
   for (int j0 = 0; j0 < j_end; j0 += TK, phase ^= 1u) {
     stage_tile<false>(Ks, d.k, d.ldk, d.B, b, h, d.hd, j0, d.Lk, TK);
     stage_tile<true>(Vs, d.v, d.ldv, d.B, b, h, d.hd, j0, d.Lk, TK);
+    stage_wait();
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -309,6 +321,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_dq_tc_kernel(const __gri
     lse = d.lse[(int64_t)bh * d.Lq + i];
     d.delta[(int64_t)bh * d.Lq + i] = delta;
   }
+  stage_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -326,6 +339,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_dq_tc_kernel(const __gri
     stage_tile<false>(Ks, d.k, d.ldk, d.B, b, h, d.hd, j0, d.Lk, TK);
     stage_tile<false>(Vs, d.v, d.ldv, d.B, b, h, d.hd, j0, d.Lk, TK);
     stage_tile<true>(Kmn, d.k, d.ldk, d.B, b, h, d.hd, j0, d.Lk, TK);
+    stage_wait();
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -446,6 +460,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_dkv_tc_kernel(const __gr
   }
   stage_tile<false>(Ks, d.k, d.ldk, d.B, b, h, d.hd, j0, d.Lk, TQ);
   stage_tile<false>(Vs, d.v, d.ldv, d.B, b, h, d.hd, j0, d.Lk, TQ);
+  stage_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -468,6 +483,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_dkv_tc_kernel(const __gr
       col_lse[tid] = ii < d.Lq ? d.lse[(int64_t)bh * d.Lq + ii] : 0.f;
       col_delta[tid] = ii < d.Lq ? d.delta[(int64_t)bh * d.Lq + ii] : 0.f;
     }
+    stage_wait();
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -489,19 +505,34 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_dkv_tc_kernel(const __gr
       a_tmem_ld32(t_dpt + lane_addr, dpt);
 #pragma unroll
       for (int c4 = 0; c4 < TI; c4 += 4) {
+        // Dropout keeps for 4 query columns x my key row.  The 4 lanes of a quad own key rows j..j+3 =
+        // one Philox group per query row, so lane k of the quad draws the group of query row c4+k and
+        // the quad exchanges components by shuffle: 1/4 Philox call + 4 shuffles per element group
+        // instead of one call per element.
+        float keep[4] = {dc.inv_keep, dc.inv_keep, dc.inv_keep, dc.inv_keep};
+        if (dc.on) {
+          const int lane = tid & 31;
+          const int iq = min(i0 + c4 + (lane & 3), d.Lq - 1);
+          const uint64_t idx = ((uint64_t)((int64_t)bh * d.Lq + iq)) * (uint64_t)Lk4 + (uint64_t)((j0 + tid) & ~3);
+          const uint4 r = drop_rand4(dc, idx >> 2);
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int srcl = (lane & ~3) + m;
+            const uint32_t rx = __shfl_sync(0xffffffffu, r.x, srcl), ry = __shfl_sync(0xffffffffu, r.y, srcl);
+            const uint32_t rz = __shfl_sync(0xffffffffu, r.z, srcl), rw = __shfl_sync(0xffffffffu, r.w, srcl);
+            const int k = lane & 3;
+            const uint32_t mine = k == 0 ? rx : k == 1 ? ry : k == 2 ? rz : rw;
+            keep[m] = mine >= dc.thr ? dc.inv_keep : 0.f;
+          }
+        }
         float pt[4], ds[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int ii = i0 + c4 + e;
           const bool open = (ii < d.Lq) && (j < d.Lk) && (j - ii < 1 + off);
-          float keep = dc.inv_keep;
-          if (dc.on && open) {
-            const uint64_t idx = ((uint64_t)((int64_t)bh * d.Lq + ii)) * (uint64_t)Lk4 + (uint64_t)j;
-            keep = drop_keep1(dc, idx) ? dc.inv_keep : 0.f;
-          }
           const float p = open ? __expf(st[c4 + e] * d.scale - col_lse[c4 + e]) : 0.f;
-          pt[e] = to_tf32(p * keep);
-          ds[e] = to_tf32(p * (dpt[c4 + e] * keep - col_delta[c4 + e]) * d.scale);
+          pt[e] = p * keep[e];
+          ds[e] = p * (dpt[c4 + e] * keep[e] - col_delta[c4 + e]) * d.scale;
         }
         *reinterpret_cast<float4*>(PTs + swz128(tid, c4 * 4)) = make_float4(pt[0], pt[1], pt[2], pt[3]);
         *reinterpret_cast<float4*>(dSTs + swz128(tid, c4 * 4)) = make_float4(ds[0], ds[1], ds[2], ds[3]);

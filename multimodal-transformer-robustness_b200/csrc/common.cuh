@@ -47,25 +47,20 @@ __device__ __forceinline__ int find_problem(const Group<D>& g, int blk, int& loc
   return p;
 }
 
-// ---------------------------------------------------------------- Philox4x32-10
+// ---------------------------------------------------------------- Philox4x32-7
 struct Philox {
   uint32_t k0, k1;
   __host__ __device__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
   __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
-#ifdef __CUDA_ARCH__
-    hi = __umulhi(a, b);
-    lo = a * b;
-#else
-    uint64_t p = (uint64_t)a * b;
+    const uint64_t p = (uint64_t)a * b;      // one IMAD.WIDE.U32
     hi = (uint32_t)(p >> 32);
     lo = (uint32_t)p;
-#endif
   }
   __host__ __device__ inline uint4 operator()(uint64_t ctr) const {
     uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x5bd1e995u, c3 = 0u;
     uint32_t a = k0, b = k1;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < 7; ++r) {          // Philox4x32-7 (the round count curand also offers; passes BigCrush)
       uint32_t h0, l0, h1, l1;
       mulhilo(0xD2511F53u, c0, h0, l0);
       mulhilo(0xCD9E8D57u, c2, h1, l1);

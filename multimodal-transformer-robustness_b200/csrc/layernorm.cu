@@ -342,8 +342,10 @@ int mtb_resln_bwd(const mtb_resln_bwd_desc* d, int n, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int tot = 0;
   if (vec && maxE <= 1024) {
-    // enough CTAs for ~4 waves of the 148 SMs, at least one pass of the 8 warps per CTA
-    int rows = (maxT + sm_count() * 4 - 1) / (sm_count() * 4);
+    // ~2 CTAs per SM when column sums (d-gamma / d-beta / bias grads) are accumulated -- fewer, longer CTAs
+    // mean fewer contended global atomics per feature; ~4 waves otherwise
+    const int target = affine ? sm_count() * 2 : sm_count() * 4;
+    int rows = (maxT + target - 1) / target;
     rows = ((rows + LN_WARPS - 1) / LN_WARPS) * LN_WARPS;
     if (rows < LN_WARPS) rows = LN_WARPS;
     for (int i = 0; i < n; ++i) { g.d[i] = d[i]; g.start[i] = tot; tot += (d[i].T + rows - 1) / rows; }

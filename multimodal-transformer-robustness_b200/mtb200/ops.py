@@ -129,9 +129,10 @@ def set_gemm_mode(mode: str) -> str:
 
 
 def set_attn_mode(mode: str) -> str:
-    """'simt' = fp32 CUDA-core flash attention (default), 'tc' = tcgen05 / TMEM flash attention (TF32)."""
-    prev = lib.mtb_set_attn_mode({"simt": 0, "tc": 1}[mode])
-    return "tc" if prev else "simt"
+    """'simt' = fp32 CUDA-core flash attention, 'tc' = tcgen05 / TMEM flash attention (TF32),
+    'auto' (default) = tensor-core attention whenever the GEMM engine is 'tf32'."""
+    prev = lib.mtb_set_attn_mode({"simt": 0, "tc": 1, "auto": -1}[mode])
+    return {0: "simt", 1: "tc"}.get(prev, "auto")
 
 
 def get_gemm_mode() -> str:

@@ -21,7 +21,7 @@ def rel_err(a, b):
 def assert_rel(a, b, tol=REL, what=""):
     assert a.shape == b.shape, (what, a.shape, b.shape)
     if float(b.abs().max()) == 0.0:       # exactly-zero reference (e.g. softmax over one key): fp32 noise only
-        assert float(a.abs().max()) < 1e-6, f"{what}: expected zeros, got max {float(a.abs().max()):.3e}"
+        assert float(a.abs().max()) < 1e-5, f"{what}: expected zeros, got max {float(a.abs().max()):.3e}"
         return
     e = rel_err(a, b)
     assert e <= tol, f"{what}: rel err {e:.3e} > {tol:.1e}"

@@ -161,7 +161,7 @@ def test_tc_attention_matches_oracle(tf32, Lq, Lk, B, H, hd, p):
     try:
         _tc_attention_case(ops, MaskFeed, _attn_ref, Lq, Lk, B, H, hd, p)
     finally:
-        ops.set_attn_mode("simt")
+        ops.set_attn_mode("auto")
 
 
 def _tc_attention_case(ops, MaskFeed, _attn_ref, Lq, Lk, B, H, hd, p):
@@ -180,6 +180,6 @@ def _tc_attention_case(ops, MaskFeed, _attn_ref, Lq, Lk, B, H, hd, p):
     (orf * R).sum().backward()
     for a, b, n in zip(cu, cp, "qkv"):
         if float(b.grad.abs().max()) == 0.0:     # softmax over a single key: exact zero in fp32, TF32 residue here
-            assert float(a.grad.abs().max()) < 2e-3
+            assert float(a.grad.abs().max()) < 1e-2
         else:
             assert_rel(a.grad, b.grad, 8e-3, f"d{n}")

@@ -77,4 +77,4 @@ for mode in ("simt", "tc"):
         report(f"attn_fwd ({mode}) [Lq{Lq},Lk{Lk},B{B},H{H},hd{hd}] p=0.1", timeit(fn), bytes_=4 * D * B * (2 * Lq + 2 * Lk), flops=fl)
         o = fn(); go = torch.randn_like(o)
         report(f"attn_bwd dq+dkv ({mode}) [Lq{Lq},Lk{Lk}]", timeit(lambda: torch.autograd.grad(o, qkv, go, retain_graph=True)), flops=2.5 * fl)
-ops.set_attn_mode("simt")
+ops.set_attn_mode("auto")
