@@ -25,6 +25,10 @@ import tempfile
 import threading
 import time
 
+# CUDA loads kernel modules lazily by default: the first use of every (torch or libmultb200) kernel
+# variant inside the timed loop would stall a step by tens of milliseconds.  Load everything up front.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for _p in (os.path.join(ROOT, "multimodal-transformer-robustness_b200"), ROOT):
     if _p not in sys.path:

@@ -86,7 +86,8 @@ int mtb_linear_bwd(const mtb_linear_bwd_desc* d, int n, void* stream) {
   MTB_CHECK(n >= 1 && n <= MTB_MAX_GROUP, "linear_bwd: group size %d out of range", n);
   for (int i = 0; i < n; ++i) {
     MTB_CHECK(d[i].dY && d[i].W, "linear_bwd: null operand in problem %d", i);
-    MTB_CHECK(!d[i].db || d[i].dW, "linear_bwd: bias gradient requested without weight gradient (problem %d)", i);
+    MTB_CHECK(!d[i].db || d[i].dW || mtb::g_gemm_mode == 1,
+              "linear_bwd: the fp32 engine computes the bias gradient inside the weight-gradient GEMM (problem %d)", i);
     MTB_CHECK(!d[i].dW || d[i].X, "linear_bwd: weight gradient needs the forward input (problem %d)", i);
     MTB_CHECK(d[i].act == 0 || d[i].Yact, "linear_bwd: act=1 needs the forward output (problem %d)", i);
   }

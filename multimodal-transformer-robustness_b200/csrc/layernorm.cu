@@ -192,31 +192,29 @@ __global__ void __launch_bounds__(LN_THREADS) resln_bwd_kernel(const __grid_cons
     }
   }
   if (AFFINE_GRAD) {
-    if (agrad) {
+    // combine the 8 warps' register partials in shared memory, one warp at a time (plain adds between
+    // barriers: shared-memory float atomics are CAS loops and serialise badly under 8-way contention)
+#pragma unroll 1
+    for (int w = 0; w < LN_WARPS; ++w) {
+      if (warp == w) {
 #pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int v = lane + 32 * i;
-        if (v < nv) {
-          const int c = v << 2;
-          atomicAdd(&sred[c], dg[i].x); atomicAdd(&sred[c + 1], dg[i].y);
-          atomicAdd(&sred[c + 2], dg[i].z); atomicAdd(&sred[c + 3], dg[i].w);
-          atomicAdd(&sred[E + c], db[i].x); atomicAdd(&sred[E + c + 1], db[i].y);
-          atomicAdd(&sred[E + c + 2], db[i].z); atomicAdd(&sred[E + c + 3], db[i].w);
+        for (int i = 0; i < MAXV; ++i) {
+          const int v = lane + 32 * i;
+          if (v < nv) {
+            const int c = v << 2;
+            if (agrad) {
+              sred[c] += dg[i].x; sred[c + 1] += dg[i].y; sred[c + 2] += dg[i].z; sred[c + 3] += dg[i].w;
+              sred[E + c] += db[i].x; sred[E + c + 1] += db[i].y; sred[E + c + 2] += db[i].z; sred[E + c + 3] += db[i].w;
+            }
+            if (bgrad) {
+              sred[2 * E + c] += dba[i].x; sred[2 * E + c + 1] += dba[i].y;
+              sred[2 * E + c + 2] += dba[i].z; sred[2 * E + c + 3] += dba[i].w;
+            }
+          }
         }
       }
+      __syncthreads();
     }
-    if (bgrad) {
-#pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int v = lane + 32 * i;
-        if (v < nv) {
-          const int c = v << 2;
-          atomicAdd(&sred[2 * E + c], dba[i].x); atomicAdd(&sred[2 * E + c + 1], dba[i].y);
-          atomicAdd(&sred[2 * E + c + 2], dba[i].z); atomicAdd(&sred[2 * E + c + 3], dba[i].w);
-        }
-      }
-    }
-    __syncthreads();
     if (agrad || bgrad) {
       for (int c = threadIdx.x; c < E; c += LN_THREADS) {
         const int ic = d.idx ? d.idx[c] : c;

@@ -322,20 +322,35 @@ struct ActgradArgs {
   const float* dY; int64_t ldy; const float* Y; int64_t ldyy; float* out; float* db;
   int M, N, seg_len; float inv_keep; uint8_t seg[TC_MAXSEG];
 };
-__global__ void __launch_bounds__(128) actgrad_kernel(const ActgradArgs a) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int m0 = blockIdx.y * 64, m1 = min(a.M, m0 + 64);
-  if (n >= a.N) return;
+constexpr int ACT_ROWS = 32;           // rows per block: 4 row-lanes x 8 rows, all 8 loads of a lane in flight
+__global__ void __launch_bounds__(512) actgrad_kernel(const ActgradArgs a) {
+  __shared__ float part[4][128];
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int m0 = blockIdx.y * ACT_ROWS + threadIdx.y * 8;
   float s = 0.f;
-#pragma unroll 4
-  for (int m = m0; m < m1; ++m) {
-    const float v = a.Y[(int64_t)m * a.ldyy + n] > 0.f ? a.dY[(int64_t)m * a.ldy + n] * a.inv_keep : 0.f;
-    a.out[(int64_t)m * a.N + n] = v;
-    s += v;
+  if (n < a.N) {
+    float dy[8], y[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int m = m0 + u;
+      const bool ok = m < a.M;
+      dy[u] = ok ? a.dY[(int64_t)m * a.ldy + n] : 0.f;
+      y[u] = ok ? a.Y[(int64_t)m * a.ldyy + n] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int m = m0 + u;
+      const float v = y[u] > 0.f ? dy[u] * a.inv_keep : 0.f;
+      if (m < a.M) a.out[(int64_t)m * a.N + n] = v;
+      s += v;
+    }
   }
-  if (a.db) {
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < a.N && a.db) {
+    const float t = (part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x]);
     const int sgi = n / a.seg_len;
-    atomicAdd(a.db + (int64_t)a.seg[sgi] * a.seg_len + (n - sgi * a.seg_len), s);
+    atomicAdd(a.db + (int64_t)a.seg[sgi] * a.seg_len + (n - sgi * a.seg_len), t);
   }
 }
 // db[phys(n)] += sum_m dY[m, n]; one thread per column, 64 rows per block, 8 independent loads in flight
@@ -546,8 +561,8 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
       aa.dY = x.dY; aa.ldy = x.ldy; aa.Y = x.Yact; aa.ldyy = x.ldyact; aa.out = x.scratch; aa.db = x.db;
       aa.M = x.M; aa.N = x.N; aa.seg_len = an.len; aa.inv_keep = x.p > 0.f ? 1.f / (1.f - x.p) : 1.f;
       for (int s2 = 0; s2 < TC_MAXSEG; ++s2) aa.seg[s2] = s2 < an.n ? an.phys[s2] : 0;
-      dim3 grid((x.N + 127) / 128, (x.M + 63) / 64);
-      actgrad_kernel<<<grid, 128, 0, st>>>(aa);
+      dim3 grid((x.N + 127) / 128, (x.M + ACT_ROWS - 1) / ACT_ROWS);
+      actgrad_kernel<<<grid, dim3(128, 4), 0, st>>>(aa);
       mtb::note_launch();
       MTB_CUDA(cudaGetLastError());
     }
@@ -563,10 +578,17 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
       MTB_CUDA(cudaGetLastError());
     }
   }
-  int rc = launch_tc(dg, ndg, st);
-  if (rc) return rc;
-  rc = launch_tc(wg, nwg, st);
-  if (rc) return rc;
+  // dgrad and wgrad problems are independent of each other: one launch carries both kinds
+  // (the kernel switches operand majors per problem), which fills the SMs better than two launches
+  TcProblem all[2 * MTB_MAX_GROUP];
+  int nall = 0;
+  for (int i = 0; i < ndg; ++i) all[nall++] = dg[i];
+  for (int i = 0; i < nwg; ++i) all[nall++] = wg[i];
+  for (int off = 0; off < nall; off += MTB_MAX_GROUP) {
+    const int m = nall - off < MTB_MAX_GROUP ? nall - off : MTB_MAX_GROUP;
+    int rc = launch_tc(all + off, m, st);
+    if (rc) return rc;
+  }
   if (nrest) return linear_bwd_simt(rest, nrest, st);
   return 0;
 }

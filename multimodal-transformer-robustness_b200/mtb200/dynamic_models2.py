@@ -217,6 +217,17 @@ class DynamicMULTModel(nn.Module):
                         return False
         return True
 
+    def prefetch_plan(self, x) -> bool:
+        """Build (and cache) the plan of the CURRENT configuration for inputs shaped like ``x`` without
+        running it.  The trainer calls this right after it has sampled the next step's sub-network and
+        launched the backward pass, so plan construction overlaps GPU execution instead of delaying the
+        next forward.  Only for sequence-preserving front-ends (output length = input length)."""
+        if not self._engine_ok(x) or not all(isinstance(pj, Conv1x1FrontEnd) for pj in self.proj):
+            return False
+        meta = tuple((int(t.shape[1]), int(t.shape[0])) for t in x)
+        self.engine().plan_for(meta, self.training, torch.is_grad_enabled())
+        return True
+
     def _forward_engine(self, x):
         need = self._needed_modalities() if self.prune_dead_branches else set(self.modality_list)
         px = []

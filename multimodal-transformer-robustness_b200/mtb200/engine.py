@@ -380,8 +380,13 @@ class PlanBuilder:
             e.saved["g_x"] = None
             e.saved["g_xk"] = None
             e.saved["g_xv"] = None
+        # Tensor-core engine: the weight-gradient GEMMs of a layer do not feed the backward chain, so they are
+        # split off the four linear backward calls and issued as ONE grouped launch per stage-layer
+        # (4-6 problems per branch, split over tokens) -- fewer launches, fuller SMs.
+        defer = lib.mtb_get_gemm_mode() == 1
         for i in reversed(range(max_layers)):
             act = [e for e in group if e.n_layers > i]
+            wg_descs = []
             # h'. res_ln2 backward -> g_x1 (residual), g_y
             descs = []
             for e in act:
@@ -411,12 +416,25 @@ class PlanBuilder:
                 g_h, g_xn1 = A.mat(Tq, Fa), A.mat(Tq, e.E)
                 scratch = A.alloc(Tq * Fa)
                 S["g_xn1"] = g_xn1
-                d2.append(LinearBwdDesc(S["g_y"].ptr, S["g_y"].ld, None, 0, S["h"].ptr, S["h"].ld, W2.data_ptr(), W2.stride(0), midx, None,
-                                        g_h.ptr, g_h.ld, 0, self.grad_ptr(W2), None, Tq, e.E, Fa, 0, 0.0, None,
-                                        _segs(e.mask), Segs(0, 0)))
-                d1.append(LinearBwdDesc(g_h.ptr, g_h.ld, S["h"].ptr, S["h"].ld, S["xn1"].ptr, S["xn1"].ld, W1.data_ptr(), W1.stride(0), None, midx,
-                                        g_xn1.ptr, g_xn1.ld, 0, self.grad_ptr(W1), self.grad_ptr(b1), Tq, Fa, e.E, 1, S["p_relu"], scratch,
-                                        Segs(0, 0), _segs(e.mask)))
+                if defer:
+                    d2.append(LinearBwdDesc(S["g_y"].ptr, S["g_y"].ld, None, 0, None, 0, W2.data_ptr(), W2.stride(0), midx, None,
+                                            g_h.ptr, g_h.ld, 0, None, None, Tq, e.E, Fa, 0, 0.0, None, _segs(e.mask), Segs(0, 0)))
+                    wg_descs.append(LinearBwdDesc(S["g_y"].ptr, S["g_y"].ld, None, 0, S["h"].ptr, S["h"].ld, W2.data_ptr(), W2.stride(0), midx, None,
+                                                  None, 0, 0, self.grad_ptr(W2), None, Tq, e.E, Fa, 0, 0.0, None, _segs(e.mask), Segs(0, 0)))
+                    # fc1: the dgrad call materialises dY' = dY*[h>0]/(1-p) into `scratch` (bias grad fused there);
+                    # the deferred wgrad reads it back as a plain dY
+                    d1.append(LinearBwdDesc(g_h.ptr, g_h.ld, S["h"].ptr, S["h"].ld, None, 0, W1.data_ptr(), W1.stride(0), None, midx,
+                                            g_xn1.ptr, g_xn1.ld, 0, None, self.grad_ptr(b1), Tq, Fa, e.E, 1, S["p_relu"], scratch,
+                                            Segs(0, 0), _segs(e.mask)))
+                    wg_descs.append(LinearBwdDesc(scratch, Fa, None, 0, S["xn1"].ptr, S["xn1"].ld, W1.data_ptr(), W1.stride(0), None, midx,
+                                                  None, 0, 0, self.grad_ptr(W1), None, Tq, Fa, e.E, 0, 0.0, None, Segs(0, 0), _segs(e.mask)))
+                else:
+                    d2.append(LinearBwdDesc(S["g_y"].ptr, S["g_y"].ld, None, 0, S["h"].ptr, S["h"].ld, W2.data_ptr(), W2.stride(0), midx, None,
+                                            g_h.ptr, g_h.ld, 0, self.grad_ptr(W2), None, Tq, e.E, Fa, 0, 0.0, None,
+                                            _segs(e.mask), Segs(0, 0)))
+                    d1.append(LinearBwdDesc(g_h.ptr, g_h.ld, S["h"].ptr, S["h"].ld, S["xn1"].ptr, S["xn1"].ld, W1.data_ptr(), W1.stride(0), None, midx,
+                                            g_xn1.ptr, g_xn1.ld, 0, self.grad_ptr(W1), self.grad_ptr(b1), Tq, Fa, e.E, 1, S["p_relu"], scratch,
+                                            Segs(0, 0), _segs(e.mask)))
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, d2, f"fc2_bwd[{i}]")
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, d1, f"fc1_bwd[{i}]")
             # e'. res_ln1 backward -> g_x (residual into the layer input), g_a
@@ -448,9 +466,15 @@ class PlanBuilder:
                 ridx = e.mask.idx.data_ptr() if e.mask is not None else None
                 g_o = A.mat(Tq, D)
                 S["g_o"] = g_o
-                descs.append(LinearBwdDesc(S["g_a"].ptr, S["g_a"].ld, None, 0, S["o"].ptr, S["o"].ld, Wo.data_ptr(), Wo.stride(0), ridx, None,
-                                           g_o.ptr, g_o.ld, 0, self.grad_ptr(Wo), None, Tq, e.E, D, 0, 0.0, None,
-                                           _segs(e.mask), Segs(0, 0)))
+                if defer:
+                    descs.append(LinearBwdDesc(S["g_a"].ptr, S["g_a"].ld, None, 0, None, 0, Wo.data_ptr(), Wo.stride(0), ridx, None,
+                                               g_o.ptr, g_o.ld, 0, None, None, Tq, e.E, D, 0, 0.0, None, _segs(e.mask), Segs(0, 0)))
+                    wg_descs.append(LinearBwdDesc(S["g_a"].ptr, S["g_a"].ld, None, 0, S["o"].ptr, S["o"].ld, Wo.data_ptr(), Wo.stride(0), ridx, None,
+                                                  None, 0, 0, self.grad_ptr(Wo), None, Tq, e.E, D, 0, 0.0, None, _segs(e.mask), Segs(0, 0)))
+                else:
+                    descs.append(LinearBwdDesc(S["g_a"].ptr, S["g_a"].ld, None, 0, S["o"].ptr, S["o"].ld, Wo.data_ptr(), Wo.stride(0), ridx, None,
+                                               g_o.ptr, g_o.ld, 0, self.grad_ptr(Wo), None, Tq, e.E, D, 0, 0.0, None,
+                                               _segs(e.mask), Segs(0, 0)))
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, descs, f"out_proj_bwd[{i}]")
             # c'. attention backward
             descs = []
@@ -488,17 +512,32 @@ class PlanBuilder:
                 e.saved["g_xn"] = g_xn
                 if not e.cross:
                     cidx = e.mask.idx.data_ptr() if e.mask is not None else None
-                    descs.append(LinearBwdDesc(S["dqkv"].ptr, S["dqkv"].ld, None, 0, xn_in.ptr, xn_in.ld, W.data_ptr(), W.stride(0), None, cidx,
-                                               g_xn.ptr, g_xn.ld, 0, gW, gb, Tq, 3 * D, e.E, 0, 0.0, None, Segs(0, 0), _segs(e.mask)))
+                    if defer:
+                        descs.append(LinearBwdDesc(S["dqkv"].ptr, S["dqkv"].ld, None, 0, None, 0, W.data_ptr(), W.stride(0), None, cidx,
+                                                   g_xn.ptr, g_xn.ld, 0, None, None, Tq, 3 * D, e.E, 0, 0.0, None, Segs(0, 0), _segs(e.mask)))
+                        wg_descs.append(LinearBwdDesc(S["dqkv"].ptr, S["dqkv"].ld, None, 0, xn_in.ptr, xn_in.ld, W.data_ptr(), W.stride(0), None, cidx,
+                                                      None, 0, 0, gW, gb, Tq, 3 * D, e.E, 0, 0.0, None, Segs(0, 0), _segs(e.mask)))
+                    else:
+                        descs.append(LinearBwdDesc(S["dqkv"].ptr, S["dqkv"].ld, None, 0, xn_in.ptr, xn_in.ld, W.data_ptr(), W.stride(0), None, cidx,
+                                                   g_xn.ptr, g_xn.ld, 0, gW, gb, Tq, 3 * D, e.E, 0, 0.0, None, Segs(0, 0), _segs(e.mask)))
                 else:
                     g_kn, g_vn = A.mat(Tk, e.E), A.mat(Tk, e.E)
                     S["g_kn"], S["g_vn"] = g_kn, g_vn
                     srcs = (xn_in, S["kn"][0], S["vn"][0])
                     for part, (dy, src, dst, T) in enumerate(zip((S["dq"], S["dk"], S["dv"]), srcs, (g_xn, g_kn, g_vn), (Tq, Tk, Tk))):
-                        descs.append(LinearBwdDesc(dy.ptr, dy.ld, None, 0, src.ptr, src.ld, W.data_ptr() + F4 * part * D * W.stride(0), W.stride(0),
-                                                   None, None, dst.ptr, dst.ld, 0, (gW + F4 * part * D * W.stride(0)) if gW else None,
-                                                   (gb + F4 * part * D) if gb else None, T, D, e.E, 0, 0.0, None, Segs(0, 0), Segs(0, 0)))
+                        gWp = (gW + F4 * part * D * W.stride(0)) if gW else None
+                        gbp = (gb + F4 * part * D) if gb else None
+                        Wp = W.data_ptr() + F4 * part * D * W.stride(0)
+                        if defer:
+                            descs.append(LinearBwdDesc(dy.ptr, dy.ld, None, 0, None, 0, Wp, W.stride(0), None, None, dst.ptr, dst.ld, 0,
+                                                       None, None, T, D, e.E, 0, 0.0, None, Segs(0, 0), Segs(0, 0)))
+                            wg_descs.append(LinearBwdDesc(dy.ptr, dy.ld, None, 0, src.ptr, src.ld, Wp, W.stride(0), None, None, None, 0, 0,
+                                                          gWp, gbp, T, D, e.E, 0, 0.0, None, Segs(0, 0), Segs(0, 0)))
+                        else:
+                            descs.append(LinearBwdDesc(dy.ptr, dy.ld, None, 0, src.ptr, src.ld, Wp, W.stride(0),
+                                                       None, None, dst.ptr, dst.ld, 0, gWp, gbp, T, D, e.E, 0, 0.0, None, Segs(0, 0), Segs(0, 0)))
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, descs, f"in_proj_bwd[{i}]")
+            self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, wg_descs, f"wgrad[{i}]")
             # a'. LN0 backward on the key / value streams (gradients accumulate over layers, in place)
             descs = []
             for e in act:
@@ -657,6 +696,9 @@ class Engine:
         plan = self.last_plan
         if plan is None:
             return []
+        cached = getattr(plan, "_ranges", None)
+        if cached is not None and cached[0] == max_gap:
+            return cached[1]
         spans = sorted((self._grad_off[id(p)], self._grad_off[id(p)] + p.numel()) for p in plan.active_params)
         out: List[Tuple[int, int]] = []
         for lo, hi in spans:
@@ -664,6 +706,7 @@ class Engine:
                 out[-1] = (out[-1][0], max(out[-1][1], hi))
             else:
                 out.append((lo, hi))
+        plan._ranges = (max_gap, out)
         return out
 
     def clip_grad_norm_(self, max_norm: float, extra: Sequence[torch.Tensor] = ()) -> torch.Tensor:
@@ -674,14 +717,9 @@ class Engine:
         flats = [self.grad_arena[lo:hi] for lo, hi in rs] + [g.reshape(-1) for g in extra]   # extra: grads living outside the arena
         if not flats:
             return torch.zeros((), device=self.device)
-        sq = None
-        for t in flats:
-            v = torch.dot(t, t)
-            sq = v if sq is None else sq + v
-        total = sq.sqrt()
+        total = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(flats)))     # multi-tensor: 2 kernels
         coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
-        for t in flats:
-            t.mul_(coef)
+        torch._foreach_mul_(flats, coef)
         return total
 
     def manual_seed(self, seed: int):
@@ -695,7 +733,7 @@ class Engine:
         cross_depth = tuple(sorted({m.trans['cross' + n].active_layer_num for i in m.active_modality for n in m.active_cross[i]}))
         self_depth = tuple(m.trans_mems['mems' + ch].active_layer_num for ch in m.modality_list)
         ffn = m.trans_mems0['mems0' + m.modality_list[0]].layers[0].active_hidden_out_fc1 if m.layers_single_attn > 0 else 0
-        return (tuple(shapes), training, need_grad, tuple(m.active_modality), tuple(tuple(c) for c in m.active_cross),
+        return (lib.mtb_get_gemm_mode(), tuple(shapes), training, need_grad, tuple(m.active_modality), tuple(tuple(c) for c in m.active_cross),
                 tuple(tuple(o) for o in m.active_cross_output), depth, cross_depth, self_depth, ffn)
 
     def _build(self, px_meta, training, need_grad, arena) -> Plan:
@@ -1019,7 +1057,10 @@ class _EngineFn(torch.autograd.Function):
     def backward(ctx, d_pred):
         eng, plan = ctx.eng, ctx.plan
         m = eng.model
-        eng.grad_arena.zero_()
+        eng.last_plan = plan
+        rs = eng.active_ranges()              # only the regions this plan exposes are (re)zeroed; see active_ranges
+        if rs:
+            torch._foreach_zero_([eng.grad_arena[lo:hi] for lo, hi in rs])
         plan.d_pred.copy_(d_pred)
         eng._launch(plan, "bwd")
         for p in plan.active_params:

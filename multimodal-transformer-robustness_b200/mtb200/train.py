@@ -87,6 +87,8 @@ def train_step(model, optimizer, criterion, inputs, target, hyp: HypParams, grad
     loss = criterion(preds, target)
     sample_next_config(model, hyp)           # config of step n+1 is drawn between fwd and bwd of step n
     loss.backward()
+    if hasattr(model, "prefetch_plan"):
+        model.prefetch_plan(inputs)          # next step's plan is built while the GPU runs this step's backward
     eng = getattr(model, "_engine", None)
     live = eng is not None and getattr(eng, "_grads_live", False)
     if grad_sync is not None:
