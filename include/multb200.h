@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MTB_ABI_VERSION 9
+#define MTB_ABI_VERSION 10
 #define MTB_MAX_GROUP 24
 
 /* Dropout RNG: Philox4x32-7.  Element `i` of a dropout site is kept iff
@@ -212,6 +212,32 @@ typedef struct {
   float scale; float p; mtb_rng rng;
 } mtb_attn_bwd_desc;
 int mtb_attn_bwd(const mtb_attn_bwd_desc* d, int n, void* stream);
+
+/* ---- fused gradient clip + Adam over the flat arenas --------------------------------
+ * Replaces `torch.nn.utils.clip_grad_norm_(model.parameters(), clip); optimizer.step()` of
+ * src/train.py:181-182 (optimizer = torch.optim.Adam, src/train.py:51) for parameters whose
+ * gradients live in one flat fp32 arena.  Static tables (built once per model) cut every
+ * parameter into chunks: chunk c covers `chunk_n[c]` elements of parameter `chunk_pid[c]`
+ * starting at `chunk_param[c]` (parameter storage) and at arena offset `chunk_off[c]` (same
+ * offset in grad / exp_avg / exp_avg_sq).  `active[pid] != 0` marks the parameters that
+ * received a gradient this step (torch skips `.grad is None`); only those are clipped and
+ * updated and only their `steps[pid]` counters advance (per-parameter bias correction, as
+ * torch keeps it).  scalars[0] = total gradient norm (what clip_grad_norm_ returns),
+ * scalars[1] = clip coefficient applied.  max_norm <= 0 disables clipping.  Three launches. */
+typedef struct {
+  float* const* chunk_param;     /* [n_chunks] device array of device pointers */
+  const int64_t* chunk_off;      /* [n_chunks] */
+  const int32_t* chunk_n;        /* [n_chunks] */
+  const int32_t* chunk_pid;      /* [n_chunks] */
+  const uint8_t* active;         /* [n_params] */
+  int32_t* steps;                /* [n_params] */
+  float* grad; float* exp_avg; float* exp_avg_sq;   /* flat arenas */
+  float* partial;                /* scratch [n_chunks] */
+  float* scalars;                /* out [2] */
+  int n_chunks, n_params;
+  float lr, beta1, beta2, eps, weight_decay, max_norm;
+} mtb_adam_desc;
+int mtb_adam_step(const mtb_adam_desc* d, void* stream);
 
 #ifdef __cplusplus
 }

@@ -4,13 +4,19 @@ set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 OUT="$HERE/lib"
-mkdir -p "$OUT" "$HERE/build"
+# MTB_VARIANT=trace builds lib/libmultb200_trace.so with in-kernel timestamps (tools/tc_trace.py)
+VARIANT="${MTB_VARIANT:-}"
+BUILD="$HERE/build${VARIANT:+/$VARIANT}"
+LIBNAME="libmultb200${VARIANT:+_$VARIANT}.so"
+EXTRA=()
+[[ "$VARIANT" == "trace" ]] && EXTRA+=(-DMTB_TC_TRACE)
+mkdir -p "$OUT" "$BUILD"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
-       --expt-relaxed-constexpr -Xptxas -v)
+       --expt-relaxed-constexpr -Xptxas -v "${EXTRA[@]}")
 objs=()
 pids=()
 for f in "$HERE"/csrc/*.cu; do
-  o="$HERE/build/$(basename "${f%.cu}").o"
+  o="$BUILD/$(basename "${f%.cu}").o"
   objs+=("$o")
   if [[ ! -f "$o" || "$f" -nt "$o" || "$HERE/csrc/common.cuh" -nt "$o" || "$HERE/../include/multb200.h" -nt "$o" ]]; then
     ( "$NVCC" "${FLAGS[@]}" -c "$f" -o "$o" > "$o.log" 2>&1 || { cat "$o.log"; exit 1; } ) &
@@ -18,5 +24,5 @@ for f in "$HERE"/csrc/*.cu; do
   fi
 done
 for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libmultb200.so" "${objs[@]}"
-echo "built $OUT/libmultb200.so"
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/$LIBNAME" "${objs[@]}"
+echo "built $OUT/$LIBNAME"

@@ -44,6 +44,8 @@ int preload_linear_tc();
 int preload_attention_simt();
 int preload_attention_tc();
 int attn_bwd_tc(const mtb_attn_bwd_desc* d, int n, cudaStream_t st);
+int adam_step(const mtb_adam_desc* d, cudaStream_t st);
+int preload_optim();
 
 }  // namespace mtb
 
@@ -60,7 +62,7 @@ int mtb_set_gemm_mode(int mode) {
 int mtb_get_gemm_mode(void) { return mtb::g_gemm_mode; }
 int mtb_preload(void) {
   const int bad = mtb::preload_elementwise() + mtb::preload_layernorm() + mtb::preload_linear_simt() + mtb::preload_linear_tc() +
-                  mtb::preload_attention_simt() + mtb::preload_attention_tc();
+                  mtb::preload_attention_simt() + mtb::preload_attention_tc() + mtb::preload_optim();
   MTB_CHECK(bad == 0, "preload: %d kernels failed to load (%s)", bad, cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
@@ -111,6 +113,11 @@ int mtb_attn_bwd(const mtb_attn_bwd_desc* d, int n, void* stream) {
               "attn_bwd: null operand in problem %d", i);
   if (mtb::g_attn_mode == 1 || (mtb::g_attn_mode < 0 && mtb::g_gemm_mode == 1)) return mtb::attn_bwd_tc(d, n, (cudaStream_t)stream);
   return mtb::attn_bwd_simt(d, n, (cudaStream_t)stream);
+}
+
+int mtb_adam_step(const mtb_adam_desc* d, void* stream) {
+  MTB_CHECK(d != nullptr, "adam_step: null descriptor");
+  return mtb::adam_step(d, (cudaStream_t)stream);
 }
 
 }  // extern "C"

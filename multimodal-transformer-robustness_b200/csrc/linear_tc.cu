@@ -39,7 +39,7 @@ constexpr int TC_MAXSEG = 16;
 // tensor maps {col_in_block, col_block, row_in_block, row_block}, tiles never straddle a block
 // and TMA zero-fills the tail of a partially covered block.  Unsegmented axes use one block.
 struct alignas(64) TcProblem {
-  CUtensorMap mapA, mapB;
+  CUtensorMap mapA, mapB, mapC;   // operands (loads) and the output (store / reduce-add)
   float* C; int64_t ldc;
   const float* bias;
   int I, J, R;         // compact sizes
@@ -133,14 +133,23 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, bool mn_major) {
   return d;
 }
 
+#ifdef MTB_TC_TRACE
+__device__ unsigned long long g_tc_trace[64];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TRACE(i) do { if (blockIdx.x == 0) { asm volatile("" ::: "memory"); g_tc_trace[(i)] = gtime(); asm volatile("" ::: "memory"); } } while (0)
+#else
+#define TRACE(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ TcGroup g) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float epi_tile[4][32 * 33];        // per-epilogue-warp transpose tile (padded: conflict free)
+  __shared__ __align__(16) float bias_s[256];   // bias of this tile's columns, staged while the main loop runs
 
+  if (threadIdx.x == 0) TRACE(0);
   int p = 0;
   while (p + 1 < g.n && (int)blockIdx.x >= g.start[p + 1]) ++p;
   const int local = blockIdx.x - g.start[p];
@@ -169,6 +178,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.mapB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.mapC) : "memory");
     for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     mbar_init(smem_u32(&tmem_full_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -181,6 +191,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_slot;
+  if (threadIdx.x == 0) TRACE(1);
 
   if (nkb > 0) {
     if (warp == 0) {
@@ -190,6 +201,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
           const int s = kb % TC_STAGES;
           const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+          if (kb < 16) TRACE(8 + kb);
           const uint32_t fb = smem_u32(&full_bar[s]);
           mbar_expect_tx(fb, (uint32_t)TC_A_BYTES + b_bytes);
           const uint32_t sa = smem_base + (uint32_t)s * TC_STAGE_BYTES;
@@ -226,6 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
           const int s = kb % TC_STAGES;
           const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
           mbar_wait(smem_u32(&full_bar[s]), ph);
+          if (kb < 16) TRACE(24 + kb);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_base + (uint32_t)s * TC_STAGE_BYTES;
           const uint32_t sb = sa + TC_A_BYTES;
@@ -241,40 +254,58 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
       }
     } else {
       // ===== epilogue warps: TMEM lane quadrant = warp_id % 4 =====
-      // tcgen05.ld hands every thread one accumulator ROW; storing that directly would make each
-      // warp-wide store touch 32 different cache lines.  Each 32 x 32 chunk is therefore transposed
-      // through a padded shared-memory tile so that one store instruction writes 32 consecutive
-      // floats of a single row (fully coalesced 128 B), for plain, accumulate and atomic epilogues.
+      // tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns per chunk).  Bias / ReLU /
+      // dropout are applied in registers, the 32 x 32 chunk is written to a 128B-swizzled staging tile in the
+      // (now idle) operand ring with conflict-free 128-bit stores, and one lane hands the tile to the TMA
+      // unit: a tensor store for plain outputs, a tensor reduce-add (performed in L2) for `+=` and split-K
+      // outputs.  TMA clips rows >= i_len and columns >= j_len, so partial tiles need no predicates.  Two
+      // staging tiles per warp keep one store in flight while the next chunk is prepared.
       const int q = warp & 3;
-      float* tp = &epi_tile[q][0];
       const int il_w = il0 + q * 32;                      // first row of this warp inside the block
-      const int il = il_w + lane;
-      const bool row_ok = il < P.i_len;
-      const int64_t row_c = (int64_t)is * P.i_len + il;   // compact row (dropout index)
-      mbar_wait(smem_u32(&tmem_full_bar), 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int i_len = P.i_len, j_len = P.j_len, BJ = P.BJ, Jtot = P.J, act = P.act, epi = P.epi;
+      const int64_t row_c = (int64_t)is * i_len + il_w + lane;   // compact row (dropout index)
+      const int cj = P.c_jseg[js], ci = P.c_iseg[is];
+      const float* brow = P.bias ? P.bias + (int64_t)P.bias_seg[js] * j_len : nullptr;
       const DropCtx dc = make_drop(P.rng, P.p);
-      float* cbase = P.C + ((int64_t)P.c_iseg[is] * P.i_len + il_w) * P.ldc + (int64_t)P.c_jseg[js] * P.j_len;
-      const float* brow = P.bias ? P.bias + (int64_t)P.bias_seg[js] * P.j_len : nullptr;
-      const int rows_here = min(32, P.i_len - il_w);      // warp-uniform; <= 0 when the whole warp is out of range
-      for (int c0 = 0; c0 < P.BJ; c0 += 32) {
-        if (jl0 + c0 >= P.j_len) break;                   // warp-uniform
+      const bool rows_any = il_w < i_len;                 // warp-uniform
+      // staging tiles per warp: a quarter of the operand ring, 4 KB each (2..8)
+      int nstage = (int)(((uint32_t)TC_STAGES * TC_STAGE_BYTES) >> 14);
+      nstage = nstage > 8 ? 8 : nstage;
+      const uint32_t stage0 = smem_base + (uint32_t)q * ((uint32_t)nstage << 12);
+      const uint32_t my_row = (uint32_t)lane * 128u;
+      const uint32_t sw = (uint32_t)(lane & 7);
+      if (brow) {
+        for (int c = threadIdx.x - 64; c < BJ; c += 128) bias_s[c] = jl0 + c < j_len ? __ldg(brow + jl0 + c) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");    // the four epilogue warps only
+      }
+      mbar_wait(smem_u32(&tmem_full_bar), 0);
+      if (threadIdx.x == 64) TRACE(2);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      int nbuf = 0;
+      for (int c0 = 0; c0 < BJ; c0 += 32) {
+        if (jl0 + c0 >= j_len || !rows_any) break;        // warp-uniform
         uint32_t v[32];
+        if (threadIdx.x == 64 && nbuf < 3) TRACE(40 + nbuf * 6);
         tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        if (rows_here <= 0) continue;
-        if (P.act == 1 && row_ok) {                       // bias + ReLU + dropout need the row-major view (Philox groups of 4 columns)
+        if (threadIdx.x == 64 && nbuf < 3) TRACE(41 + nbuf * 6);
+        const int jb = jl0 + c0;
+        if (brow) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {               // warp-wide broadcast reads
+            const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[c0 + c]);
+            v[c] = __float_as_uint(__uint_as_float(v[c]) + b4.x); v[c + 1] = __float_as_uint(__uint_as_float(v[c + 1]) + b4.y);
+            v[c + 2] = __float_as_uint(__uint_as_float(v[c + 2]) + b4.z); v[c + 3] = __float_as_uint(__uint_as_float(v[c + 3]) + b4.w);
+          }
+        }
+        if (act == 1) {                                   // ReLU + dropout (Philox groups of 4 consecutive columns)
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
-            const int j = jl0 + c0 + c;
+            const int j = jb + c;
             float o[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              o[e] = __uint_as_float(v[c + e]);
-              if (brow && j + e < P.j_len) o[e] += __ldg(brow + j + e);
-              o[e] = fmaxf(o[e], 0.f);
-            }
-            if (dc.on && j < P.j_len) {
-              const uint64_t idx = (uint64_t)row_c * (uint64_t)P.J + (uint64_t)((int64_t)js * P.j_len + j);
+            for (int e = 0; e < 4; ++e) o[e] = fmaxf(__uint_as_float(v[c + e]), 0.f);
+            if (dc.on && j < j_len) {
+              const uint64_t idx = (uint64_t)row_c * (uint64_t)Jtot + (uint64_t)((int64_t)js * j_len + j);
               if ((idx & 3) == 0) {
                 const uint4 r = drop_rand4(dc, idx >> 2);
                 o[0] = r.x >= dc.thr ? o[0] * dc.inv_keep : 0.f; o[1] = r.y >= dc.thr ? o[1] * dc.inv_keep : 0.f;
@@ -288,32 +319,61 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             for (int e = 0; e < 4; ++e) v[c + e] = __float_as_uint(o[e]);
           }
         }
-#pragma unroll
-        for (int c = 0; c < 32; ++c) tp[lane * 33 + c] = __uint_as_float(v[c]);   // bank (lane + c) % 32: conflict free
-        __syncwarp();
-        const int j = jl0 + c0 + lane;                    // my column in the transposed view
-        const bool col_ok = (j < P.j_len) && (c0 + lane < P.BJ);
-        const float bj = (P.act != 1 && brow && col_ok) ? __ldg(brow + j) : 0.f;
-        if (col_ok) {
-          float* cp = cbase + j;
-#pragma unroll 4
-          for (int r = 0; r < rows_here; ++r) {
-            const float val = tp[r * 33 + lane] + bj;
-            if (P.epi == 0) cp[(int64_t)r * P.ldc] = val;
-            else if (P.epi == 1) cp[(int64_t)r * P.ldc] += val;
-            else atomicAdd(cp + (int64_t)r * P.ldc, val);
+        if (threadIdx.x == 64 && nbuf < 3) TRACE(42 + nbuf * 6);
+        const uint32_t st = stage0 + (uint32_t)(nbuf % nstage) * 4096u;
+        if (nbuf >= nstage) {                             // the store issued `nstage` chunks ago must have finished reading this tile
+          if (lane == 0) {
+            switch (nstage) {                             // wait_group takes an immediate: allow nstage - 1 stores in flight
+              case 2: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+              case 3: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+              case 4: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+              case 5: asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory"); break;
+              case 6: asm volatile("cp.async.bulk.wait_group.read 5;" ::: "memory"); break;
+              case 7: asm volatile("cp.async.bulk.wait_group.read 6;" ::: "memory"); break;
+              default: asm volatile("cp.async.bulk.wait_group.read 7;" ::: "memory"); break;
+            }
           }
+          __syncwarp();
         }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)                       // 16-byte chunk c of row r lives at chunk (c ^ (r & 7)): SWIZZLE_128B
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + my_row + (((uint32_t)c ^ sw) << 4)),
+                       "r"(v[4 * c]), "r"(v[4 * c + 1]), "r"(v[4 * c + 2]), "r"(v[4 * c + 3]) : "memory");
+        if (threadIdx.x == 64 && nbuf < 3) TRACE(43 + nbuf * 6);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
+        if (threadIdx.x == 64 && nbuf < 3) TRACE(44 + nbuf * 6);
+        if (lane == 0) {
+          if (epi == 0)
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(&P.mapC), "r"(st), "r"(jb), "r"(cj), "r"(il_w), "r"(ci) : "memory");
+          else
+            asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(&P.mapC), "r"(st), "r"(jb), "r"(cj), "r"(il_w), "r"(ci) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (threadIdx.x == 64 && nbuf < 3) TRACE(45 + nbuf * 6);
+        ++nbuf;
       }
+      if (threadIdx.x == 64) TRACE(5);
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
     }
   }
+  if (threadIdx.x == 64) TRACE(3);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 0) TRACE(4);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TC_TMEM_COLS) : "memory");
   }
 }
+
+#ifdef MTB_TC_TRACE
+extern "C" int mtb_debug_tc_trace(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(unsigned long long) * 64);
+}
+#endif
 
 // ------------------------------------------------------------------ small helpers (backward)
 // scratch = dY * [Y > 0] * inv_keep  (ReLU + dropout backward applied once, feeds dgrad and wgrad) and, fused,
@@ -413,12 +473,13 @@ static bool make_map(CUtensorMap* m, const float* ptr, int64_t ld, int64_t clen,
 
 static bool tma_ok(const float* p, int64_t ld) { return p != nullptr && ((((uintptr_t)p) & 15) == 0) && (ld % 4 == 0) && ld > 0; }
 
+// Tile width along J: a multiple of 32 (the epilogue moves 32-column TMA boxes), chosen to minimise
+// tiles x (width + 128) -- the "+ 128" is the A tile every extra column tile has to load again.
 static int pick_bj(int J) {
   int best = 64, best_cost = 1 << 30;
-  const int cand[5] = {256, 224, 208, 128, 64};
-  for (int c : cand) {
+  for (int c = 256; c >= 32; c -= 32) {
     const int tiles = (J + c - 1) / c;
-    const int cost = tiles * c;                  // padded columns computed
+    const int cost = tiles * (c + 128);
     if (cost < best_cost) { best_cost = cost; best = c; }
   }
   return best;
@@ -485,14 +546,15 @@ int linear_fwd_tc(const mtb_linear_desc* d, int n, cudaStream_t st) {
   for (int i = 0; i < n; ++i) {
     const mtb_linear_desc& x = d[i];
     Axis an, ak;
-    bool ok = x.N >= 16 && x.K >= 8 && x.M >= 1 && tma_ok(x.X, x.ldx) && tma_ok(x.W, x.ldw) &&
+    bool ok = x.N >= 16 && x.K >= 8 && x.M >= 1 && tma_ok(x.X, x.ldx) && tma_ok(x.W, x.ldw) && tma_ok(x.Y, x.ldy) &&
               make_axis(an, x.N, x.row_idx, x.row_segs) && make_axis(ak, x.K, x.col_idx, x.col_segs);
     TcProblem& q = tc[ntc];
     if (ok) {
       q = TcProblem{};
       q.BJ = pick_bj(an.len);
       ok = make_map(&q.mapA, x.X, x.ldx, ak.len, ak.n, x.M, 1, TC_BR, TC_BI, false) &&
-           make_map(&q.mapB, x.W, x.ldw, ak.len, ak.nphys, an.len, an.nphys, TC_BR, q.BJ, false);
+           make_map(&q.mapB, x.W, x.ldw, ak.len, ak.nphys, an.len, an.nphys, TC_BR, q.BJ, false) &&
+           make_map(&q.mapC, x.Y, x.ldy, an.len, an.n, x.M, 1, 32, 32, false);
     }
     if (!ok) { rest[nrest++] = x; continue; }
     q.C = x.Y; q.ldc = x.ldy; q.bias = x.bias;
@@ -529,7 +591,8 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
       qd.BJ = round_bj_mn(pick_bj(ak.len));
       if (qd.BJ > 256) qd.BJ = 256;
       built = built && make_map(&qd.mapA, dYp, ldyp, an.len, an.n, x.M, 1, TC_BR, TC_BI, false) &&
-              make_map(&qd.mapB, x.W, x.ldw, ak.len, ak.nphys, an.len, an.nphys, 32, TC_BR, true);
+              make_map(&qd.mapB, x.W, x.ldw, ak.len, ak.nphys, an.len, an.nphys, 32, TC_BR, true) &&
+              make_map(&qd.mapC, x.dX, x.lddx, ak.len, ak.n, x.M, 1, 32, 32, false);
       qd.C = x.dX; qd.ldc = x.lddx; qd.bias = nullptr;
       qd.I = x.M; qd.J = x.K; qd.R = x.N;
       qd.i_len = x.M; qd.i_nseg = 1; qd.j_len = ak.len; qd.j_nseg = ak.n; qd.r_len = an.len; qd.r_nseg = an.n;
@@ -541,7 +604,8 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
       qw.BJ = round_bj_mn(pick_bj(ak.len));
       if (qw.BJ > 256) qw.BJ = 256;
       built = built && make_map(&qw.mapA, dYp, ldyp, an.len, an.n, x.M, 1, 32, TC_BR, true) &&
-              make_map(&qw.mapB, x.X, x.ldx, ak.len, ak.n, x.M, 1, 32, TC_BR, true);
+              make_map(&qw.mapB, x.X, x.ldx, ak.len, ak.n, x.M, 1, 32, TC_BR, true) &&
+              make_map(&qw.mapC, x.dW, x.ldw, ak.len, ak.nphys, an.len, an.nphys, 32, 32, false);
       qw.C = x.dW; qw.ldc = x.ldw; qw.bias = nullptr;
       qw.I = x.N; qw.J = x.K; qw.R = x.M;
       qw.i_len = an.len; qw.i_nseg = an.n; qw.j_len = ak.len; qw.j_nseg = ak.n; qw.r_len = x.M; qw.r_nseg = 1;

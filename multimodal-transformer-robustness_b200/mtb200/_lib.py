@@ -9,10 +9,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmultb200.so")
+LIB_PATH = os.environ.get("MTB_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libmultb200.so")   # MTB_LIB: instrumented debug builds
 
 MAX_GROUP = 24
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 class MtbError(RuntimeError):
@@ -90,6 +90,14 @@ class AttnBwdDesc(C.Structure):
                 ("H", C.c_int), ("hd", C.c_int), ("scale", C.c_float), ("p", C.c_float), ("rng", Rng)]
 
 
+class AdamDesc(C.Structure):
+    _fields_ = [("chunk_param", C.c_void_p), ("chunk_off", C.c_void_p), ("chunk_n", C.c_void_p), ("chunk_pid", C.c_void_p),
+                ("active", C.c_void_p), ("steps", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p),
+                ("exp_avg_sq", C.c_void_p), ("partial", C.c_void_p), ("scalars", C.c_void_p),
+                ("n_chunks", C.c_int), ("n_params", C.c_int), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("weight_decay", C.c_float), ("max_norm", C.c_float)]
+
+
 # name -> (argtypes, restype); every symbol include/multb200.h declares
 SYMBOLS = {
     "mtb_abi_version": ([], C.c_int),
@@ -111,6 +119,7 @@ SYMBOLS = {
     "mtb_linear_bwd": ([C.POINTER(LinearBwdDesc), C.c_int, C.c_void_p], C.c_int),
     "mtb_attn_fwd": ([C.POINTER(AttnDesc), C.c_int, C.c_void_p], C.c_int),
     "mtb_attn_bwd": ([C.POINTER(AttnBwdDesc), C.c_int, C.c_void_p], C.c_int),
+    "mtb_adam_step": ([C.POINTER(AdamDesc), C.c_void_p], C.c_int),
 }
 
 

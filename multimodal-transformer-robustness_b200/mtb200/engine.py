@@ -1063,10 +1063,15 @@ class _EngineFn(torch.autograd.Function):
             torch._foreach_zero_([eng.grad_arena[lo:hi] for lo, hi in rs])
         plan.d_pred.copy_(d_pred)
         eng._launch(plan, "bwd")
+        live = True
         for p in plan.active_params:
             g = eng.grad_views[id(p)]
-            p.grad = g if p.grad is None else p.grad + g
-        eng._grads_live = True
+            if p.grad is None:
+                p.grad = g
+            else:                                  # gradient accumulation over several backward passes:
+                p.grad = p.grad + g                # the sum lives outside the arena
+                live = False
+        eng._grads_live = live
         outs = []
         for i, shp in enumerate(ctx.shapes):
             ch = m.modality_list[i]

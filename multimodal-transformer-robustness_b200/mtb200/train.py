@@ -93,6 +93,9 @@ def train_step(model, optimizer, criterion, inputs, target, hyp: HypParams, grad
     live = eng is not None and getattr(eng, "_grads_live", False)
     if grad_sync is not None:
         grad_sync(eng if live else None)
+    if hasattr(optimizer, "step_clipped"):     # mtb200.optim.FlatAdam: clip + Adam fused over the flat arenas
+        optimizer.step_clipped(hyp.clip)
+        return loss
     if live:   # same result as torch's clip over the active set, computed on the flat gradient arena
         eng.clip_grad_norm_(hyp.clip, [p.grad for p in model._outside_engine_params() if p.grad is not None])
     else:

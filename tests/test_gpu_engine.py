@@ -224,3 +224,49 @@ def test_ea_branch_memoisation_is_results_identical():
         preds[memo] = [ea.get_acc(c) for c in cands]
     for a, b in zip(preds[False], preds[True]):
         assert abs(a - b) <= 1e-6 * max(1.0, abs(a)), (a, b)
+
+
+def test_flat_adam_equals_torch_clip_plus_adam():
+    """mtb200.optim.FlatAdam.step_clipped == clip_grad_norm_ + torch.optim.Adam.step on identical gradients, over
+    random sub-networks (parameters that did not run keep grad None: skipped, own step counters)."""
+    from mtb200 import ops
+    from mtb200.dynamic_models2 import DynamicMULTModel
+    from mtb200.optim import FlatAdam
+    from mtb200.train import ALL_POOL_3, HypParams, sample_next_config
+    torch.manual_seed(7)
+    ops.manual_seed(7)
+    ops.set_gemm_mode("fp32")
+    lens = (6, 14, 14)
+    m = DynamicMULTModel(origin_dimensions=[12, 7, 5], dimension=40, num_heads=8, head_dim=5, layers_single_attn=2,
+                         layers_hybrid_attn=2, layers_self_attn=1, attn_dropout=[0.1, 0.1, 0.0, 0.0], relu_dropout=0.1,
+                         res_dropout=0.3, out_dropout=0.1, embed_dropout=0.3, attn_mask=True, output_dim=1,
+                         modality_set=["l", "a", "v"], all_steps=False, front_end="conv1d").cuda().train()
+    hyp = HypParams(["l", "a", "v"], ALL_POOL_3, 2, 1, 2, 40, 8, 5, seq_lens=lens)
+    names = [k for k, _ in m.named_parameters()]
+    shadow = [p.detach().clone().requires_grad_(True) for p in m.parameters()]
+    ref = torch.optim.Adam(shadow, lr=3e-3)
+    opt = FlatAdam(m, lr=3e-3)
+    xs = [torch.randn(4, lens[i], d, device="cuda") for i, d in enumerate((12, 7, 5))]
+    y = torch.randn(4, 1, device="cuda")
+    sample_next_config(m, hyp)
+    seen = set()
+    for it in range(25):
+        m.zero_grad()
+        pred, _ = m(xs)
+        (torch.nn.functional.l1_loss(pred, y) * (30.0 if it % 2 else 0.3)).backward()   # clipped and unclipped steps
+        sample_next_config(m, hyp)
+        for s, p in zip(shadow, m.parameters()):
+            s.grad = None if p.grad is None else p.grad.detach().clone()
+        seen.add(tuple(p.grad is not None for p in m.parameters()))
+        n_ref = torch.nn.utils.clip_grad_norm_(shadow, 1.0)
+        ref.step()
+        n = opt.step_clipped(1.0)
+        assert abs(float(n) - float(n_ref)) <= 1e-5 * float(n_ref)
+        for k, s, p in zip(names, shadow, m.parameters()):
+            if s.grad is not None:
+                assert_rel(p.grad, s.grad, 1e-5, f"it {it} clipped grad {k}")
+            err = float((p.detach() - s.detach()).abs().max())
+            assert err <= 2e-6 + 1e-5 * float(s.detach().abs().max()), (it, k, err)
+    assert len(seen) >= 4          # several different active sets were exercised
+    st = opt.state_dict()
+    assert int(st["steps"].max()) <= 25 and int(st["steps"].min()) >= 0

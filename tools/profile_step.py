@@ -10,7 +10,8 @@ ops.set_gemm_mode("tf32")
 dev = torch.device("cuda")
 model = B.build_model().to(dev).train()
 hyp = B.make_hyp(B.SEQ)
-opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+from mtb200.optim import FlatAdam
+opt = FlatAdam(model, lr=1e-4)
 crit = torch.nn.L1Loss()
 gen = torch.Generator().manual_seed(1000)
 xs_h, y_h = B.synth_batch(16, B.SEQ, gen)
@@ -37,8 +38,8 @@ for it in range(N + 5):
         print(f"  it {it}: fwd {dt*1e3:8.2f} ms  launches fwd/bwd {pl.n_fwd_launches}/{pl.n_bwd_launches} hits {pl.hits} cfg {model.active_modality} {model.active_cross_output}", flush=True)
     t0 = time.perf_counter(); loss = crit(preds, y); sample_next_config(model, hyp); tick("loss+sample", t0)
     t0 = time.perf_counter(); loss.backward(); tick("backward", t0)
-    t0 = time.perf_counter(); torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0); tick("clip", t0)
-    t0 = time.perf_counter(); opt.step(); tick("adam", t0)
+    t0 = time.perf_counter(); model.prefetch_plan(xs); tick("prefetch_plan", t0)
+    t0 = time.perf_counter(); opt.step_clipped(1.0); tick("clip+adam", t0)
 torch.cuda.synchronize()
 tot = time.perf_counter() - tall
 print(f"steps {N}  total/step {tot/N*1e3:.2f} ms (with per-phase syncs)")
