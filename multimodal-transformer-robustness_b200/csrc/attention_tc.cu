@@ -106,11 +106,11 @@ __device__ __forceinline__ uint32_t idesc_tf32(int M, int N, bool a_mn, bool b_m
 // 4-byte cp.async (LDGSTS) with zero-fill straight into its swizzled slot: no registers, and ALL
 // copies of a tile are in flight at once -- one L2 latency per tile instead of one per element
 // (the first version's load -> convert -> store loop spent 70 % of its stall samples here).
-template <bool MNSW>
+template <bool MNSW, int NT = ATC_THREADS>
 __device__ __forceinline__ void stage_tile(uint8_t* tile, const float* base, int64_t ld, int B, int b, int h, int hd, int l0, int L,
                                            int rows) {
   const uint32_t tbase = a_smem_u32(tile);
-  for (int e = threadIdx.x; e < rows * HP; e += ATC_THREADS) {
+  for (int e = threadIdx.x; e < rows * HP; e += NT) {
     const int r = e >> 5, c = e & 31;
     const int l = l0 + r;
     const bool ok = (l < L) && (c < hd);
@@ -127,7 +127,108 @@ __device__ __forceinline__ void stage_wait() {
 
 __device__ __forceinline__ int a_round4(int x) { return (x + 3) & ~3; }
 
-__global__ void __launch_bounds__(ATC_THREADS) attn_fwd_tc_kernel(const __grid_constant__ Group<mtb_attn_desc> g) {
+// 256-thread staging with incremental addressing: thread t always moves head-dim column t & 31 of rows
+// (t >> 5) + 8 k, so the column test, the swizzle term (row & 7 / row & 3 are invariant under + 8) and the
+// source offset are computed once; each copy is then a compare, a select and a cp.async.
+template <bool MNSW>
+__device__ __forceinline__ void stage_rows256(uint8_t* tile, const float* base, int64_t ld, int B, int b, int h, int hd, int l0, int L,
+                                              int rows) {
+  const int c = threadIdx.x & 31, r0 = threadIdx.x >> 5;
+  const bool ok_c = c < hd;
+  const float* src = base + ((int64_t)(l0 + r0) * B + b) * ld + h * hd + c;
+  const int64_t sstep = (int64_t)8 * B * ld;
+  uint32_t dst = a_smem_u32(tile) + (MNSW ? swz128_32(r0, c * 4) : swz128(r0, c * 4));
+#pragma unroll 4
+  for (int r = r0; r < rows; r += 8) {
+    const bool ok = ok_c && (l0 + r < L);
+    const float* sp = ok ? src : base;
+    const int nbytes = ok ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(sp), "r"(nbytes) : "memory");
+    src += sstep;
+    dst += 8 * 128;
+  }
+}
+__device__ __forceinline__ void a_tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+#ifdef MTB_TC_TRACE
+__device__ unsigned long long g_attn_trace[128];
+__device__ __forceinline__ unsigned long long a_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) :: "memory"); return t; }
+#define ATRACE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (i) < 128) g_attn_trace[(i)] = a_gtime(); } while (0)
+extern "C" int mtb_debug_attn_trace(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_attn_trace, sizeof(unsigned long long) * 128);
+}
+#else
+#define ATRACE(i) do { } while (0)
+#endif
+
+// ---------------------------------------------------------------------------- forward
+// 256 threads: TWO threads per query row.  Warp w serves TMEM lane quadrant w & 3 (rows) and key-column half
+// w >> 2 of every 64-key tile; the two half-row threads run INDEPENDENT online softmaxes (own running max /
+// sum, own PV accumulator fed by its own K = 32 MMA group) and are merged once after the last tile, so no
+// per-tile exchange is needed.  The loop is software pipelined: K/V of tile t+1 are fetched (cp.async) and
+// S_{t+1} = Q K_{t+1}^T is issued while tile t is in its softmax / PV phase; one __syncthreads per tile.
+constexpr int AF_THREADS = 256;
+constexpr int ATC_FWD_SMEM = TQ * 128 + 4 * TK * 128 + (TK / 32) * TQ * 128 + 1024;
+
+__device__ __forceinline__ float fast_exp2(float x) {          // one MUFU.EX2; exp2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool MASKED>
+__device__ __forceinline__ void fwd_softmax_half(float (&s)[32], const float c2, const int i, const int jb, const int Lk, const int off,
+                                                 float& m_run, float& l_run, float& corr, const DropCtx& dc, const uint64_t idx0,
+                                                 uint8_t* prow_region, const int row) {
+  float mx = -CUDART_INF_F;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    if (MASKED) {
+      const int j = jb + c;
+      const bool open = (j < Lk) && (j - i < 1 + off);
+      s[c] = open ? s[c] * c2 : -CUDART_INF_F;
+    } else {
+      s[c] *= c2;
+    }
+    mx = fmaxf(mx, s[c]);
+  }
+  const float m_new = fmaxf(m_run, mx);
+  const bool dead = (m_new == -CUDART_INF_F);                 // no open column seen so far in my half
+  corr = dead ? 1.f : fast_exp2(m_run - m_new);
+  const float m_use = dead ? 0.f : m_new;
+  float rs = 0.f;
+#pragma unroll
+  for (int c4 = 0; c4 < 32; c4 += 4) {
+    float pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      pk[e] = fast_exp2(s[c4 + e] - m_use);                      // exp2(-inf) = 0 for masked entries
+      rs += pk[e];
+    }
+    if (dc.on) {
+      const uint4 r = drop_rand4(dc, (idx0 + (uint64_t)c4) >> 2);
+      pk[0] = r.x >= dc.thr ? pk[0] * dc.inv_keep : 0.f; pk[1] = r.y >= dc.thr ? pk[1] * dc.inv_keep : 0.f;
+      pk[2] = r.z >= dc.thr ? pk[2] * dc.inv_keep : 0.f; pk[3] = r.w >= dc.thr ? pk[3] * dc.inv_keep : 0.f;
+    }
+    *reinterpret_cast<float4*>(prow_region + swz128(row, c4 * 4)) =
+        make_float4(to_tf32(pk[0]), to_tf32(pk[1]), to_tf32(pk[2]), to_tf32(pk[3]));
+  }
+  l_run = l_run * corr + rs;
+  m_run = m_new;
+}
+
+__global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid_constant__ Group<mtb_attn_desc> g) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
@@ -135,19 +236,23 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_tc_kernel(const __grid_c
   const int pi = find_problem(g, blockIdx.x, local);
   const mtb_attn_desc& d = g.d[pi];
   const int qtiles = (d.Lq + TQ - 1) / TQ;
-  const int bh = local / qtiles, qt = local - bh * qtiles;
+  const int BH = d.B * d.H;
+  // heaviest query tiles (most key tiles under the causal-offset mask) get the lowest block indices
+  const int bh = local % BH, qt = qtiles - 1 - local / BH;
   const int b = bh / d.H, h = bh - b * d.H;
   const int i0 = qt * TQ;
-  const int off = abs(d.Lk - d.Lq);
-  const int Lk4 = a_round4(d.Lk);
+  const int Lq = d.Lq, Lk = d.Lk, hd = d.hd;
+  const int off = abs(Lk - Lq);
+  const int Lk4 = a_round4(Lk);
   const DropCtx dc = make_drop(d.rng, d.p);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane;                 // query row inside the tile = TMEM lane
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Qs = smem;                       // [128][128 B]  K-major
-  uint8_t* Ks = Qs + TQ * 128;              // [ 64][128 B]  K-major
-  uint8_t* Vs = Ks + TK * 128;              // [ 64][128 B]  MN-major (32 B-atom swizzle)
-  uint8_t* Ps = Vs + TK * 128;              // 2 regions of [128][128 B], K-major, 32 key columns each
+  uint8_t* KV = Qs + TQ * 128;              // 2 buffers x { K [64][128 B] K-major, V [64][128 B] MN-major (32 B-atom swizzle) }
+  uint8_t* Ps = KV + 4 * TK * 128;          // 2 regions of [128][128 B], K-major, 32 key columns each
 
   if (tid == 0) {
     a_mbar_init(a_smem_u32(&bar_s), 1);
@@ -158,110 +263,115 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_tc_kernel(const __grid_c
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(&tmem_slot)), "r"(ATC_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  stage_tile<false>(Qs, d.q, d.ldq, d.B, b, h, d.hd, i0, d.Lq, TQ);
+  const int i_last = min(Lq, i0 + TQ) - 1;
+  const int j_end = min(Lk, i_last + off + 1);
+  const int T = (j_end + TK - 1) / TK;
+  stage_tile<false, AF_THREADS>(Qs, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TQ);
+  stage_tile<false, AF_THREADS>(KV, d.k, d.ldk, d.B, b, h, hd, 0, Lk, TK);
+  stage_tile<true, AF_THREADS>(KV + TK * 128, d.v, d.ldv, d.B, b, h, hd, 0, Lk, TK);
   stage_wait();
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t t_s = tmem, t_o = tmem + 64;
-  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  const uint32_t t_s = tmem, t_o = tmem + 64;        // S: 64 columns; PV accumulators of the two halves: 32 + 32
+  const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+  const uint32_t id_s = idesc_tf32(TQ, TK, false, false);
+  const uint32_t id_o = idesc_tf32(TQ, HP, false, true);
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < HP / 8; ++k)
+      a_mma_tf32(t_s, desc_kmajor(a_smem_u32(Qs) + k * 32), desc_kmajor(a_smem_u32(KV) + k * 32), id_s, k != 0 ? 1u : 0u);
+    a_commit(a_smem_u32(&bar_s));
+  }
 
-  const int i = i0 + tid;                    // my query row
+  const int i = i0 + row;                    // my query row
+  const int irow = min(i, Lq - 1);
+  const float c2 = d.scale * 1.4426950408889634f;   // softmax in the exp2 domain
   float o[HP];
 #pragma unroll
   for (int c = 0; c < HP; ++c) o[c] = 0.f;
   float m_run = -CUDART_INF_F, l_run = 0.f;
+  uint8_t* my_p = Ps + half * (TQ * 128);
+  const uint64_t idx_row = ((uint64_t)((int64_t)bh * Lq + irow)) * (uint64_t)Lk4 + (uint64_t)(half * 32);
 
-  const int i_last = min(d.Lq, i0 + TQ) - 1;
-  const int j_end = min(d.Lk, i_last + off + 1);
-  const uint32_t id_s = idesc_tf32(TQ, TK, false, false);
-  const uint32_t id_o = idesc_tf32(TQ, HP, false, true);
-  uint32_t phase = 0;
-  for (int j0 = 0; j0 < j_end; j0 += TK, phase ^= 1u) {
-    stage_tile<false>(Ks, d.k, d.ldk, d.B, b, h, d.hd, j0, d.Lk, TK);
-    stage_tile<true>(Vs, d.v, d.ldv, d.B, b, h, d.hd, j0, d.Lk, TK);
-    stage_wait();
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < HP / 8; ++k)
-        a_mma_tf32(t_s, desc_kmajor(a_smem_u32(Qs) + k * 32), desc_kmajor(a_smem_u32(Ks) + k * 32), id_s, k != 0 ? 1u : 0u);
-      a_commit(a_smem_u32(&bar_s));
+  ATRACE(0);
+  for (int t = 0; t < T; ++t) {
+    const int j0 = t * TK;
+    const uint32_t ph = (uint32_t)t & 1u;
+    uint8_t* cur = KV + (t & 1) * (2 * TK * 128);
+    uint8_t* nxt = KV + ((t + 1) & 1) * (2 * TK * 128);
+    ATRACE(8 + t * 8 + 0);
+    if (t + 1 < T) {                         // prefetch the next key / value tile behind this tile's softmax
+      stage_tile<false, AF_THREADS>(nxt, d.k, d.ldk, d.B, b, h, hd, j0 + TK, Lk, TK);
+      stage_tile<true, AF_THREADS>(nxt + TK * 128, d.v, d.ldv, d.B, b, h, hd, j0 + TK, Lk, TK);
     }
-    a_mbar_wait(a_smem_u32(&bar_s), phase);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    ATRACE(8 + t * 8 + 1);
+    a_mbar_wait(a_smem_u32(&bar_s), ph);
     tc_fence_after();
-    // ---- softmax on my row -----------------------------------------------------------------
-    float s[TK];
-    {
-      float t0[32], t1[32];
-      a_tmem_ld32(t_s + lane_addr, t0);
-      a_tmem_ld32(t_s + lane_addr + 32, t1);
-#pragma unroll
-      for (int c = 0; c < 32; ++c) { s[c] = t0[c]; s[32 + c] = t1[c]; }
-    }
-    float mx = -CUDART_INF_F;
-#pragma unroll
-    for (int c = 0; c < TK; ++c) {
-      const int j = j0 + c;
-      const bool open = (j < d.Lk) && (j - i < 1 + off);
-      s[c] = open ? s[c] * d.scale : -CUDART_INF_F;
-      mx = fmaxf(mx, s[c]);
-    }
-    const float m_new = fmaxf(m_run, mx);
-    const float corr = (m_new == -CUDART_INF_F) ? 1.f : __expf(m_run - m_new);
-    float rs = 0.f;
-    const int irow = min(i, d.Lq - 1);
-#pragma unroll
-    for (int c4 = 0; c4 < TK; c4 += 4) {
-      float keep[4] = {dc.inv_keep, dc.inv_keep, dc.inv_keep, dc.inv_keep};
-      if (dc.on) {
-        const uint64_t idx = ((uint64_t)((int64_t)bh * d.Lq + irow)) * (uint64_t)Lk4 + (uint64_t)(j0 + c4);
-        const uint4 r = drop_rand4(dc, idx >> 2);
-        keep[0] = r.x >= dc.thr ? dc.inv_keep : 0.f; keep[1] = r.y >= dc.thr ? dc.inv_keep : 0.f;
-        keep[2] = r.z >= dc.thr ? dc.inv_keep : 0.f; keep[3] = r.w >= dc.thr ? dc.inv_keep : 0.f;
-      }
-      float pk[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float p = (s[c4 + e] == -CUDART_INF_F) ? 0.f : __expf(s[c4 + e] - m_new);
-        rs += p;
-        pk[e] = to_tf32(p * keep[e]);
-      }
-      uint8_t* region = Ps + (c4 >> 5) * (TQ * 128);
-      *reinterpret_cast<float4*>(region + swz128(tid, (c4 & 31) * 4)) = make_float4(pk[0], pk[1], pk[2], pk[3]);
-    }
-    l_run = l_run * corr + rs;
-    m_run = m_new;
-    fence_async_smem();
+    ATRACE(8 + t * 8 + 2);
+    float s[32];
+    a_tmem_ld32(t_s + lane_addr + half * 32, s);
     tc_fence_before();
-    __syncthreads();
+    float corr;
+    const bool tile_open = (j0 + TK <= Lk) && (j0 + TK - 1 - i0 < 1 + off);     // CTA-uniform: no entry of this tile is masked
+    if (tile_open)
+      fwd_softmax_half<false>(s, c2, i, j0 + half * 32, Lk, off, m_run, l_run, corr, dc, idx_row + (uint64_t)j0, my_p, row);
+    else
+      fwd_softmax_half<true>(s, c2, i, j0 + half * 32, Lk, off, m_run, l_run, corr, dc, idx_row + (uint64_t)j0, my_p, row);
+    ATRACE(8 + t * 8 + 3);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    fence_async_smem();
+    __syncthreads();                          // P written, S read by everyone, next K / V landed
+    ATRACE(8 + t * 8 + 4);
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
-      for (int kk = 0; kk < TK / 8; ++kk)
-        a_mma_tf32(t_o, desc_kmajor(a_smem_u32(Ps) + (kk >> 2) * (TQ * 128) + (kk & 3) * 32),
-                   desc_mnmajor(a_smem_u32(Vs) + kk * 1024), id_o, kk != 0 ? 1u : 0u);
+      for (int kk = 0; kk < TK / 8; ++kk)     // half hf = kk >> 2 accumulates P[:, 32 hf : 32 hf + 32] V[32 hf : 32 hf + 32, :] on its own
+        a_mma_tf32(t_o + (kk >> 2) * 32, desc_kmajor(a_smem_u32(Ps) + (kk >> 2) * (TQ * 128) + (kk & 3) * 32),
+                   desc_mnmajor(a_smem_u32(cur + TK * 128) + kk * 1024), id_o, (kk & 3) != 0 ? 1u : 0u);
       a_commit(a_smem_u32(&bar_o));
+      if (t + 1 < T) {
+#pragma unroll
+        for (int k = 0; k < HP / 8; ++k)
+          a_mma_tf32(t_s, desc_kmajor(a_smem_u32(Qs) + k * 32), desc_kmajor(a_smem_u32(nxt) + k * 32), id_s, k != 0 ? 1u : 0u);
+        a_commit(a_smem_u32(&bar_s));
+      }
     }
-    a_mbar_wait(a_smem_u32(&bar_o), phase);
+    a_mbar_wait(a_smem_u32(&bar_o), ph);
     tc_fence_after();
+    ATRACE(8 + t * 8 + 5);
     float pv[32];
-    a_tmem_ld32(t_o + lane_addr, pv);
+    a_tmem_ld32(t_o + lane_addr + half * 32, pv);
 #pragma unroll
     for (int c = 0; c < HP; ++c) o[c] = o[c] * corr + pv[c];
     tc_fence_before();          // my TMEM reads are done before the next tile's MMAs overwrite S / PV
+    ATRACE(8 + t * 8 + 6);
   }
-  if (i < d.Lq) {
-    const float inv = 1.f / l_run;
-    float* op = d.o + ((int64_t)i * d.B + b) * d.ldo + h * d.hd;
+  ATRACE(1);
+  // ---- merge the two half-row states: half 1 hands (m, l, o) to half 0 through the (idle) P region ----------
+  float* ex = reinterpret_cast<float*>(Ps);            // [128][36]
+  if (half == 1) {
+    float* e = ex + row * 36;
+    e[0] = m_run; e[1] = l_run;
+#pragma unroll
+    for (int c = 0; c < HP; c += 4) *reinterpret_cast<float4*>(e + 4 + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+  }
+  __syncthreads();
+  if (half == 0 && i < Lq) {
+    const float* e = ex + row * 36;
+    const float m_b = e[0], l_b = e[1];
+    const float m = fmaxf(m_run, m_b);                 // finite: key 0 is open for every row and belongs to half 0
+    const float wa = fast_exp2(m_run - m), wb = fast_exp2(m_b - m);
+    const float l = l_run * wa + l_b * wb;
+    const float inv = 1.f / l;
+    float* op = d.o + ((int64_t)i * d.B + b) * d.ldo + h * hd;
 #pragma unroll
     for (int c = 0; c < HP; ++c)
-      if (c < d.hd) op[c] = o[c] * inv;
-    if (d.lse) d.lse[(int64_t)bh * d.Lq + i] = m_run + logf(l_run);
+      if (c < hd) op[c] = (o[c] * wa + e[4 + c] * wb) * inv;
+    if (d.lse) d.lse[(int64_t)bh * Lq + i] = m * 0.6931471805599453f + logf(l);
   }
   tc_fence_before();
   __syncthreads();
@@ -272,12 +382,48 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_tc_kernel(const __grid_c
 
 
 // ============================================================================ backward: dQ (+ delta)
-// Per 64-row key tile: S = Q K^T and dP = dO V^T on the tensor core, dS = P * (dP * keep - delta) * scale
-// on CUDA cores, dQ += dS K on the tensor core (accumulating in TMEM across key tiles).
+// One CTA (256 threads) per (batch, head, 128-row query tile); two threads per query row (key-column halves of
+// every 64-key tile).  Per key tile: S = Q K^T and dP = dO V^T on the tensor core,
+// dS = P * (dP * keep - delta) * scale on CUDA cores, dQ += dS K on the tensor core (accumulating in TMEM).
+// Software pipelined like the forward kernel: K / V of tile t+1 are fetched and S_{t+1} / dP_{t+1} issued while
+// tile t is processed, the Philox keep bits of tile t+1 are drawn while the MMAs run; one __syncthreads per tile.
 constexpr int ATC_DQ_TMEM = 256;
-constexpr int ATC_DQ_SMEM = 2 * TQ * 128 + 3 * TK * 128 + (TK / 32) * TQ * 128 + 1024;
+constexpr int ATC_DQ_SMEM = 2 * TQ * 128 + 4 * TK * 128 + (TK / 32) * TQ * 128 + 1024;
+constexpr int AQ_THREADS = 256;
 
-__global__ void __launch_bounds__(ATC_THREADS) attn_bwd_dq_tc_kernel(const __grid_constant__ Group<mtb_attn_bwd_desc> g) {
+__device__ __forceinline__ uint32_t row_keep_bits32(const DropCtx& dc, uint64_t idx0) {   // keep bits of 32 consecutive columns
+  uint32_t bits = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const uint4 r = drop_rand4(dc, (idx0 >> 2) + (uint64_t)q);
+    bits |= ((r.x >= dc.thr ? 1u : 0u) | (r.y >= dc.thr ? 2u : 0u) | (r.z >= dc.thr ? 4u : 0u) | (r.w >= dc.thr ? 8u : 0u)) << (4 * q);
+  }
+  return bits;
+}
+
+template <bool MASKED>
+__device__ __forceinline__ void dq_math(const float (&s)[32], const float (&dp)[32], float lse2, float delta, uint32_t kbits, bool drop_on,
+                                        float inv_keep, float c2, float scale, int i, int jb, int Lk, int off, uint8_t* ds_region, int row) {
+#pragma unroll
+  for (int c4 = 0; c4 < 32; c4 += 4) {
+    float ds[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = c4 + e;
+      float p = fast_exp2(fmaf(s[c], c2, -lse2));
+      if (MASKED) {
+        const int j = jb + c;
+        const bool open = (j < Lk) && (j - i < 1 + off);
+        p = open ? p : 0.f;
+      }
+      const float keep = (!drop_on || ((kbits >> c) & 1u)) ? inv_keep : 0.f;
+      ds[e] = p * (dp[c] * keep - delta) * scale;
+    }
+    *reinterpret_cast<float4*>(ds_region + swz128(row, c4 * 4)) = make_float4(to_tf32(ds[0]), to_tf32(ds[1]), to_tf32(ds[2]), to_tf32(ds[3]));
+  }
+}
+
+__global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __grid_constant__ Group<mtb_attn_bwd_desc> g) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_a, bar_b;
   __shared__ uint32_t tmem_slot;
@@ -285,21 +431,25 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_dq_tc_kernel(const __gri
   const int pi = find_problem(g, blockIdx.x, local);
   const mtb_attn_bwd_desc& d = g.d[pi];
   const int qtiles = (d.Lq + TQ - 1) / TQ;
-  const int bh = local / qtiles, qt = local - bh * qtiles;
+  const int BH = d.B * d.H;
+  const int bh = local % BH, qt = qtiles - 1 - local / BH;      // heaviest query tiles first
   const int b = bh / d.H, h = bh - b * d.H;
   const int i0 = qt * TQ;
-  const int off = abs(d.Lk - d.Lq);
-  const int Lk4 = a_round4(d.Lk);
+  const int Lq = d.Lq, Lk = d.Lk, hd = d.hd;
+  const int off = abs(Lk - Lq);
+  const int Lk4 = a_round4(Lk);
   const DropCtx dc = make_drop(d.rng, d.p);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Qs = smem;                        // [128][128 B] K-major   (A of S)
   uint8_t* dOs = Qs + TQ * 128;              // [128][128 B] K-major   (A of dP)
   uint8_t* Ks = dOs + TQ * 128;              // [ 64][128 B] K-major   (B of S)
   uint8_t* Vs = Ks + TK * 128;               // [ 64][128 B] K-major   (B of dP)
-  uint8_t* Kmn = Vs + TK * 128;              // [ 64][128 B] MN-major  (B of dQ)
-  uint8_t* dSs = Kmn + TK * 128;             // 2 regions [128][128 B] K-major (A of dQ)
+  uint8_t* Kmn = Vs + TK * 128;              // 2 x [ 64][128 B] MN-major  (B of dQ), double buffered
+  uint8_t* dSs = Kmn + 2 * TK * 128;         // 2 regions [128][128 B] K-major (A of dQ)
 
   if (tid == 0) {
     a_mbar_init(a_smem_u32(&bar_a), 1);
@@ -310,100 +460,93 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_dq_tc_kernel(const __gri
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(&tmem_slot)), "r"(ATC_DQ_TMEM) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  stage_tile<false>(Qs, d.q, d.ldq, d.B, b, h, d.hd, i0, d.Lq, TQ);
-  stage_tile<false>(dOs, d.d_o, d.lddo, d.B, b, h, d.hd, i0, d.Lq, TQ);
-  const int i = i0 + tid;
-  float delta = 0.f, lse = 0.f;
-  if (i < d.Lq) {
-    const float* op = d.o + ((int64_t)i * d.B + b) * d.ldo + h * d.hd;
-    const float* gp = d.d_o + ((int64_t)i * d.B + b) * d.lddo + h * d.hd;
-    for (int c = 0; c < d.hd; ++c) delta = fmaf(op[c], gp[c], delta);
-    lse = d.lse[(int64_t)bh * d.Lq + i];
-    d.delta[(int64_t)bh * d.Lq + i] = delta;
+  stage_rows256<false>(Qs, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TQ);
+  stage_rows256<false>(dOs, d.d_o, d.lddo, d.B, b, h, hd, i0, Lq, TQ);
+  stage_rows256<false>(Ks, d.k, d.ldk, d.B, b, h, hd, 0, Lk, TK);
+  stage_rows256<false>(Vs, d.v, d.ldv, d.B, b, h, hd, 0, Lk, TK);
+  stage_rows256<true>(Kmn, d.k, d.ldk, d.B, b, h, hd, 0, Lk, TK);
+  const int i = i0 + row;
+  const int irow = min(i, Lq - 1);
+  float delta = 0.f, lse2 = 0.f;
+  if (i < Lq) {
+    const float* op = d.o + ((int64_t)i * d.B + b) * d.ldo + h * hd;
+    const float* gp = d.d_o + ((int64_t)i * d.B + b) * d.lddo + h * hd;
+    for (int c = 0; c < hd; ++c) delta = fmaf(op[c], gp[c], delta);
+    lse2 = d.lse[(int64_t)bh * Lq + i] * 1.4426950408889634f;
+    if (half == 0) d.delta[(int64_t)bh * Lq + i] = delta;
   }
   stage_wait();
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t t_s = tmem, t_dp = tmem + 64, t_dq = tmem + 128;
-  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-  const int i_last = min(d.Lq, i0 + TQ) - 1;
-  const int j_end = min(d.Lk, i_last + off + 1);
+  const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+  const int i_last = min(Lq, i0 + TQ) - 1;
+  const int j_end = min(Lk, i_last + off + 1);
+  const int T = (j_end + TK - 1) / TK;
   const uint32_t id_s = idesc_tf32(TQ, TK, false, false);
   const uint32_t id_q = idesc_tf32(TQ, HP, false, true);
-  const int irow = min(i, d.Lq - 1);
-  uint32_t phase = 0;
-  int tile = 0;
-  for (int j0 = 0; j0 < j_end; j0 += TK, phase ^= 1u, ++tile) {
-    stage_tile<false>(Ks, d.k, d.ldk, d.B, b, h, d.hd, j0, d.Lk, TK);
-    stage_tile<false>(Vs, d.v, d.ldv, d.B, b, h, d.hd, j0, d.Lk, TK);
-    stage_tile<true>(Kmn, d.k, d.ldk, d.B, b, h, d.hd, j0, d.Lk, TK);
-    stage_wait();
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
+  const float c2 = d.scale * 1.4426950408889634f;
+  auto issue_s = [&]() {                      // S and dP of the tile currently in Ks / Vs
 #pragma unroll
-      for (int k = 0; k < HP / 8; ++k)
-        a_mma_tf32(t_s, desc_kmajor(a_smem_u32(Qs) + k * 32), desc_kmajor(a_smem_u32(Ks) + k * 32), id_s, k != 0 ? 1u : 0u);
+    for (int k = 0; k < HP / 8; ++k)
+      a_mma_tf32(t_s, desc_kmajor(a_smem_u32(Qs) + k * 32), desc_kmajor(a_smem_u32(Ks) + k * 32), id_s, k != 0 ? 1u : 0u);
 #pragma unroll
-      for (int k = 0; k < HP / 8; ++k)
-        a_mma_tf32(t_dp, desc_kmajor(a_smem_u32(dOs) + k * 32), desc_kmajor(a_smem_u32(Vs) + k * 32), id_s, k != 0 ? 1u : 0u);
-      a_commit(a_smem_u32(&bar_a));
-    }
-    a_mbar_wait(a_smem_u32(&bar_a), phase);
+    for (int k = 0; k < HP / 8; ++k)
+      a_mma_tf32(t_dp, desc_kmajor(a_smem_u32(dOs) + k * 32), desc_kmajor(a_smem_u32(Vs) + k * 32), id_s, k != 0 ? 1u : 0u);
+    a_commit(a_smem_u32(&bar_a));
+  };
+  if (tid == 0) issue_s();
+  const uint64_t idx_row = ((uint64_t)((int64_t)bh * Lq + irow)) * (uint64_t)Lk4 + (uint64_t)(half * 32);
+  uint32_t kbits = dc.on ? row_keep_bits32(dc, idx_row) : 0u;
+  uint8_t* my_ds = dSs + half * (TQ * 128);
+
+  for (int t = 0; t < T; ++t) {
+    const int j0 = t * TK;
+    const uint32_t ph = (uint32_t)t & 1u;
+    a_mbar_wait(a_smem_u32(&bar_a), ph);       // S_t, dP_t ready; Ks / Vs and (dQ_{t-1} retired) the other Kmn buffer are free
     tc_fence_after();
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float s[32], dp[32];
-      a_tmem_ld32(t_s + lane_addr + half * 32, s);
-      a_tmem_ld32(t_dp + lane_addr + half * 32, dp);
-#pragma unroll
-      for (int c4 = 0; c4 < 32; c4 += 4) {
-        const int jb = j0 + half * 32 + c4;
-        float keep[4] = {dc.inv_keep, dc.inv_keep, dc.inv_keep, dc.inv_keep};
-        if (dc.on) {
-          const uint64_t idx = ((uint64_t)((int64_t)bh * d.Lq + irow)) * (uint64_t)Lk4 + (uint64_t)jb;
-          const uint4 r = drop_rand4(dc, idx >> 2);
-          keep[0] = r.x >= dc.thr ? dc.inv_keep : 0.f; keep[1] = r.y >= dc.thr ? dc.inv_keep : 0.f;
-          keep[2] = r.z >= dc.thr ? dc.inv_keep : 0.f; keep[3] = r.w >= dc.thr ? dc.inv_keep : 0.f;
-        }
-        float ds[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = jb + e;
-          const bool open = (i < d.Lq) && (j < d.Lk) && (j - i < 1 + off);
-          const float p = open ? __expf(s[c4 + e] * d.scale - lse) : 0.f;
-          ds[e] = to_tf32(p * (dp[c4 + e] * keep[e] - delta) * d.scale);
-        }
-        *reinterpret_cast<float4*>(dSs + half * (TQ * 128) + swz128(tid, c4 * 4)) = make_float4(ds[0], ds[1], ds[2], ds[3]);
-      }
+    if (t + 1 < T) {
+      stage_rows256<false>(Ks, d.k, d.ldk, d.B, b, h, hd, j0 + TK, Lk, TK);
+      stage_rows256<false>(Vs, d.v, d.ldv, d.B, b, h, hd, j0 + TK, Lk, TK);
+      stage_rows256<true>(Kmn + ((t + 1) & 1) * (TK * 128), d.k, d.ldk, d.B, b, h, hd, j0 + TK, Lk, TK);
     }
-    fence_async_smem();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    float s[32], dp[32];
+    a_tmem_ld32(t_s + lane_addr + half * 32, s);
+    a_tmem_ld32(t_dp + lane_addr + half * 32, dp);
     tc_fence_before();
-    __syncthreads();
+    const bool tile_open = (j0 + TK <= Lk) && (j0 + TK - 1 - i0 < 1 + off);      // CTA-uniform
+    if (tile_open)
+      dq_math<false>(s, dp, lse2, delta, kbits, dc.on, dc.inv_keep, c2, d.scale, i, j0 + half * 32, Lk, off, my_ds, row);
+    else
+      dq_math<true>(s, dp, lse2, delta, kbits, dc.on, dc.inv_keep, c2, d.scale, i, j0 + half * 32, Lk, off, my_ds, row);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    fence_async_smem();
+    __syncthreads();                           // dS written, S / dP read by everyone, next K / V / Kmn landed
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
       for (int kk = 0; kk < TK / 8; ++kk)
         a_mma_tf32(t_dq, desc_kmajor(a_smem_u32(dSs) + (kk >> 2) * (TQ * 128) + (kk & 3) * 32),
-                   desc_mnmajor(a_smem_u32(Kmn) + kk * 1024), id_q, (tile | kk) != 0 ? 1u : 0u);
+                   desc_mnmajor(a_smem_u32(Kmn + (t & 1) * (TK * 128)) + kk * 1024), id_q, (t | kk) != 0 ? 1u : 0u);
       a_commit(a_smem_u32(&bar_b));
+      if (t + 1 < T) issue_s();
     }
-    a_mbar_wait(a_smem_u32(&bar_b), phase);       // operands free again; accumulator keeps growing in TMEM
-    tc_fence_after();
-    tc_fence_before();
+    if (dc.on && t + 1 < T) kbits = row_keep_bits32(dc, idx_row + (uint64_t)(j0 + TK));   // drawn while the MMAs run
   }
   {
-    float dq[32];
-    a_tmem_ld32(t_dq + lane_addr, dq);
-    if (i < d.Lq) {
-      float* qp = d.dq + ((int64_t)i * d.B + b) * d.lddq + h * d.hd;
+    a_mbar_wait(a_smem_u32(&bar_b), (uint32_t)(T - 1) & 1u);
+    tc_fence_after();
+    float dq[16];
+    a_tmem_ld16(t_dq + lane_addr + half * 16, dq);
+    if (i < Lq) {
+      float* qp = d.dq + ((int64_t)i * d.B + b) * d.lddq + h * hd + half * 16;
 #pragma unroll
-      for (int c = 0; c < HP; ++c)
-        if (c < d.hd) qp[c] = dq[c];
+      for (int c = 0; c < 16; ++c)
+        if (half * 16 + c < hd) qp[c] = dq[c];
     }
   }
   tc_fence_before();
@@ -414,40 +557,87 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_dq_tc_kernel(const __gri
 }
 
 // ============================================================================ backward: dK, dV
-// One CTA per (batch, head, 128-row KEY tile); thread t owns key row t.  Per 32-row query tile:
-// S^T = K Q^T and dP^T = V dO^T on the tensor core, P~^T and dS^T on CUDA cores, then
-// dV += P~^T dO and dK += dS^T Q on the tensor core (accumulators stay in TMEM).
+// One CTA (256 threads) per (batch, head, 128-row KEY tile).  Warp w serves TMEM lane quadrant w & 3 (key rows)
+// and query-column half w >> 2 of every 32-row query tile.  Per query tile: S^T = K Q^T and dP^T = V dO^T on
+// the tensor core, P~^T and dS^T on CUDA cores, then dV += P~^T dO and dK += dS^T Q on the tensor core
+// (accumulators stay in TMEM).  Software pipelined: the four operand tiles of query tile t+1 are fetched
+// (cp.async, double buffered) and its S^T / dP^T MMAs are issued while tile t is processed; the Philox keep
+// bits of tile t+1 are drawn while the MMAs run; one __syncthreads per tile.
 constexpr int TI = 32;
 constexpr int ATC_DKV_TMEM = 128;
-constexpr int ATC_DKV_SMEM = 2 * TQ * 128 + 4 * TI * 128 + 2 * TQ * 128 + 2 * TI * 4 + 1024;
+constexpr int ATC_DKV_SMEM = 2 * TQ * 128 + 2 * 4 * TI * 128 + 2 * TQ * 128 + 1024;
+constexpr int AB_THREADS = 256;
 
-__global__ void __launch_bounds__(ATC_THREADS) attn_bwd_dkv_tc_kernel(const __grid_constant__ Group<mtb_attn_bwd_desc> g) {
+// keep bits of the 16 query columns (half * 16 ..) x my key row for the query tile starting at i0.  The 4 lanes
+// of a quad own key rows j..j+3 = one Philox group per query row: lane k draws the groups of query rows
+// 4 q + k (q = 0..3), packs the 16 compare results, and the quad exchanges the packed words (4 shuffles).
+__device__ __forceinline__ void dkv_keep_bits(const DropCtx& dc, int bh, int Lq, int Lk4, int i0h, int jrow, uint32_t (&w)[4]) {
+  const int lane = threadIdx.x & 31, k = lane & 3;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int iq = min(i0h + 4 * q + k, Lq - 1);
+    const uint64_t idx = ((uint64_t)((int64_t)bh * Lq + iq)) * (uint64_t)Lk4 + (uint64_t)(jrow & ~3);
+    const uint4 r = drop_rand4(dc, idx >> 2);
+    bits |= ((r.x >= dc.thr ? 1u : 0u) | (r.y >= dc.thr ? 2u : 0u) | (r.z >= dc.thr ? 4u : 0u) | (r.w >= dc.thr ? 8u : 0u)) << (4 * q);
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) w[m] = __shfl_sync(0xffffffffu, bits, (lane & ~3) + m) >> k;   // bit 4 q of w[m]: query 4 q + m
+}
+
+template <bool MASKED>
+__device__ __forceinline__ void dkv_math(const float (&st)[16], const float (&dpt)[16], const float* lse2, const float* dlt,
+                                         const uint32_t (&kw)[4], bool drop_on, float inv_keep, float c2, float scale, int i0h, int j,
+                                         int Lq, int Lk, int off, uint8_t* pt_row, uint8_t* ds_row, int row, int cb0) {
+#pragma unroll
+  for (int c4 = 0; c4 < 16; c4 += 4) {
+    float pt[4], ds[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = c4 + e;
+      float p = fast_exp2(fmaf(st[c], c2, -lse2[c]));
+      if (MASKED) {
+        const int ii = i0h + c;
+        const bool open = (ii < Lq) && (j < Lk) && (j - ii < 1 + off);
+        p = open ? p : 0.f;
+      }
+      const float keep = (!drop_on || ((kw[e] >> c4) & 1u)) ? inv_keep : 0.f;      // query c = 4 (c4 / 4) + e -> word e, bit c4
+      pt[e] = p * keep;
+      ds[e] = p * (dpt[c] * keep - dlt[c]) * scale;
+    }
+    *reinterpret_cast<float4*>(pt_row + swz128(row, (cb0 + c4) * 4)) = make_float4(to_tf32(pt[0]), to_tf32(pt[1]), to_tf32(pt[2]), to_tf32(pt[3]));
+    *reinterpret_cast<float4*>(ds_row + swz128(row, (cb0 + c4) * 4)) = make_float4(to_tf32(ds[0]), to_tf32(ds[1]), to_tf32(ds[2]), to_tf32(ds[3]));
+  }
+}
+
+__global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __grid_constant__ Group<mtb_attn_bwd_desc> g) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_a, bar_b;
   __shared__ uint32_t tmem_slot;
+  __shared__ float col_lse2[2][TI], col_delta[2][TI];
   int local;
   const int pi = find_problem(g, blockIdx.x, local);
   const mtb_attn_bwd_desc& d = g.d[pi];
   const int ktiles = (d.Lk + TQ - 1) / TQ;
-  const int bh = local / ktiles, kt = local - bh * ktiles;
+  const int BH = d.B * d.H;
+  const int bh = local % BH, kt = local / BH;       // key tile 0 sees every query tile: heaviest first
   const int b = bh / d.H, h = bh - b * d.H;
   const int j0 = kt * TQ;
-  const int off = abs(d.Lk - d.Lq);
-  const int Lk4 = a_round4(d.Lk);
+  const int Lq = d.Lq, Lk = d.Lk, hd = d.hd;
+  const int off = abs(Lk - Lq);
+  const int Lk4 = a_round4(Lk);
   const DropCtx dc = make_drop(d.rng, d.p);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane;                 // key row inside the tile = TMEM lane
+  const int j = j0 + row;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Ks = smem;                        // [128][128 B] K-major (A of S^T)
   uint8_t* Vs = Ks + TQ * 128;               // [128][128 B] K-major (A of dP^T)
-  uint8_t* Qs = Vs + TQ * 128;               // [ 32][128 B] K-major (B of S^T)
-  uint8_t* dOs = Qs + TI * 128;              // [ 32][128 B] K-major (B of dP^T)
-  uint8_t* Qmn = dOs + TI * 128;             // [ 32][128 B] MN-major (B of dK)
-  uint8_t* dOmn = Qmn + TI * 128;            // [ 32][128 B] MN-major (B of dV)
-  uint8_t* PTs = dOmn + TI * 128;            // [128][128 B] K-major (A of dV), 32 query columns
+  uint8_t* QB = Vs + TQ * 128;               // 2 buffers x { Q K-major (B of S^T), dO K-major (B of dP^T), Q MN-major (B of dK), dO MN-major (B of dV) }, [32][128 B] each
+  uint8_t* PTs = QB + 2 * 4 * TI * 128;      // [128][128 B] K-major (A of dV), 32 query columns
   uint8_t* dSTs = PTs + TQ * 128;            // [128][128 B] K-major (A of dK)
-  float* col_lse = reinterpret_cast<float*>(dSTs + TQ * 128);
-  float* col_delta = col_lse + TI;
 
   if (tid == 0) {
     a_mbar_init(a_smem_u32(&bar_a), 1);
@@ -458,120 +648,103 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_dkv_tc_kernel(const __gr
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(&tmem_slot)), "r"(ATC_DKV_TMEM) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  stage_tile<false>(Ks, d.k, d.ldk, d.B, b, h, d.hd, j0, d.Lk, TQ);
-  stage_tile<false>(Vs, d.v, d.ldv, d.B, b, h, d.hd, j0, d.Lk, TQ);
+  const int i_begin = (max(0, j0 - off) / TI) * TI;
+  const int T = (Lq - i_begin + TI - 1) / TI;
+  const float c2 = d.scale * 1.4426950408889634f;
+  auto stage_q = [&](int t) {                 // operand tiles + per-query-row lse / delta of query tile t
+    uint8_t* qb = QB + (t & 1) * (4 * TI * 128);
+    const int i0 = i_begin + t * TI;
+    stage_rows256<false>(qb, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TI);
+    stage_rows256<false>(qb + TI * 128, d.d_o, d.lddo, d.B, b, h, hd, i0, Lq, TI);
+    stage_rows256<true>(qb + 2 * TI * 128, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TI);
+    stage_rows256<true>(qb + 3 * TI * 128, d.d_o, d.lddo, d.B, b, h, hd, i0, Lq, TI);
+    if (tid < TI) {
+      const int ii = i0 + tid;
+      col_lse2[t & 1][tid] = ii < Lq ? d.lse[(int64_t)bh * Lq + ii] * 1.4426950408889634f : 0.f;
+      col_delta[t & 1][tid] = ii < Lq ? d.delta[(int64_t)bh * Lq + ii] : 0.f;
+    }
+  };
+  stage_rows256<false>(Ks, d.k, d.ldk, d.B, b, h, hd, j0, Lk, TQ);
+  stage_rows256<false>(Vs, d.v, d.ldv, d.B, b, h, hd, j0, Lk, TQ);
+  if (T > 0) stage_q(0);
   stage_wait();
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t t_st = tmem, t_dpt = tmem + 32, t_dv = tmem + 64, t_dk = tmem + 96;
-  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-  const int j = j0 + tid;                     // my key row
+  const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
   const uint32_t id_s = idesc_tf32(TQ, TI, false, false);
   const uint32_t id_o = idesc_tf32(TQ, HP, false, true);
-  const int i_first = max(0, j0 - off);
-  uint32_t phase = 0;
-  int tile = 0;
-  for (int i0 = (i_first / TI) * TI; i0 < d.Lq; i0 += TI, phase ^= 1u, ++tile) {
-    stage_tile<false>(Qs, d.q, d.ldq, d.B, b, h, d.hd, i0, d.Lq, TI);
-    stage_tile<false>(dOs, d.d_o, d.lddo, d.B, b, h, d.hd, i0, d.Lq, TI);
-    stage_tile<true>(Qmn, d.q, d.ldq, d.B, b, h, d.hd, i0, d.Lq, TI);
-    stage_tile<true>(dOmn, d.d_o, d.lddo, d.B, b, h, d.hd, i0, d.Lq, TI);
-    if (tid < TI) {
-      const int ii = i0 + tid;
-      col_lse[tid] = ii < d.Lq ? d.lse[(int64_t)bh * d.Lq + ii] : 0.f;
-      col_delta[tid] = ii < d.Lq ? d.delta[(int64_t)bh * d.Lq + ii] : 0.f;
-    }
-    stage_wait();
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
+  auto issue_s = [&](int t) {                 // S^T_t and dP^T_t
+    uint8_t* qb = QB + (t & 1) * (4 * TI * 128);
 #pragma unroll
-      for (int k = 0; k < HP / 8; ++k)
-        a_mma_tf32(t_st, desc_kmajor(a_smem_u32(Ks) + k * 32), desc_kmajor(a_smem_u32(Qs) + k * 32), id_s, k != 0 ? 1u : 0u);
+    for (int k = 0; k < HP / 8; ++k)
+      a_mma_tf32(t_st, desc_kmajor(a_smem_u32(Ks) + k * 32), desc_kmajor(a_smem_u32(qb) + k * 32), id_s, k != 0 ? 1u : 0u);
 #pragma unroll
-      for (int k = 0; k < HP / 8; ++k)
-        a_mma_tf32(t_dpt, desc_kmajor(a_smem_u32(Vs) + k * 32), desc_kmajor(a_smem_u32(dOs) + k * 32), id_s, k != 0 ? 1u : 0u);
-      a_commit(a_smem_u32(&bar_a));
-    }
-    a_mbar_wait(a_smem_u32(&bar_a), phase);
+    for (int k = 0; k < HP / 8; ++k)
+      a_mma_tf32(t_dpt, desc_kmajor(a_smem_u32(Vs) + k * 32), desc_kmajor(a_smem_u32(qb + TI * 128) + k * 32), id_s, k != 0 ? 1u : 0u);
+    a_commit(a_smem_u32(&bar_a));
+  };
+  if (tid == 0 && T > 0) issue_s(0);
+  uint32_t kw[4] = {0u, 0u, 0u, 0u};
+  if (dc.on && T > 0) dkv_keep_bits(dc, bh, Lq, Lk4, i_begin + half * 16, j, kw);
+
+  for (int t = 0; t < T; ++t) {
+    const int i0 = i_begin + t * TI;
+    const uint32_t ph = (uint32_t)t & 1u;
+    uint8_t* qb = QB + (t & 1) * (4 * TI * 128);
+    a_mbar_wait(a_smem_u32(&bar_a), ph);       // S^T_t, dP^T_t ready; every MMA issued before them (dV / dK of tile t-1) has retired too
     tc_fence_after();
-    {
-      float st[32], dpt[32];
-      a_tmem_ld32(t_st + lane_addr, st);
-      a_tmem_ld32(t_dpt + lane_addr, dpt);
-#pragma unroll
-      for (int c4 = 0; c4 < TI; c4 += 4) {
-        // Dropout keeps for 4 query columns x my key row.  The 4 lanes of a quad own key rows j..j+3 =
-        // one Philox group per query row, so lane k of the quad draws the group of query row c4+k and
-        // the quad exchanges components by shuffle: 1/4 Philox call + 4 shuffles per element group
-        // instead of one call per element.
-        float keep[4] = {dc.inv_keep, dc.inv_keep, dc.inv_keep, dc.inv_keep};
-        if (dc.on) {
-          const int lane = tid & 31;
-          const int iq = min(i0 + c4 + (lane & 3), d.Lq - 1);
-          const uint64_t idx = ((uint64_t)((int64_t)bh * d.Lq + iq)) * (uint64_t)Lk4 + (uint64_t)((j0 + tid) & ~3);
-          const uint4 r = drop_rand4(dc, idx >> 2);
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const int srcl = (lane & ~3) + m;
-            const uint32_t rx = __shfl_sync(0xffffffffu, r.x, srcl), ry = __shfl_sync(0xffffffffu, r.y, srcl);
-            const uint32_t rz = __shfl_sync(0xffffffffu, r.z, srcl), rw = __shfl_sync(0xffffffffu, r.w, srcl);
-            const int k = lane & 3;
-            const uint32_t mine = k == 0 ? rx : k == 1 ? ry : k == 2 ? rz : rw;
-            keep[m] = mine >= dc.thr ? dc.inv_keep : 0.f;
-          }
-        }
-        float pt[4], ds[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int ii = i0 + c4 + e;
-          const bool open = (ii < d.Lq) && (j < d.Lk) && (j - ii < 1 + off);
-          const float p = open ? __expf(st[c4 + e] * d.scale - col_lse[c4 + e]) : 0.f;
-          pt[e] = p * keep[e];
-          ds[e] = p * (dpt[c4 + e] * keep[e] - col_delta[c4 + e]) * d.scale;
-        }
-        *reinterpret_cast<float4*>(PTs + swz128(tid, c4 * 4)) = make_float4(pt[0], pt[1], pt[2], pt[3]);
-        *reinterpret_cast<float4*>(dSTs + swz128(tid, c4 * 4)) = make_float4(ds[0], ds[1], ds[2], ds[3]);
-      }
-    }
-    fence_async_smem();
+    if (t + 1 < T) stage_q(t + 1);             // the other buffer was last read by tile t-1's MMAs
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    float st[16], dpt[16];
+    a_tmem_ld16(t_st + lane_addr + half * 16, st);
+    a_tmem_ld16(t_dpt + lane_addr + half * 16, dpt);
     tc_fence_before();
-    __syncthreads();
+    const bool tile_open = (i0 + TI <= Lq) && (j0 + TQ <= Lk) && (j0 + TQ - 1 - i0 < 1 + off);   // CTA-uniform
+    const float* l2 = &col_lse2[t & 1][half * 16];
+    const float* dl = &col_delta[t & 1][half * 16];
+    if (tile_open)
+      dkv_math<false>(st, dpt, l2, dl, kw, dc.on, dc.inv_keep, c2, d.scale, i0 + half * 16, j, Lq, Lk, off, PTs, dSTs, row, half * 16);
+    else
+      dkv_math<true>(st, dpt, l2, dl, kw, dc.on, dc.inv_keep, c2, d.scale, i0 + half * 16, j, Lq, Lk, off, PTs, dSTs, row, half * 16);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    fence_async_smem();
+    __syncthreads();                           // P~^T / dS^T written, S^T / dP^T read by everyone, next operand tiles landed
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
       for (int kk = 0; kk < TI / 8; ++kk)
-        a_mma_tf32(t_dv, desc_kmajor(a_smem_u32(PTs) + kk * 32), desc_mnmajor(a_smem_u32(dOmn) + kk * 1024), id_o,
-                   (tile | kk) != 0 ? 1u : 0u);
+        a_mma_tf32(t_dv, desc_kmajor(a_smem_u32(PTs) + kk * 32), desc_mnmajor(a_smem_u32(qb + 3 * TI * 128) + kk * 1024), id_o,
+                   (t | kk) != 0 ? 1u : 0u);
 #pragma unroll
       for (int kk = 0; kk < TI / 8; ++kk)
-        a_mma_tf32(t_dk, desc_kmajor(a_smem_u32(dSTs) + kk * 32), desc_mnmajor(a_smem_u32(Qmn) + kk * 1024), id_o,
-                   (tile | kk) != 0 ? 1u : 0u);
+        a_mma_tf32(t_dk, desc_kmajor(a_smem_u32(dSTs) + kk * 32), desc_mnmajor(a_smem_u32(qb + 2 * TI * 128) + kk * 1024), id_o,
+                   (t | kk) != 0 ? 1u : 0u);
       a_commit(a_smem_u32(&bar_b));
+      if (t + 1 < T) issue_s(t + 1);
     }
-    a_mbar_wait(a_smem_u32(&bar_b), phase);
-    tc_fence_after();
-    tc_fence_before();
+    if (dc.on && t + 1 < T) dkv_keep_bits(dc, bh, Lq, Lk4, i0 + TI + half * 16, j, kw);   // drawn while the MMAs run
   }
   {
-    float dv[32], dk[32];
-    if (tile > 0) {
-      a_tmem_ld32(t_dv + lane_addr, dv);
-      a_tmem_ld32(t_dk + lane_addr, dk);
+    float dv[16], dk[16];
+    if (T > 0) {
+      a_mbar_wait(a_smem_u32(&bar_b), (uint32_t)(T - 1) & 1u);
+      tc_fence_after();
+      a_tmem_ld16(t_dv + lane_addr + half * 16, dv);
+      a_tmem_ld16(t_dk + lane_addr + half * 16, dk);
     } else {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) { dv[c] = 0.f; dk[c] = 0.f; }
+      for (int c = 0; c < 16; ++c) { dv[c] = 0.f; dk[c] = 0.f; }
     }
-    if (j < d.Lk) {
-      float* kp = d.dk + ((int64_t)j * d.B + b) * d.lddk + h * d.hd;
-      float* vp = d.dv + ((int64_t)j * d.B + b) * d.lddv + h * d.hd;
+    if (j < Lk) {
+      float* kp = d.dk + ((int64_t)j * d.B + b) * d.lddk + h * hd + half * 16;
+      float* vp = d.dv + ((int64_t)j * d.B + b) * d.lddv + h * hd + half * 16;
 #pragma unroll
-      for (int c = 0; c < HP; ++c)
-        if (c < d.hd) { kp[c] = dk[c]; vp[c] = dv[c]; }
+      for (int c = 0; c < 16; ++c)
+        if (half * 16 + c < hd) { kp[c] = dk[c]; vp[c] = dv[c]; }
     }
   }
   tc_fence_before();
@@ -580,8 +753,6 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_dkv_tc_kernel(const __gr
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ATC_DKV_TMEM) : "memory");
   }
 }
-
-constexpr int ATC_FWD_SMEM = TQ * 128 + 2 * TK * 128 + (TK / 32) * TQ * 128 + 1024;
 
 int attn_fwd_simt(const mtb_attn_desc* d, int n, cudaStream_t st);
 
@@ -604,7 +775,7 @@ int attn_fwd_tc(const mtb_attn_desc* d, int n, cudaStream_t st) {
       MTB_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_FWD_SMEM));
       attr = true;
     }
-    attn_fwd_tc_kernel<<<tot, ATC_THREADS, ATC_FWD_SMEM, st>>>(g);
+    attn_fwd_tc_kernel<<<tot, AF_THREADS, ATC_FWD_SMEM, st>>>(g);
     mtb::note_launch();
     MTB_CUDA(cudaGetLastError());
   }
@@ -635,10 +806,10 @@ int attn_bwd_tc(const mtb_attn_bwd_desc* d, int n, cudaStream_t st) {
       MTB_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_DKV_SMEM));
       attr = true;
     }
-    attn_bwd_dq_tc_kernel<<<totq, ATC_THREADS, ATC_DQ_SMEM, st>>>(gq);
+    attn_bwd_dq_tc_kernel<<<totq, AQ_THREADS, ATC_DQ_SMEM, st>>>(gq);
     mtb::note_launch();
     MTB_CUDA(cudaGetLastError());
-    attn_bwd_dkv_tc_kernel<<<totk, ATC_THREADS, ATC_DKV_SMEM, st>>>(gk);
+    attn_bwd_dkv_tc_kernel<<<totk, AB_THREADS, ATC_DKV_SMEM, st>>>(gk);
     mtb::note_launch();
     MTB_CUDA(cudaGetLastError());
   }
