@@ -48,8 +48,9 @@ class DynamicMultiheadAttention(MultiheadAttention):
                            self.active_head_dim, self.attn_dropout, self.training, idx)
 
     def set_active(self, active_head_dim, active_num_heads):
-        self.active_head_dim = active_head_dim
-        self.active_num_heads = active_num_heads
+        d = self.__dict__            # plain ints: same effect as attribute assignment, without nn.Module.__setattr__'s checks
+        d["active_head_dim"] = active_head_dim
+        d["active_num_heads"] = active_num_heads
 
     def get_active_subnet(self, active_head_dim, active_num_heads, active_mask=[None]):
         """Static MultiheadAttention holding copies of the active weights (reference :122-163)."""

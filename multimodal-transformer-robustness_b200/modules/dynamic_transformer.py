@@ -125,10 +125,11 @@ class DynamicTransformerEncoder(TransformerEncoder):
 
     def set_active(self, active_layer_num, active_dimension, active_head_num, active_head_dim):
         """Only the first ``active_layer_num`` layers are updated (reference :104-107)."""
-        self.active_layer_num = active_layer_num
-        for i in range(self.active_layer_num):
-            self.layers[i].set_active(active_dimension=active_dimension, active_head_dim=active_head_dim,
-                                      active_head_num=active_head_num)
+        self.__dict__["active_layer_num"] = active_layer_num
+        layers = self.__dict__.get("_ll") or self.layers        # _ll: plain-list mirror installed by the plan executor
+        for i in range(active_layer_num):
+            layers[i].set_active(active_dimension=active_dimension, active_head_dim=active_head_dim,
+                                 active_head_num=active_head_num)
 
 
 class DynamicTransformerEncoderLayer(TransformerEncoderLayer):
@@ -200,5 +201,5 @@ class DynamicTransformerEncoderLayer(TransformerEncoderLayer):
         return x
 
     def set_active(self, active_dimension, active_head_num, active_head_dim):
-        self.active_hidden_out_fc1 = active_dimension
+        self.__dict__["active_hidden_out_fc1"] = active_dimension
         self.self_attn.set_active(active_head_dim=active_head_dim, active_num_heads=active_head_num)

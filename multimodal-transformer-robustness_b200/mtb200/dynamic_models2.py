@@ -306,9 +306,8 @@ class DynamicMULTModel(nn.Module):
                    active_dimension, active_head_num, active_head_dim, active_modality: list, active_cross: list,
                    active_cross_output: list):
         """reference :391-418"""
-        self.active_modality = active_modality
-        self.active_cross_output = active_cross_output
-        self.active_cross = active_cross
+        d = self.__dict__
+        d["active_modality"], d["active_cross_output"], d["active_cross"] = active_modality, active_cross_output, active_cross
         for i, k in enumerate(self.trans_mems0.keys()):
             self.trans_mems0[k].set_active(active_layer_num=active_single_attn_layer_num[i], active_dimension=active_dimension,
                                            active_head_num=active_head_num, active_head_dim=active_head_dim)

@@ -218,7 +218,7 @@ class PlanBuilder:
                 ln = e.enc.layer_norm.ln
                 dst = e.out
             else:
-                ln = e.enc.layers[0].layer_norms[0].ln
+                ln = e.enc._ll[0]._lns[0].ln
                 dst = A.mat(Tq, e.E)
             st = (A.alloc(Tq), A.alloc(Tq)) if ng else (None, None)
             e.saved["ln_first"] = (ln, dst, st)
@@ -238,7 +238,7 @@ class PlanBuilder:
                 if not e.cross:
                     continue
                 S = e.saved["layers"][i]
-                ln = e.enc.layers[i].layer_norms[0].ln
+                ln = e.enc._ll[i]._lns[0].ln
                 Tk = e.Lk * e.B
                 for nm in ("k", "v"):
                     dst = A.mat(Tk, e.E)
@@ -251,7 +251,7 @@ class PlanBuilder:
             descs = []
             for e in act:
                 S = e.saved["layers"][i]
-                sa = e.enc.layers[i].self_attn
+                sa = e.enc._ll[i].self_attn
                 H, hd, aH, ahd = sa.num_heads, sa.head_dim, sa.active_num_heads, sa.active_head_dim
                 assert aH == H and ahd == hd, "engine path requires full heads (the trainer always uses them)"
                 D = H * hd
@@ -277,7 +277,7 @@ class PlanBuilder:
             descs = []
             for e in act:
                 S = e.saved["layers"][i]
-                sa = e.enc.layers[i].self_attn
+                sa = e.enc._ll[i].self_attn
                 H, hd = sa.num_heads, sa.head_dim
                 D = H * hd
                 Tq = e.Lq * e.B
@@ -300,7 +300,7 @@ class PlanBuilder:
             descs = []
             for e in act:
                 S = e.saved["layers"][i]
-                sa = e.enc.layers[i].self_attn
+                sa = e.enc._ll[i].self_attn
                 D = sa.num_heads * sa.head_dim
                 Tq = e.Lq * e.B
                 a = A.mat(Tq, e.E)
@@ -314,8 +314,8 @@ class PlanBuilder:
             descs = []
             for e in act:
                 S = e.saved["layers"][i]
-                layer = e.enc.layers[i]
-                ln = layer.layer_norms[1].ln
+                layer = e.enc._ll[i]
+                ln = layer._lns[1].ln
                 Tq = e.Lq * e.B
                 x_prev = e.saved["x0"] if i == 0 else e.saved["layers"][i - 1]["x2"]
                 x1, xn1 = A.mat(Tq, e.E), A.mat(Tq, e.E)
@@ -331,7 +331,7 @@ class PlanBuilder:
             d1, d2 = [], []
             for e in act:
                 S = e.saved["layers"][i]
-                layer = e.enc.layers[i]
+                layer = e.enc._ll[i]
                 Fa = min(layer.active_hidden_out_fc1, layer.fc1.dim_out)
                 Tq = e.Lq * e.B
                 h, y = A.mat(Tq, Fa), A.mat(Tq, e.E)
@@ -351,10 +351,10 @@ class PlanBuilder:
             descs = []
             for e in act:
                 S = e.saved["layers"][i]
-                layer = e.enc.layers[i]
+                layer = e.enc._ll[i]
                 Tq = e.Lq * e.B
                 last = (i + 1 == e.n_layers)
-                ln = e.enc.layer_norm.ln if last else e.enc.layers[i + 1].layer_norms[0].ln
+                ln = e.enc.layer_norm.ln if last else e.enc._ll[i + 1]._lns[0].ln
                 x2 = A.mat(Tq, e.E)
                 dst = e.out if last else A.mat(Tq, e.E)
                 st = (A.alloc(Tq), A.alloc(Tq)) if ng else (None, None)
@@ -403,13 +403,13 @@ class PlanBuilder:
                                           S["st2"][0], S["st2"][1], ln.weight.data_ptr(), e.mask.idx.data_ptr() if masked else None,
                                           g_x1r.ptr, g_x1r.ld, g_y.ptr, g_y.ld,
                                           None if masked else self.grad_ptr(ln.weight), None if masked else self.grad_ptr(ln.bias),
-                                          Tq, e.E, pr, r, self.grad_ptr(e.enc.layers[i].fc2.l.bias)))      # fc2 bias grad = colsum(g_y), fused
+                                          Tq, e.E, pr, r, self.grad_ptr(e.enc._ll[i].fc2.l.bias)))      # fc2 bias grad = colsum(g_y), fused
             self.emit(self.bwd, lib.mtb_resln_bwd, ResLnBwdDesc, descs, f"res_ln2_bwd[{i}]")
             # g'. fc2 backward, f'. fc1 backward
             d2, d1 = [], []
             for e in act:
                 S = e.saved["layers"][i]
-                layer = e.enc.layers[i]
+                layer = e.enc._ll[i]
                 Tq, Fa = e.Lq * e.B, S["F"]
                 W1, b1, W2, b2 = layer.fc1.l.weight, layer.fc1.l.bias, layer.fc2.l.weight, layer.fc2.l.bias
                 midx = e.mask.idx.data_ptr() if e.mask is not None else None
@@ -441,8 +441,8 @@ class PlanBuilder:
             descs = []
             for e in act:
                 S = e.saved["layers"][i]
-                layer = e.enc.layers[i]
-                ln = layer.layer_norms[1].ln
+                layer = e.enc._ll[i]
+                ln = layer._lns[1].ln
                 Tq = e.Lq * e.B
                 masked = e.mask is not None
                 g_xr, g_a = A.mat(Tq, e.E), A.mat(Tq, e.E)
@@ -459,7 +459,7 @@ class PlanBuilder:
             descs = []
             for e in act:
                 S = e.saved["layers"][i]
-                sa = e.enc.layers[i].self_attn
+                sa = e.enc._ll[i].self_attn
                 D = sa.num_heads * sa.head_dim
                 Tq = e.Lq * e.B
                 Wo, bo = sa.out_proj.weight, sa.out_proj.bias
@@ -480,7 +480,7 @@ class PlanBuilder:
             descs = []
             for e in act:
                 S = e.saved["layers"][i]
-                sa = e.enc.layers[i].self_attn
+                sa = e.enc._ll[i].self_attn
                 H, hd = sa.num_heads, sa.head_dim
                 D = H * hd
                 Tq, Tk = e.Lq * e.B, e.Lk * e.B
@@ -502,7 +502,7 @@ class PlanBuilder:
             descs = []
             for e in act:
                 S = e.saved["layers"][i]
-                sa = e.enc.layers[i].self_attn
+                sa = e.enc._ll[i].self_attn
                 D = sa.num_heads * sa.head_dim
                 Tq, Tk = e.Lq * e.B, e.Lk * e.B
                 W, b = sa.in_proj_weight, sa.in_proj_bias
@@ -544,7 +544,7 @@ class PlanBuilder:
                 if not e.cross:
                     continue
                 S = e.saved["layers"][i]
-                ln = e.enc.layers[i].layer_norms[0].ln
+                ln = e.enc._ll[i]._lns[0].ln
                 Tk = e.Lk * e.B
                 for nm in ("k", "v"):
                     acc = e.saved["g_x" + nm]
@@ -652,6 +652,26 @@ def _run(ops, stream: int):
                 raise _lib.MtbError(f"{op.what} failed ({rc}): {lib.mtb_last_error().decode()}")
 
 
+def _install_fast_attrs(model):
+    """Plan construction reads thousands of sub-module / parameter attributes per step.  nn.Module resolves those
+    through __getattr__ (a Python-level fallback, ~1 us each) and ModuleList indexing is slower still.  Mirror
+    every sub-module and parameter into the instance __dict__ (found by the normal attribute lookup, and removed
+    again by nn.Module.__setattr__ should the attribute ever be re-assigned) and keep plain-list mirrors of the
+    layer lists.  Purely an access-path shortcut: _modules / _parameters stay authoritative."""
+    for m in model.modules():
+        d = m.__dict__
+        for name, sub in m._modules.items():
+            if sub is not None and name.isidentifier():
+                d[name] = sub
+        for name, p in m._parameters.items():
+            if p is not None:
+                d[name] = p
+        if isinstance(getattr(m, "layers", None), torch.nn.ModuleList):
+            d["_ll"] = list(m.layers)
+        if isinstance(getattr(m, "layer_norms", None), torch.nn.ModuleList):
+            d["_lns"] = list(m.layer_norms)
+
+
 class Engine:
     """Owns the arenas and the plan cache of one DynamicMULTModel on one device."""
 
@@ -669,6 +689,7 @@ class Engine:
         self.graph_after = graph_after
         self.plans: Dict[tuple, Plan] = {}
         self.arena: Optional[Arena] = None
+        _install_fast_attrs(model)
         self.params = [p for p in model.parameters()]
         total = 0
         self._grad_off = {}
