@@ -8,6 +8,7 @@
 //   dgrad : i=m j=k r=n   A=dY'        B=W[row(n), col(k)] (j<->r)  C=dX
 //   wgrad : i=n j=k r=m   A=dY'^T      B=X^T                        C=dW[row(n), col(k)] (atomic, split-R)
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace mtb {
 
@@ -147,6 +148,12 @@ int launch_gemm_simt(const GemmP* p, int n, cudaStream_t st) {
         tot += ((p[off + i].I + GB - 1) / GB) * ((p[off + i].J + GB - 1) / GB) * p[off + i].splits;
     }
     g.start[m] = tot;
+    static const bool dbg = getenv("MTB_TC_DEBUG") != nullptr;
+    if (dbg) {
+      fprintf(stderr, "[simt] grid %d:", tot);
+      for (int i = 0; i < m; ++i) fprintf(stderr, " {I %d J %d R %d sp %d epi %d act %d}", g.d[i].I, g.d[i].J, g.d[i].R, g.d[i].splits, g.d[i].epi, g.d[i].act);
+      fprintf(stderr, "\n");
+    }
     if (tot > 0) {
       gemm_simt_kernel<<<tot, G_THREADS, 0, st>>>(g);
       mtb::note_launch();

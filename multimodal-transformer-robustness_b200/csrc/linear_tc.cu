@@ -15,6 +15,7 @@
 // Partial tiles (M % 128, N % BJ, K % 32 such as K = 200) rely on TMA zero fill.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace mtb {
 
@@ -25,7 +26,7 @@ constexpr int TC_BI = 128;                 // UMMA M
 constexpr int TC_BR = 32;                  // reduction elements per stage (32 fp32 = one 128 B swizzle row)
 constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BI * 128;    // 16 KB
-constexpr int TC_SMEM_BUDGET = 92 * 1024;  // <= half an SM's shared memory: two CTAs per SM overlap
+constexpr int TC_SMEM_BUDGET = 100 * 1024;  // <= half an SM's shared memory: two CTAs per SM overlap
                                            // one tile's epilogue with the other's main loop
 constexpr int TC_THREADS = 192;
 constexpr int TC_TMEM_COLS = 256;
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
       const int i_len = P.i_len, j_len = P.j_len, BJ = P.BJ, Jtot = P.J, act = P.act, epi = P.epi;
       const int64_t row_c = (int64_t)is * i_len + il_w + lane;   // compact row (dropout index)
       const int cj = P.c_jseg[js], ci = P.c_iseg[is];
-      const float* brow = P.bias ? P.bias + (int64_t)P.bias_seg[js] * j_len : nullptr;
+      const float* brow = (P.bias && split == 0) ? P.bias + (int64_t)P.bias_seg[js] * j_len : nullptr;   // split-K: bias once
       const DropCtx dc = make_drop(P.rng, P.p);
       const bool rows_any = il_w < i_len;                 // warp-uniform
       // staging tiles per warp: a quarter of the operand ring, 4 KB each (2..8)
@@ -484,6 +485,29 @@ static int pick_bj(int J) {
   }
   return best;
 }
+// Launches that cannot fill the GPU with full-width tiles (<= one CTA per SM) are pure latency: halve the tile
+// width so twice as many CTAs each run a shorter main loop (3-stage ring at <= 128 columns) and epilogue.
+static int pick_bj_narrow(int J) {
+  const int bj = pick_bj(J);
+  if (J < 128) return bj;
+  const int tiles = (J + bj - 1) / bj;
+  int nb = ((J + 2 * tiles - 1) / (2 * tiles) + 31) / 32 * 32;
+  return nb < 64 ? 64 : nb;
+}
+static int tiles_of(int I, int i_n, int J, int j_n, int bj) { return ((I + TC_BI - 1) / TC_BI) * i_n * ((J + bj - 1) / bj) * j_n; }
+// split of a long reduction across CTAs when a problem has too few tiles to matter (reduce-add epilogue)
+static int pick_splitk(int tiles, int nkb) {
+  if (tiles > 16 || nkb < 24) return 1;
+  int s = nkb / 6;
+  const int cap = sm_count() / tiles;
+  if (s > cap) s = cap;
+  return s < 1 ? 1 : s;
+}
+static int zero_matrix(float* p, int64_t ld, int rows, int cols, cudaStream_t st) {
+  if (ld == cols) { MTB_CUDA(cudaMemsetAsync(p, 0, (size_t)rows * cols * sizeof(float), st)); }
+  else { MTB_CUDA(cudaMemset2DAsync(p, (size_t)ld * sizeof(float), 0, (size_t)cols * sizeof(float), (size_t)rows, st)); }
+  return 0;
+}
 static int round_bj_mn(int bj) { return ((bj + 31) / 32) * 32; }   // MN-major B tiles are loaded in 32-wide boxes
 
 // axis description derived from the public descriptor
@@ -513,7 +537,7 @@ static bool g_attr_done = false;
 static int launch_tc(const TcProblem* probs, int n, cudaStream_t st) {
   if (n == 0) return 0;
   if (!g_attr_done) {
-    MTB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (TC_A_BYTES + 256 * 128) + 2048));
+    MTB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048));
     g_attr_done = true;
   }
   TcGroup g;
@@ -533,6 +557,14 @@ static int launch_tc(const TcProblem* probs, int n, cudaStream_t st) {
   }
   g.start[n] = tot;
   if (tot == 0) return 0;
+  static const bool dbg = getenv("MTB_TC_DEBUG") != nullptr;
+  if (dbg) {
+    fprintf(stderr, "[tc] grid %d:", tot);
+    for (int i = 0; i < n; ++i)
+      fprintf(stderr, " {I %d J %d R %d BJ %d st %d sp %d mn %d%d epi %d}", g.d[i].I, g.d[i].J, g.d[i].R, g.d[i].BJ, g.d[i].stages, g.d[i].splits,
+              g.d[i].a_mn, g.d[i].b_mn, g.d[i].epi);
+    fprintf(stderr, "\n");
+  }
   gemm_tc_kernel<<<tot, TC_THREADS, smem, st>>>(g);
   mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
@@ -542,16 +574,25 @@ static int launch_tc(const TcProblem* probs, int n, cudaStream_t st) {
 int linear_fwd_tc(const mtb_linear_desc* d, int n, cudaStream_t st) {
   TcProblem tc[MTB_MAX_GROUP];
   mtb_linear_desc rest[MTB_MAX_GROUP];
-  int ntc = 0, nrest = 0;
+  Axis ans[MTB_MAX_GROUP], aks[MTB_MAX_GROUP];
+  bool oks[MTB_MAX_GROUP];
+  int ntc = 0, nrest = 0, full_tiles = 0;
   for (int i = 0; i < n; ++i) {
     const mtb_linear_desc& x = d[i];
-    Axis an, ak;
-    bool ok = x.N >= 16 && x.K >= 8 && x.M >= 1 && tma_ok(x.X, x.ldx) && tma_ok(x.W, x.ldw) && tma_ok(x.Y, x.ldy) &&
-              make_axis(an, x.N, x.row_idx, x.row_segs) && make_axis(ak, x.K, x.col_idx, x.col_segs);
+    oks[i] = x.N >= 16 && x.K >= 8 && x.M >= 1 && tma_ok(x.X, x.ldx) && tma_ok(x.W, x.ldw) && tma_ok(x.Y, x.ldy) &&
+             make_axis(ans[i], x.N, x.row_idx, x.row_segs) && make_axis(aks[i], x.K, x.col_idx, x.col_segs);
+    if (oks[i]) full_tiles += tiles_of(x.M, 1, ans[i].len, ans[i].n, pick_bj(ans[i].len));
+  }
+  const bool narrow = full_tiles <= sm_count();
+  for (int i = 0; i < n; ++i) {
+    const mtb_linear_desc& x = d[i];
+    const Axis& an = ans[i];
+    const Axis& ak = aks[i];
+    bool ok = oks[i];
     TcProblem& q = tc[ntc];
     if (ok) {
       q = TcProblem{};
-      q.BJ = pick_bj(an.len);
+      q.BJ = narrow ? pick_bj_narrow(an.len) : pick_bj(an.len);
       ok = make_map(&q.mapA, x.X, x.ldx, ak.len, ak.n, x.M, 1, TC_BR, TC_BI, false) &&
            make_map(&q.mapB, x.W, x.ldw, ak.len, ak.nphys, an.len, an.nphys, TC_BR, q.BJ, false) &&
            make_map(&q.mapC, x.Y, x.ldy, an.len, an.n, x.M, 1, 32, 32, false);
@@ -564,6 +605,14 @@ int linear_fwd_tc(const mtb_linear_desc* d, int n, cudaStream_t st) {
     ident(q.c_iseg, 1); ident(q.c_jseg, an.n); copy_phys(q.bias_seg, an);
     q.a_mn = 0; q.b_mn = 0; q.splits = 1; q.epi = 0;
     q.act = x.act; q.p = x.p; q.rng = x.rng;
+    if (x.act == 0) {     // few tiles, long reduction (the head's [B, 3000] inputs): split K, partial sums meet in L2
+      const int nkb = ((ak.len + TC_BR - 1) / TC_BR) * ak.n;
+      const int sp = pick_splitk(tiles_of(x.M, 1, an.len, an.n, q.BJ), nkb);
+      if (sp > 1) {
+        q.splits = sp; q.epi = 2;
+        if (zero_matrix(x.Y, x.ldy, x.M, x.N, st)) return -2;
+      }
+    }
     ++ntc;
   }
   int rc = launch_tc(tc, ntc, st);
@@ -612,12 +661,7 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
       ident(qw.a_iseg, an.n); ident(qw.a_rseg, 1); ident(qw.b_jseg, ak.n); ident(qw.b_rseg, 1);
       copy_phys(qw.c_iseg, an); copy_phys(qw.c_jseg, ak); ident(qw.bias_seg, 1);
       qw.a_mn = 1; qw.b_mn = 1; qw.epi = 2;
-      const int tiles = ((an.len + TC_BI - 1) / TC_BI) * an.n * ((ak.len + qw.BJ - 1) / qw.BJ) * ak.n;
-      const int nkb = (x.M + TC_BR - 1) / TC_BR;
-      int s = (sm_count() + tiles - 1) / tiles;
-      if (s > nkb / 2) s = nkb / 2;
-      if (s < 1) s = 1;
-      qw.splits = s;
+      qw.splits = 1;        // decided for the whole launch below
     }
     if (!built) { rest[nrest++] = x; continue; }
     if (x.act == 1) {       // dY' = dY * [Y > 0] / (1 - p), materialised once for dgrad + wgrad; bias grad fused
@@ -644,6 +688,44 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
   }
   // dgrad and wgrad problems are independent of each other: one launch carries both kinds
   // (the kernel switches operand majors per problem), which fills the SMs better than two launches
+  // ---- launch-wide tiling policy (B operands are MN-major here: 32-wide TMA boxes, so BJ is free to change) ----
+  int dg_ctas = 0;
+  for (int i = 0; i < ndg; ++i) dg_ctas += tiles_of(dg[i].i_len, dg[i].i_nseg, dg[i].j_len, dg[i].j_nseg, dg[i].BJ);
+  if (dg_ctas <= sm_count()) {
+    dg_ctas = 0;
+    for (int i = 0; i < ndg; ++i) {
+      dg[i].BJ = pick_bj_narrow(dg[i].j_len);
+      dg_ctas += tiles_of(dg[i].i_len, dg[i].i_nseg, dg[i].j_len, dg[i].j_nseg, dg[i].BJ);
+    }
+  }
+  for (int i = 0; i < ndg; ++i) {        // few tiles, long reduction (head): split it; partial sums meet in L2
+    TcProblem& q = dg[i];
+    const int nkb = ((q.r_len + TC_BR - 1) / TC_BR) * q.r_nseg;
+    const int sp = pick_splitk(tiles_of(q.i_len, q.i_nseg, q.j_len, q.j_nseg, q.BJ), nkb);
+    if (sp > 1) {
+      q.splits = sp;
+      if (q.epi == 0) {
+        q.epi = 2;
+        if (zero_matrix(q.C, q.ldc, q.I, q.J, st)) return -2;
+      }
+      dg_ctas += (sp - 1) * tiles_of(q.i_len, q.i_nseg, q.j_len, q.j_nseg, q.BJ);
+    }
+  }
+  {
+    // weight gradients reduce over the token axis: give every CTA >= 8 reduction slabs and aim the whole launch
+    // at about one wave (2 CTAs / SM) -- more splits only multiply the reduce-add traffic on the same tiles
+    long long work = 0;
+    for (int i = 0; i < nwg; ++i)
+      work += (long long)tiles_of(wg[i].i_len, wg[i].i_nseg, wg[i].j_len, wg[i].j_nseg, wg[i].BJ) * ((wg[i].r_len + TC_BR - 1) / TC_BR);
+    int budget = 2 * sm_count() - (dg_ctas < sm_count() ? dg_ctas : sm_count());
+    int kpc = (int)((work + budget - 1) / budget);
+    if (kpc < 8) kpc = 8;
+    for (int i = 0; i < nwg; ++i) {
+      const int nkb = (wg[i].r_len + TC_BR - 1) / TC_BR;
+      int sp = (nkb + kpc - 1) / kpc;
+      wg[i].splits = sp < 1 ? 1 : sp;
+    }
+  }
   TcProblem all[2 * MTB_MAX_GROUP];
   int nall = 0;
   for (int i = 0; i < ndg; ++i) all[nall++] = dg[i];

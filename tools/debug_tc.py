@@ -9,7 +9,7 @@ def rel(a, b):
     return float((a.double().cpu() - b.double().cpu()).abs().max() / b.double().abs().max())
 
 torch.manual_seed(0)
-shapes = [(128, 208, 32), (128, 208, 64), (800, 600, 200), (8000, 200, 200), (130, 64, 40), (8000, 800, 200), (16, 3000, 600), (300, 200, 800)]
+shapes = [(16, 200, 3000), (16, 416, 3008), (128, 208, 32), (128, 208, 64), (800, 600, 200), (8000, 200, 200), (130, 64, 40), (8000, 800, 200), (16, 3000, 600), (300, 200, 800)]
 if len(sys.argv) > 1:
     shapes = shapes[:int(sys.argv[1])]
 for (M, N, K) in shapes:
