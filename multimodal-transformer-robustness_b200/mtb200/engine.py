@@ -88,12 +88,19 @@ class CountingArena(Arena):
         self.buf = None
 
 
+_NO_SEGS = Segs(0, 0)          # ctypes copies nested structures on assignment: shared instances are safe
+_NO_RNG = Rng(0, 0, None)
+
+
 def _segs(m: Optional[Mask]) -> Segs:
     if m is None or m.segs is None:
-        return Segs(0, 0)
-    s = Segs(m.seg_len, len(m.segs))
-    for i, v in enumerate(m.segs):
-        s.seg[i] = v
+        return _NO_SEGS
+    s = m.segs_c
+    if s is None:
+        s = Segs(m.seg_len, len(m.segs))
+        for i, v in enumerate(m.segs):
+            s.seg[i] = v
+        m.segs_c = s
     return s
 
 
@@ -161,7 +168,7 @@ class PlanBuilder:
     # -- helpers
     def rng(self, tag: str, n_elems: int, p: float) -> Rng:
         if not (self.training and p > 0.0):
-            return Rng(0, 0, None)
+            return _NO_RNG
         off = self.rng_off
         self.rng_off += (n_elems + 3) // 4 + 1
         self.sites[tag] = (off, n_elems, p)
@@ -224,7 +231,7 @@ class PlanBuilder:
             e.saved["ln_first"] = (ln, dst, st)
             e.saved["xn"] = dst
             descs.append(ResLnDesc(e.saved["x0"].ptr, e.E, None, 0, None, 0, dst.ptr, dst.ld, ln.weight.data_ptr(),
-                                   ln.bias.data_ptr(), idx, st[0], st[1], Tq, e.E, ln.eps, 0.0, Rng(0, 0, None)))
+                                   ln.bias.data_ptr(), idx, st[0], st[1], Tq, e.E, ln.eps, 0.0, _NO_RNG))
         self.emit(self.fwd, lib.mtb_resln_fwd, ResLnDesc, descs, "ln_first")
 
         max_layers = max((e.n_layers for e in group), default=0)
@@ -245,7 +252,7 @@ class PlanBuilder:
                     st = (A.alloc(Tk), A.alloc(Tk)) if ng else (None, None)
                     S[nm + "n"] = (dst, st)
                     descs.append(ResLnDesc(e.saved["x" + nm].ptr, e.E, None, 0, None, 0, dst.ptr, e.E, ln.weight.data_ptr(),
-                                           ln.bias.data_ptr(), None, st[0], st[1], Tk, e.E, ln.eps, 0.0, Rng(0, 0, None)))
+                                           ln.bias.data_ptr(), None, st[0], st[1], Tk, e.E, ln.eps, 0.0, _NO_RNG))
             self.emit(self.fwd, lib.mtb_resln_fwd, ResLnDesc, descs, f"ln0_kv[{i}]")
             # b. in-projection ----------------------------------------------------------------
             descs = []
@@ -263,7 +270,7 @@ class PlanBuilder:
                     S["qkv"] = qkv
                     cidx = e.mask.idx.data_ptr() if e.mask is not None else None
                     descs.append(LinearDesc(e.saved["xn"].ptr, e.saved["xn"].ld, W.data_ptr(), W.stride(0), b.data_ptr(), None, cidx,
-                                            qkv.ptr, qkv.ld, Tq, 3 * D, e.E, 0, 0.0, Rng(0, 0, None), Segs(0, 0), _segs(e.mask)))
+                                            qkv.ptr, qkv.ld, Tq, 3 * D, e.E, 0, 0.0, _NO_RNG, _NO_SEGS, _segs(e.mask)))
                 else:
                     q, k, v = A.mat(Tq, D), A.mat(Tk, D), A.mat(Tk, D)
                     S["q"], S["k"], S["v"] = q, k, v
@@ -271,7 +278,7 @@ class PlanBuilder:
                     for part, (src, dst, T) in enumerate(zip(srcs, (q, k, v), (Tq, Tk, Tk))):
                         descs.append(LinearDesc(src.ptr, src.ld, W.data_ptr() + F4 * part * D * W.stride(0), W.stride(0),
                                                 b.data_ptr() + F4 * part * D, None, None, dst.ptr, dst.ld, T, D, e.E, 0, 0.0,
-                                                Rng(0, 0, None), Segs(0, 0), Segs(0, 0)))
+                                                _NO_RNG, _NO_SEGS, _NO_SEGS))
             self.emit(self.fwd, lib.mtb_linear_fwd, LinearDesc, descs, f"in_proj[{i}]")
             # c. attention core ----------------------------------------------------------------
             descs = []
@@ -308,7 +315,7 @@ class PlanBuilder:
                 Wo, bo = sa.out_proj.weight, sa.out_proj.bias
                 ridx = e.mask.idx.data_ptr() if e.mask is not None else None
                 descs.append(LinearDesc(S["o"].ptr, S["o"].ld, Wo.data_ptr(), Wo.stride(0), bo.data_ptr(), ridx, None, a.ptr, a.ld,
-                                        Tq, e.E, D, 0, 0.0, Rng(0, 0, None), _segs(e.mask), Segs(0, 0)))
+                                        Tq, e.E, D, 0, 0.0, _NO_RNG, _segs(e.mask), _NO_SEGS))
             self.emit(self.fwd, lib.mtb_linear_fwd, LinearDesc, descs, f"out_proj[{i}]")
             # e. dropout + residual + LN1 ------------------------------------------------------
             descs = []
@@ -342,9 +349,9 @@ class PlanBuilder:
                 W1, b1, W2, b2 = layer.fc1.l.weight, layer.fc1.l.bias, layer.fc2.l.weight, layer.fc2.l.bias
                 midx = e.mask.idx.data_ptr() if e.mask is not None else None
                 d1.append(LinearDesc(S["xn1"].ptr, S["xn1"].ld, W1.data_ptr(), W1.stride(0), b1.data_ptr(), None, midx, h.ptr, h.ld,
-                                     Tq, Fa, e.E, 1, pl, r, Segs(0, 0), _segs(e.mask)))
+                                     Tq, Fa, e.E, 1, pl, r, _NO_SEGS, _segs(e.mask)))
                 d2.append(LinearDesc(h.ptr, h.ld, W2.data_ptr(), W2.stride(0), b2.data_ptr(), midx, None, y.ptr, y.ld,
-                                     Tq, e.E, Fa, 0, 0.0, Rng(0, 0, None), _segs(e.mask), Segs(0, 0)))
+                                     Tq, e.E, Fa, 0, 0.0, _NO_RNG, _segs(e.mask), _NO_SEGS))
             self.emit(self.fwd, lib.mtb_linear_fwd, LinearDesc, d1, f"fc1[{i}]")
             self.emit(self.fwd, lib.mtb_linear_fwd, LinearDesc, d2, f"fc2[{i}]")
             # h. dropout + residual + next LN0 / final LN ---------------------------------------
@@ -372,7 +379,7 @@ class PlanBuilder:
         """Appends the backward launches of ``group`` to self.bwd.  Requires e.d_out for every
         encoder; allocates and fills e.d_q_in (and d_k_in / d_v_in) as contiguous [T, E] mats."""
         A = self.arena
-        none_rng = Rng(0, 0, None)
+        none_rng = _NO_RNG
         max_layers = max((e.n_layers for e in group), default=0)
         # running gradients per encoder: g_xn (wrt the LN output feeding the next block), g_x (residual path)
         for e in group:
@@ -418,23 +425,23 @@ class PlanBuilder:
                 S["g_xn1"] = g_xn1
                 if defer:
                     d2.append(LinearBwdDesc(S["g_y"].ptr, S["g_y"].ld, None, 0, None, 0, W2.data_ptr(), W2.stride(0), midx, None,
-                                            g_h.ptr, g_h.ld, 0, None, None, Tq, e.E, Fa, 0, 0.0, None, _segs(e.mask), Segs(0, 0)))
+                                            g_h.ptr, g_h.ld, 0, None, None, Tq, e.E, Fa, 0, 0.0, None, _segs(e.mask), _NO_SEGS))
                     wg_descs.append(LinearBwdDesc(S["g_y"].ptr, S["g_y"].ld, None, 0, S["h"].ptr, S["h"].ld, W2.data_ptr(), W2.stride(0), midx, None,
-                                                  None, 0, 0, self.grad_ptr(W2), None, Tq, e.E, Fa, 0, 0.0, None, _segs(e.mask), Segs(0, 0)))
+                                                  None, 0, 0, self.grad_ptr(W2), None, Tq, e.E, Fa, 0, 0.0, None, _segs(e.mask), _NO_SEGS))
                     # fc1: the dgrad call materialises dY' = dY*[h>0]/(1-p) into `scratch` (bias grad fused there);
                     # the deferred wgrad reads it back as a plain dY
                     d1.append(LinearBwdDesc(g_h.ptr, g_h.ld, S["h"].ptr, S["h"].ld, None, 0, W1.data_ptr(), W1.stride(0), None, midx,
                                             g_xn1.ptr, g_xn1.ld, 0, None, self.grad_ptr(b1), Tq, Fa, e.E, 1, S["p_relu"], scratch,
-                                            Segs(0, 0), _segs(e.mask)))
+                                            _NO_SEGS, _segs(e.mask)))
                     wg_descs.append(LinearBwdDesc(scratch, Fa, None, 0, S["xn1"].ptr, S["xn1"].ld, W1.data_ptr(), W1.stride(0), None, midx,
-                                                  None, 0, 0, self.grad_ptr(W1), None, Tq, Fa, e.E, 0, 0.0, None, Segs(0, 0), _segs(e.mask)))
+                                                  None, 0, 0, self.grad_ptr(W1), None, Tq, Fa, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
                 else:
                     d2.append(LinearBwdDesc(S["g_y"].ptr, S["g_y"].ld, None, 0, S["h"].ptr, S["h"].ld, W2.data_ptr(), W2.stride(0), midx, None,
                                             g_h.ptr, g_h.ld, 0, self.grad_ptr(W2), None, Tq, e.E, Fa, 0, 0.0, None,
-                                            _segs(e.mask), Segs(0, 0)))
+                                            _segs(e.mask), _NO_SEGS))
                     d1.append(LinearBwdDesc(g_h.ptr, g_h.ld, S["h"].ptr, S["h"].ld, S["xn1"].ptr, S["xn1"].ld, W1.data_ptr(), W1.stride(0), None, midx,
                                             g_xn1.ptr, g_xn1.ld, 0, self.grad_ptr(W1), self.grad_ptr(b1), Tq, Fa, e.E, 1, S["p_relu"], scratch,
-                                            Segs(0, 0), _segs(e.mask)))
+                                            _NO_SEGS, _segs(e.mask)))
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, d2, f"fc2_bwd[{i}]")
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, d1, f"fc1_bwd[{i}]")
             # e'. res_ln1 backward -> g_x (residual into the layer input), g_a
@@ -468,13 +475,13 @@ class PlanBuilder:
                 S["g_o"] = g_o
                 if defer:
                     descs.append(LinearBwdDesc(S["g_a"].ptr, S["g_a"].ld, None, 0, None, 0, Wo.data_ptr(), Wo.stride(0), ridx, None,
-                                               g_o.ptr, g_o.ld, 0, None, None, Tq, e.E, D, 0, 0.0, None, _segs(e.mask), Segs(0, 0)))
+                                               g_o.ptr, g_o.ld, 0, None, None, Tq, e.E, D, 0, 0.0, None, _segs(e.mask), _NO_SEGS))
                     wg_descs.append(LinearBwdDesc(S["g_a"].ptr, S["g_a"].ld, None, 0, S["o"].ptr, S["o"].ld, Wo.data_ptr(), Wo.stride(0), ridx, None,
-                                                  None, 0, 0, self.grad_ptr(Wo), None, Tq, e.E, D, 0, 0.0, None, _segs(e.mask), Segs(0, 0)))
+                                                  None, 0, 0, self.grad_ptr(Wo), None, Tq, e.E, D, 0, 0.0, None, _segs(e.mask), _NO_SEGS))
                 else:
                     descs.append(LinearBwdDesc(S["g_a"].ptr, S["g_a"].ld, None, 0, S["o"].ptr, S["o"].ld, Wo.data_ptr(), Wo.stride(0), ridx, None,
                                                g_o.ptr, g_o.ld, 0, self.grad_ptr(Wo), None, Tq, e.E, D, 0, 0.0, None,
-                                               _segs(e.mask), Segs(0, 0)))
+                                               _segs(e.mask), _NO_SEGS))
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, descs, f"out_proj_bwd[{i}]")
             # c'. attention backward
             descs = []
@@ -514,12 +521,12 @@ class PlanBuilder:
                     cidx = e.mask.idx.data_ptr() if e.mask is not None else None
                     if defer:
                         descs.append(LinearBwdDesc(S["dqkv"].ptr, S["dqkv"].ld, None, 0, None, 0, W.data_ptr(), W.stride(0), None, cidx,
-                                                   g_xn.ptr, g_xn.ld, 0, None, None, Tq, 3 * D, e.E, 0, 0.0, None, Segs(0, 0), _segs(e.mask)))
+                                                   g_xn.ptr, g_xn.ld, 0, None, None, Tq, 3 * D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
                         wg_descs.append(LinearBwdDesc(S["dqkv"].ptr, S["dqkv"].ld, None, 0, xn_in.ptr, xn_in.ld, W.data_ptr(), W.stride(0), None, cidx,
-                                                      None, 0, 0, gW, gb, Tq, 3 * D, e.E, 0, 0.0, None, Segs(0, 0), _segs(e.mask)))
+                                                      None, 0, 0, gW, gb, Tq, 3 * D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
                     else:
                         descs.append(LinearBwdDesc(S["dqkv"].ptr, S["dqkv"].ld, None, 0, xn_in.ptr, xn_in.ld, W.data_ptr(), W.stride(0), None, cidx,
-                                                   g_xn.ptr, g_xn.ld, 0, gW, gb, Tq, 3 * D, e.E, 0, 0.0, None, Segs(0, 0), _segs(e.mask)))
+                                                   g_xn.ptr, g_xn.ld, 0, gW, gb, Tq, 3 * D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
                 else:
                     g_kn, g_vn = A.mat(Tk, e.E), A.mat(Tk, e.E)
                     S["g_kn"], S["g_vn"] = g_kn, g_vn
@@ -530,12 +537,12 @@ class PlanBuilder:
                         Wp = W.data_ptr() + F4 * part * D * W.stride(0)
                         if defer:
                             descs.append(LinearBwdDesc(dy.ptr, dy.ld, None, 0, None, 0, Wp, W.stride(0), None, None, dst.ptr, dst.ld, 0,
-                                                       None, None, T, D, e.E, 0, 0.0, None, Segs(0, 0), Segs(0, 0)))
+                                                       None, None, T, D, e.E, 0, 0.0, None, _NO_SEGS, _NO_SEGS))
                             wg_descs.append(LinearBwdDesc(dy.ptr, dy.ld, None, 0, src.ptr, src.ld, Wp, W.stride(0), None, None, None, 0, 0,
-                                                          gWp, gbp, T, D, e.E, 0, 0.0, None, Segs(0, 0), Segs(0, 0)))
+                                                          gWp, gbp, T, D, e.E, 0, 0.0, None, _NO_SEGS, _NO_SEGS))
                         else:
                             descs.append(LinearBwdDesc(dy.ptr, dy.ld, None, 0, src.ptr, src.ld, Wp, W.stride(0),
-                                                       None, None, dst.ptr, dst.ld, 0, gWp, gbp, T, D, e.E, 0, 0.0, None, Segs(0, 0), Segs(0, 0)))
+                                                       None, None, dst.ptr, dst.ld, 0, gWp, gbp, T, D, e.E, 0, 0.0, None, _NO_SEGS, _NO_SEGS))
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, descs, f"in_proj_bwd[{i}]")
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, wg_descs, f"wgrad[{i}]")
             # a'. LN0 backward on the key / value streams (gradients accumulate over layers, in place)
@@ -884,14 +891,14 @@ class Engine:
         hp, hs = hmask.idx.data_ptr(), _segs(hmask)
         pb.emit(pb.fwd, lib.mtb_linear_fwd, LinearDesc,
                 [LinearDesc(out.ptr, out.ld, W1.data_ptr(), W1.stride(0), b1.data_ptr(), None, hp, z1.ptr, z1.ld, B, Cd, C_total, 1, po, r,
-                            Segs(0, 0), hs)], "proj1")
+                            _NO_SEGS, hs)], "proj1")
         pb.emit(pb.fwd, lib.mtb_linear_fwd, LinearDesc,
                 [LinearDesc(z1.ptr, z1.ld, W2.data_ptr(), W2.stride(0), b2.data_ptr(), hp, None, z2.ptr, z2.ld, B, C_total, Cd, 0, 0.0,
-                            Rng(0, 0, None), hs, Segs(0, 0))], "proj2")
+                            _NO_RNG, hs, _NO_SEGS)], "proj2")
         pb.addn(pb.fwd, [(z3, [out, z2], False)], "head_residual")
         pb.emit(pb.fwd, lib.mtb_linear_fwd, LinearDesc,
                 [LinearDesc(z3.ptr, z3.ld, W3.data_ptr(), W3.stride(0), b3.data_ptr(), None, hp, pred.ptr, pred.ld, B, m.output_dim, C_total,
-                            0, 0.0, Rng(0, 0, None), Segs(0, 0), hs)], "out_layer")
+                            0, 0.0, _NO_RNG, _NO_SEGS, hs)], "out_layer")
 
         plan.inputs = [(i, stage_in[ch]) for i, ch in enumerate(names) if ch in need]
         plan._pred_mat = pred
@@ -905,13 +912,13 @@ class Engine:
             scratch = A.alloc(B * Cd)
             pb.emit(pb.bwd, lib.mtb_linear_bwd, LinearBwdDesc,
                     [LinearBwdDesc(d_pred.ptr, d_pred.ld, None, 0, z3.ptr, z3.ld, W3.data_ptr(), W3.stride(0), None, hp, g_z3.ptr, g_z3.ld, 0,
-                                   pb.grad_ptr(W3), pb.grad_ptr(b3), B, m.output_dim, C_total, 0, 0.0, None, Segs(0, 0), hs)], "out_layer_bwd")
+                                   pb.grad_ptr(W3), pb.grad_ptr(b3), B, m.output_dim, C_total, 0, 0.0, None, _NO_SEGS, hs)], "out_layer_bwd")
             pb.emit(pb.bwd, lib.mtb_linear_bwd, LinearBwdDesc,
                     [LinearBwdDesc(g_z3.ptr, g_z3.ld, None, 0, z1.ptr, z1.ld, W2.data_ptr(), W2.stride(0), hp, None, g_z1.ptr, g_z1.ld, 0,
-                                   pb.grad_ptr(W2), pb.grad_ptr(b2), B, C_total, Cd, 0, 0.0, None, hs, Segs(0, 0))], "proj2_bwd")
+                                   pb.grad_ptr(W2), pb.grad_ptr(b2), B, C_total, Cd, 0, 0.0, None, hs, _NO_SEGS)], "proj2_bwd")
             pb.emit(pb.bwd, lib.mtb_linear_bwd, LinearBwdDesc,
                     [LinearBwdDesc(g_z1.ptr, g_z1.ld, z1.ptr, z1.ld, out.ptr, out.ld, W1.data_ptr(), W1.stride(0), None, hp, g_outb.ptr, g_outb.ld,
-                                   0, pb.grad_ptr(W1), pb.grad_ptr(b1), B, Cd, C_total, 1, po, scratch, Segs(0, 0), hs)], "proj1_bwd")
+                                   0, pb.grad_ptr(W1), pb.grad_ptr(b1), B, Cd, C_total, 1, po, scratch, _NO_SEGS, hs)], "proj1_bwd")
             pb.addn(pb.bwd, [(g_out, [g_z3, g_outb], False)], "head_residual_bwd")
             # scatter into zero-filled d(mems output): only the last time step received gradient
             items = []

@@ -58,6 +58,8 @@ class FlatAdam(torch.optim.Optimizer):
         self.exp_avg_sq = torch.zeros_like(eng.grad_arena)
         self.partial = torch.zeros(self.n_chunks, dtype=torch.float32, device=dev)
         self.scalars = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._pin = torch.zeros(64, self.n_params, dtype=torch.uint8).pin_memory()
+        self._pin_slot = 0
         self._param_ptr0 = eng.params[0].data_ptr()
         self._eng = eng
         self._flag_cache.clear()
@@ -98,13 +100,17 @@ class FlatAdam(torch.optim.Optimizer):
         cache = self._flag_cache if plan is None else plan.__dict__.setdefault("_adam_flags", {})
         flags = cache.get(key)
         if flags is None:
-            host = torch.zeros(self.n_params, dtype=torch.uint8)
+            # staged through a ring of pinned rows: a pageable-memory copy would wait for the stream to drain
+            idx = list(extra)
             if plan is not None:
-                for p in plan.active_params:
-                    host[self._index[id(p)]] = 1
-            for i in extra:
-                host[i] = 1
-            flags = host.to(eng.device)
+                idx.extend(self._index[id(p)] for p in plan.active_params)
+            self._pin_slot = (self._pin_slot + 1) % self._pin.shape[0]
+            host = self._pin[self._pin_slot]
+            host.zero_()
+            if idx:
+                host[torch.tensor(idx, dtype=torch.int64)] = 1
+            flags = torch.empty(self.n_params, dtype=torch.uint8, device=eng.device)
+            flags.copy_(host, non_blocking=True)
             if len(cache) > 1024:
                 cache.clear()
             cache[key] = flags

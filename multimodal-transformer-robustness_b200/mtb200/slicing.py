@@ -39,10 +39,11 @@ class Mask:
     """An ``active_mask``: int32 device index tensor plus (when the indices are a union of
     equally sized, aligned blocks -- the only kind the model produces, src/dynamic_models2.py:243-251)
     the block structure, which lets the tensor-core GEMM address the blocks through TMA."""
-    __slots__ = ("idx", "seg_len", "segs")
+    __slots__ = ("idx", "seg_len", "segs", "segs_c")
 
     def __init__(self, idx: torch.Tensor, seg_len: int = 0, segs=None):
         self.idx, self.seg_len, self.segs = idx, seg_len, segs
+        self.segs_c = None            # cached ctypes form (plan executor)
 
     def numel(self) -> int:
         return self.idx.numel()
