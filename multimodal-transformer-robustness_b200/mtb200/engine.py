@@ -88,6 +88,51 @@ class CountingArena(Arena):
         self.buf = None
 
 
+class SubArena(Arena):
+    """bump allocator over a fixed, persistent region of the encoder buffer"""
+
+    def __init__(self, base: int, cap: int):
+        self.base, self.cap, self.off, self.peak, self.buf = base, cap, 0, 0, None
+
+
+class Region:
+    """Persistent home of one encoder: its output, the gradient w.r.t. its output, (masked `mems` stacks) the
+    concat buffer it reads, and a work area for everything its forward / backward allocates.  Because these
+    addresses never change, the launch descriptors of an encoder invocation depend only on the encoder's own
+    configuration -- not on which other branches are active -- and are memoised (Engine._enc_plan)."""
+    __slots__ = ("out", "dout", "cat", "work", "work_cap")
+
+
+_FWD_RANK = {"ln0_kv": 0, "in_proj": 1, "attn": 2, "out_proj": 3, "res_ln1": 4, "fc1": 5, "fc2": 6, "res_ln2": 7}
+_BWD_RANK = {"res_ln2_bwd": 0, "fc2_bwd": 1, "fc1_bwd": 2, "res_ln1_bwd": 3, "out_proj_bwd": 4, "attn_bwd": 5, "in_proj_bwd": 6,
+             "wgrad": 7, "ln0_kv_bwd": 8}
+
+
+def _rank(what: str) -> Tuple[int, int]:
+    """position of a grouped launch inside its stage: encoders of one stage run in lock-step, launch `what` of
+    every encoder that has it travels in ONE grouped call"""
+    if what == "embed":
+        return (-2, 0)
+    if what == "ln_first":
+        return (-1, 0)
+    if what == "ln_first_bwd":
+        return (1, 0)
+    if what == "embed_bwd":
+        return (2, 0)
+    name, i = what[:-1].split("[")
+    i = int(i)
+    if name in _FWD_RANK:
+        return (i, _FWD_RANK[name])
+    return (-i, _BWD_RANK[name])
+
+
+class EncPlan:
+    """memoised launches of one encoder invocation: [(rank, Op with unfinalised descriptor list)]"""
+    __slots__ = ("spec", "fwd", "bwd", "active_params", "sites")
+
+
+STEP_SPAN = 1 << 34            # Philox offset advance per training step (larger than any encoder's span)
+
 _NO_SEGS = Segs(0, 0)          # ctypes copies nested structures on assignment: shared instances are safe
 _NO_RNG = Rng(0, 0, None)
 
@@ -696,6 +741,10 @@ class Engine:
         self.graph_after = graph_after
         self.plans: Dict[tuple, Plan] = {}
         self.arena: Optional[Arena] = None
+        self.enc_buf: Optional[torch.Tensor] = None
+        self._layout = None
+        self._regions: Dict[int, Region] = {}
+        self._enc_cache: Dict[tuple, EncPlan] = {}
         _install_fast_attrs(model)
         self.params = [p for p in model.parameters()]
         total = 0
@@ -712,6 +761,7 @@ class Engine:
         self._param_ptr0 = self.params[0].data_ptr() if self.params else 0
         self.last_plan: Optional[Plan] = None
         self.step_offset = 0       # host mirror of rng_state[1]
+        self._enc_index = {id(enc): j for j, (_, _, enc) in enumerate(self._all_encoders())}
         self.stats = {"plans": 0, "graph_replays": 0, "eager_runs": 0}
 
     def grad_ptr(self, p) -> int:
@@ -753,6 +803,7 @@ class Engine:
     def manual_seed(self, seed: int):
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.plans.clear()
+        self._enc_cache.clear()
 
     # ------------------------------------------------------------------ plan construction
     def _key(self, shapes, training, need_grad):
@@ -764,92 +815,232 @@ class Engine:
         return (lib.mtb_get_gemm_mode(), tuple(shapes), training, need_grad, tuple(m.active_modality), tuple(tuple(c) for c in m.active_cross),
                 tuple(tuple(o) for o in m.active_cross_output), depth, cross_depth, self_depth, ffn)
 
+    # -- persistent layout -------------------------------------------------------------------------
+    def _all_encoders(self):
+        m = self.model
+        out = []
+        for ch in m.modality_list:
+            out.append(("mems0", ch, m.trans_mems0['mems0' + ch]))
+        for k, enc in m.trans.items():
+            out.append(("cross", k[len("cross"):], enc))
+        for ch in m.modality_list:
+            out.append(("mems", ch, m.trans_mems['mems' + ch]))
+        return out
+
+    def _measure(self, kind, name, enc, Lq, Lk, B, E, mask) -> int:
+        """bytes one invocation of `enc` allocates at full depth (forward + backward), from a dry run"""
+        layers = enc._ll
+        saved = [l.__dict__.get("active_hidden_out_fc1") for l in layers]
+        try:
+            for l in layers:
+                l.__dict__["active_hidden_out_fc1"] = l.fc1.dim_out
+            peak = 0
+            mode0 = lib.mtb_get_gemm_mode()
+            for mode in (0, 1):                  # the two GEMM engines allocate different scratch
+                lib.mtb_set_gemm_mode(mode)
+                ca = CountingArena()
+                pb = PlanBuilder(self, ca, True, True)
+                src = (1 << 20, B * E, E, 1)
+                e = EncSpec("", enc, Lq, Lk, B, E, len(layers), mask, src, src if kind == "cross" else None,
+                            Mat(1 << 20, Lq * B, E), kind, name)
+                pb.encoders_forward([e])
+                e.d_out = Mat(1 << 20, Lq * B, E)
+                pb.encoders_backward([e])
+                peak = max(peak, ca.peak)
+            lib.mtb_set_gemm_mode(mode0)
+            return peak
+        finally:
+            for l, v in zip(layers, saved):
+                l.__dict__["active_hidden_out_fc1"] = v
+
+    def _ensure_layout(self, px_meta):
+        """Carve the persistent encoder buffer: one Region per encoder (+ one staging buffer per modality), sized
+        for the largest batch / sequence lengths seen so far.  Growing it invalidates every cached plan."""
+        m = self.model
+        d = m.d
+        B = px_meta[0][1]
+        Ls = tuple(pm[0] for pm in px_meta)
+        if self._layout is not None:
+            B0, Ls0 = self._layout
+            if B <= B0 and all(l <= l0 for l, l0 in zip(Ls, Ls0)):
+                return
+            B, Ls = max(B, B0), tuple(max(l, l0) for l, l0 in zip(Ls, Ls0))
+            self.plans.clear()
+            self._enc_cache.clear()
+        names = list(m.modality_list)
+        length = dict(zip(names, Ls))
+        off = 0
+
+        def take(nfloats):
+            nonlocal off
+            o = off
+            off += (nfloats * F4 + 255) & ~255
+            return o
+        stage_off = {ch: take(length[ch] * B * d) for ch in names}
+        regs = {}
+        for kind, name, enc in self._all_encoders():
+            Lq = length[name[-1]]
+            if kind == "cross":
+                Lk = length[name[:-1][-1]]
+                E, mask = d, None
+            elif kind == "mems":
+                Lq = Lk = max(Ls)            # a modality's outputs may all be branches querying another (longer) stream
+                slots = len(m.modality_index_list[names.index(name)])
+                E, mask = d * slots, make_mask(list(range(d * slots)), self.device)
+            else:
+                Lk, E, mask = Lq, d, None
+            r = Region()
+            r.out, r.dout = take(Lq * B * E), take(Lq * B * E)
+            r.cat = take(Lq * B * E) if kind == "mems" else None
+            r.work_cap = int(self._measure(kind, name, enc, Lq, Lk, B, E, mask) * 1.02) + (1 << 20)
+            r.work = take(r.work_cap // F4)
+            regs[id(enc)] = r
+        free, _ = torch.cuda.mem_get_info(self.device)
+        if off > free * 0.9:
+            raise MemoryError(f"mtb200 engine: encoder buffer needs {off >> 20} MB, {free >> 20} MB free")
+        self.enc_buf = None
+        self.enc_buf = torch.empty(off, dtype=torch.uint8, device=self.device)
+        base = self.enc_buf.data_ptr()
+        for r in regs.values():
+            r.out += base
+            r.dout += base
+            r.work += base
+            if r.cat is not None:
+                r.cat += base
+        self._regions = regs
+        self._stage_ptr = {ch: base + o for ch, o in stage_off.items()}
+        self._layout = (B, Ls)
+        # plan-level scratch (head, fan-in temporaries): re-used by every plan
+        self.arena = Arena(self.device, (64 << 20) + B * max(m.combined_dim, 1) * F4 * 64)
+
+    def view(self, mt: Mat) -> torch.Tensor:
+        """torch view of a contiguous Mat living in the plan arena or in the persistent encoder buffer"""
+        assert mt.ld == mt.cols
+        for buf in (self.arena.buf, self.enc_buf):
+            o = mt.ptr - buf.data_ptr()
+            if 0 <= o < buf.numel():
+                return buf[o:o + mt.rows * mt.cols * F4].view(torch.float32).view(mt.rows, mt.cols)
+        raise ValueError("Mat outside the engine's buffers")
+
+    def _enc_plan(self, kind, name, tag, enc, Lq, Lk, B, E, n_layers, mask, q_src, kv_src, want_bwd, training, need_grad) -> EncPlan:
+        """Launch descriptors of ONE encoder invocation, memoised: every address involved (inputs, output,
+        activations, gradients, dropout-stream offsets) is a fixed function of the encoder and this key."""
+        want_bwd = bool(want_bwd and need_grad)
+        ffn = tuple(l.active_hidden_out_fc1 for l in enc._ll[:n_layers])
+        key = (id(enc), Lq, Lk, B, E, n_layers, id(mask) if mask is not None else 0, q_src, kv_src, want_bwd, training, need_grad,
+               ffn, lib.mtb_get_gemm_mode())
+        ep = self._enc_cache.get(key)
+        if ep is not None:
+            return ep
+        reg = self._regions[id(enc)]
+        e = EncSpec(tag, enc, Lq, Lk, B, E, n_layers, mask, q_src, kv_src, Mat(reg.out, Lq * B, E), kind, name)
+        pb = PlanBuilder(self, SubArena(reg.work, reg.work_cap), training, need_grad)
+        pb.rng_off = self._enc_index[id(enc)] << 56
+        pb.encoders_forward([e])
+        if want_bwd:
+            e.d_out = Mat(reg.dout, Lq * B, E)
+            pb.encoders_backward([e])
+        ep = EncPlan()
+        ep.spec = e
+        ep.fwd = [(_rank(op.what), op) for op in pb.fwd]
+        ep.bwd = [(_rank(op.what), op) for op in pb.bwd]
+        ep.active_params, ep.sites = pb.active_params, pb.sites
+        e.saved = None                       # only the Mats on the spec are needed from here on
+        if len(self._enc_cache) > 4096:
+            self._enc_cache.clear()
+        self._enc_cache[key] = ep
+        self.stats["enc_plans"] = self.stats.get("enc_plans", 0) + 1
+        return ep
+
+    @staticmethod
+    def _merge(lst, eps, which):
+        """lock-step merge: launch `what` of every encoder of the stage goes into one grouped Op"""
+        buckets = {}
+        for ep in eps:
+            for rk, op in (ep.fwd if which == "fwd" else ep.bwd):
+                b = buckets.get(rk)
+                if b is None:
+                    buckets[rk] = [op, list(op.descs)]
+                else:
+                    b[1].extend(op.descs)
+        for rk in sorted(buckets):
+            op, descs = buckets[rk]
+            lst.append(Op(op.fn, op.dtype, descs, op.what))
+
     def _build(self, px_meta, training, need_grad, arena) -> Plan:
         """px_meta: per modality (L, B) of the front-end output [L, B, d] (strided view); the input
         pointers/strides are bound through static staging buffers."""
         m = self.model
         d = m.d
         pb = PlanBuilder(self, arena, training, need_grad)
+        pb.rng_off = 31 << 56                               # plan-level sites (head dropout)
         plan = Plan()
         A = arena
         names = list(m.modality_list)
         need = m._needed_modalities() if m.prune_dead_branches else set(names)
         B = px_meta[0][1]
-        # staging buffers for the front-end outputs, contiguous [L, B, d]
-        stage_in: Dict[str, Mat] = {}
-        for i, ch in enumerate(names):
-            if ch in need:
-                L = px_meta[i][0]
-                stage_in[ch] = A.mat(L * B, d)
         length = {ch: px_meta[i][0] for i, ch in enumerate(names)}
-
-        # where does every branch output live?  inside its modality's concat buffer when it is an
-        # output of that modality (so the concat never materialises), else in a private buffer
-        cat_buf: Dict[int, Mat] = {}
-        slot_of: Dict[str, Tuple[int, int]] = {}
-        for i in m.active_modality:
-            outs = m.active_cross_output[i]
-            if not outs:
-                continue
-            Ls = {length[n[-1]] for n in outs}
-            assert len(Ls) == 1, f"outputs of modality {names[i]} have different lengths {Ls} (SURVEY.md D2)"
-            L = Ls.pop()
-            cat_buf[i] = A.mat(L * B, d * len(outs))
-            for k, n in enumerate(outs):
-                slot_of[n] = (i, k)
-
-        def out_mat(name: str, L: int) -> Mat:
-            if name in slot_of:
-                i, k = slot_of[name]
-                return cat_buf[i].cols_slice(k * d, d)
-            return A.mat(L * B, d)
+        stage_in: Dict[str, Mat] = {ch: Mat(self._stage_ptr[ch], length[ch] * B, d) for ch in names if ch in need}
 
         def src(mat: Mat):
             return (mat.ptr, B * mat.ld, mat.ld, 1)
 
+        # which branch outputs feed a consumer that reaches the loss?  (decides whether an encoder runs backward)
+        outs_of = {i: m.active_cross_output[i] for i in m.active_modality if m.active_cross_output[i]}
+        all_cross = [n for i in outs_of for n in m.active_cross[i]]
+        seen_c = set()
+        all_cross = [n for n in all_cross if not (n in seen_c or seen_c.add(n))]
+        live = set()
+        if need_grad:
+            for i, outs in outs_of.items():
+                live.update(outs)
+            for n in sorted(all_cross, key=len, reverse=True):       # consumers before producers
+                if n in live:
+                    live.add(n[-1])
+                    if m.trans['cross' + n].active_layer_num > 0:      # depth-0 cross stacks never touch their key / value stream
+                        live.add(n[:-1])
+
         h: Dict[str, Mat] = {}
-        groups: List[List[EncSpec]] = []
-        spec_of: Dict[str, EncSpec] = {}
-        # stage 0: mems0
+        groups: List[List[EncPlan]] = []
+        plan_of: Dict[str, EncPlan] = {}
         g0 = []
-        for i, ch in enumerate(names):
+        for ch in names:
             if ch not in need:
                 continue
             enc = m.trans_mems0['mems0' + ch]
             L = length[ch]
-            o = out_mat(ch, L)
-            e = EncSpec(f"trans_mems0.mems0{ch}.", enc, L, L, B, d, enc.active_layer_num, None, src(stage_in[ch]), None, o, "mems0", ch)
-            g0.append(e)
-            h[ch] = o
-            spec_of[ch] = e
+            ep = self._enc_plan("mems0", ch, f"trans_mems0.mems0{ch}.", enc, L, L, B, d, enc.active_layer_num, None,
+                                src(stage_in[ch]), None, ch in live, training, need_grad)
+            g0.append(ep)
+            h[ch] = ep.spec.out
+            plan_of[ch] = ep
         groups.append(g0)
-        # cross stages by name length
-        all_cross = [n for i in m.active_modality if m.active_cross_output[i] != [] for n in m.active_cross[i]]
         max_len = max((len(n) for n in all_cross), default=1)
         for ln in range(2, max_len + 1):
             g = []
             for n in all_cross:
-                if len(n) != ln or n in spec_of:
+                if len(n) != ln:
                     continue
                 enc = m.trans['cross' + n]
                 Lq, Lk = length[n[-1]], h[n[:-1]].rows // B
-                o = out_mat(n, Lq)
-                e = EncSpec(f"trans.cross{n}.", enc, Lq, Lk, B, d, enc.active_layer_num, None, src(h[n[-1]]), src(h[n[:-1]]), o, "cross", n)
-                g.append(e)
-                h[n] = o
-                spec_of[n] = e
+                ep = self._enc_plan("cross", n, f"trans.cross{n}.", enc, Lq, Lk, B, d, enc.active_layer_num, None,
+                                    src(h[n[-1]]), src(h[n[:-1]]), n in live, training, need_grad)
+                g.append(ep)
+                h[n] = ep.spec.out
+                plan_of[n] = ep
             if g:
                 groups.append(g)
-        # mems stage
+        # mems stage: branch outputs are gathered into the (compact) concat buffer each masked stack owns
         gm = []
-        mems_of: Dict[int, EncSpec] = {}
+        mems_of: Dict[int, EncPlan] = {}
         out_index: List[int] = []
         head_cols: List[Tuple[int, int, int]] = []      # (modality, col offset in `out`, width)
+        cat_items = []
         C_total = 0
-        for i in m.active_modality:
-            outs = m.active_cross_output[i]
-            if not outs:
-                continue
+        for i, outs in outs_of.items():
+            Ls_ = {length[n[-1]] for n in outs}
+            assert len(Ls_) == 1, f"outputs of modality {names[i]} have different lengths {Ls_} (SURVEY.md D2)"
+            L = Ls_.pop()
             slot = len(m.modality_index_list[i])
             mask_idx: List[int] = []
             for n in outs:
@@ -858,25 +1049,29 @@ class Engine:
                 out_index.extend(range(d * slot * i + k * d, d * slot * i + (k + 1) * d))
             mk = make_mask(mask_idx, self.device)
             enc = m.trans_mems['mems' + names[i]]
-            cb = cat_buf[i]
-            L = cb.rows // B
-            o = A.mat(L * B, cb.cols)
-            e = EncSpec(f"trans_mems.mems{names[i]}.", enc, L, L, B, cb.cols, enc.active_layer_num, mk, src(cb), None, o, "mems", names[i])
-            gm.append(e)
-            mems_of[i] = e
-            head_cols.append((i, C_total, cb.cols))
-            C_total += cb.cols
+            w = d * len(outs)
+            cb = Mat(self._regions[id(enc)].cat, L * B, w)
+            for k, n in enumerate(outs):
+                cat_items.append((cb.cols_slice(k * d, d), [h[n]], False))
+            ep = self._enc_plan("mems", names[i], f"trans_mems.mems{names[i]}.", enc, L, L, B, w, enc.active_layer_num, mk,
+                                src(cb), None, True, training, need_grad)
+            gm.append(ep)
+            mems_of[i] = ep
+            head_cols.append((i, C_total, w))
+            C_total += w
         groups.append(gm)
 
-        for g in groups:
-            pb.encoders_forward(g)
+        for gi, g in enumerate(groups):
+            if gi == len(groups) - 1:
+                pb.addn(pb.fwd, cat_items, "cat_gather")
+            self._merge(pb.fwd, g, "fwd")
 
         # head ---------------------------------------------------------------------------------
         assert not m.all_steps, "engine path implements the last-step head (all_steps=False)"
         out = A.mat(B, C_total)
         items = []
         for (i, c0, w) in head_cols:
-            e = mems_of[i]
+            e = mems_of[i].spec
             items.append((out.cols_slice(c0, w), [e.out.rows_slice((e.Lq - 1) * B, B)], False))
         pb.addn(pb.fwd, items, "head_gather")
         hmask = make_mask(out_index, self.device)
@@ -923,35 +1118,29 @@ class Engine:
             # scatter into zero-filled d(mems output): only the last time step received gradient
             items = []
             for (i, c0, w) in head_cols:
-                e = mems_of[i]
-                e.d_out = A.mat(e.Lq * B, w)
-                if arena.buf is not None:
-                    pb.bwd.append(ZeroOp(arena.view(e.d_out)))
+                e = mems_of[i].spec
+                pb.bwd.append(ZeroOp(self.view(e.d_out)))
                 items.append((e.d_out.rows_slice((e.Lq - 1) * B, B), [g_out.cols_slice(c0, w)], False))
             pb.addn(pb.bwd, items, "head_scatter_bwd")
-            # stage groups in reverse; gradient fan-in of every branch output
+            # stage groups in reverse; the gradient of every branch output is summed into its fixed home
             grads_of: Dict[str, List[Mat]] = {}
             for gi in reversed(range(len(groups))):
                 g = groups[gi]
                 if gi != len(groups) - 1:
-                    # this group's encoders need d_out = sum of their consumers' gradients
                     items = []
-                    for e in g:
-                        pieces = grads_of.get(e.name, [])
-                        if not pieces:
-                            e.d_out = None
+                    for ep in g:
+                        if ep.spec.d_out is None:
                             continue
-                        if len(pieces) == 1:
-                            e.d_out = pieces[0]
-                        else:
-                            e.d_out = A.mat(e.Lq * B, d)
-                            items.append((e.d_out, pieces, False))
+                        pieces = grads_of.get(ep.spec.name, [])
+                        assert pieces, f"branch {ep.spec.name} was planned with a backward pass but has no consumer gradient"
+                        items.append((ep.spec.d_out, pieces, False))
                     pb.addn(pb.bwd, items, f"fan_in[{gi}]")
-                    g = [e for e in g if e.d_out is not None]
+                    g = [ep for ep in g if ep.spec.d_out is not None]
                 if not g:
                     continue
-                pb.encoders_backward(g)
-                for e in g:
+                self._merge(pb.bwd, g, "bwd")
+                for ep in g:
+                    e = ep.spec
                     if e.kind == "mems":
                         # gradient of the concat buffer -> per-slot pieces (strided views, no copy)
                         i = names.index(e.name)
@@ -963,60 +1152,42 @@ class Engine:
                             if piece is not None:
                                 grads_of.setdefault(e.name[:-1], []).append(piece)
                     # mems0: e.d_q_in is the gradient of the front-end output
-            plan._d_stage = {ch: spec_of[ch].d_q_in for ch in stage_in if spec_of[ch].d_out is not None}
+            plan._d_stage = {ch: plan_of[ch].spec.d_q_in for ch in stage_in if plan_of[ch].spec.d_out is not None}
 
         for op in pb.fwd + pb.bwd:
             if type(op) is Op:
                 op.finalize()
         plan.fwd, plan.bwd = pb.fwd, pb.bwd
-        plan.sites, plan.rng_span = pb.sites, pb.rng_off
-        plan.active_params = pb.active_params
+        sites = dict(pb.sites)
+        aps, seen_p = [], set()
+        for g in groups:
+            for ep in g:
+                sites.update(ep.sites)
+                for p_ in ep.active_params:
+                    if id(p_) not in seen_p:
+                        seen_p.add(id(p_))
+                        aps.append(p_)
+        for p_ in pb.active_params:
+            if id(p_) not in seen_p:
+                seen_p.add(id(p_))
+                aps.append(p_)
+        plan.sites, plan.rng_span = sites, (STEP_SPAN if training else 0)
+        plan.active_params = aps
         plan.n_fwd_launches = sum(len(op.arr) if type(op) is Op else 1 for op in pb.fwd)
         plan.n_bwd_launches = sum(len(op.arr) if type(op) is Op else 1 for op in pb.bwd)
         return plan
-
-    def _ensure_arena(self, px_meta, training, need_grad):
-        """Size the activation arena once from a dry run of the LARGEST sub-network (every
-        modality, every branch, every output, full depth) with every stream at the longest
-        sequence length -- an upper bound for any configuration the sampler can draw."""
-        if self.arena is not None:
-            return
-        m = self.model
-        saved = (m.active_modality, m.active_cross, m.active_cross_output,
-                 [m.trans_mems0['mems0' + ch].active_layer_num for ch in m.modality_list])
-        B = px_meta[0][1]
-        Lmax = max(pm[0] for pm in px_meta)
-        try:
-            m.active_modality = list(range(m.modality_num))
-            if m.modality_num > 1:
-                m.active_cross = [m.m.gen_modality_str_all(modality_set=[ch]) for ch in m.modality_list]
-                m.active_cross_output = [[ch] + m.m.gen_modality_str_all(modality_set=[ch]) for ch in m.modality_list]
-            else:
-                m.active_cross, m.active_cross_output = [[]], [list(m.modality_list)]
-            for ch in m.modality_list:
-                m.trans_mems0['mems0' + ch].active_layer_num = m.layers_single_attn
-            ca = CountingArena()
-            self._build(tuple((Lmax, B) for _ in px_meta), True, True, ca)
-            need_bytes = ca.peak
-        finally:
-            m.active_modality, m.active_cross, m.active_cross_output = saved[0], saved[1], saved[2]
-            for ch, n in zip(m.modality_list, saved[3]):
-                m.trans_mems0['mems0' + ch].active_layer_num = n
-        free, _ = torch.cuda.mem_get_info(self.device)
-        need_bytes = int(min(need_bytes * 1.05 + (64 << 20), free * 0.7))
-        self.arena = Arena(self.device, need_bytes)
 
     def plan_for(self, px_meta, training, need_grad) -> Plan:
         key = self._key(px_meta, training, need_grad)
         plan = self.plans.get(key)
         if plan is None:
-            self._ensure_arena(px_meta, training, need_grad)
+            self._ensure_layout(px_meta)
             self.arena.reset()
             plan = self._build(px_meta, training, need_grad, self.arena)
-            plan.pred = self.arena.view(plan._pred_mat)
+            plan.pred = self.view(plan._pred_mat)
             if need_grad:
-                plan.d_pred = self.arena.view(plan._d_pred_mat)
-            plan._stage_views = {ch: self.arena.view(mt) for ch, mt in plan._stage_in.items()}
+                plan.d_pred = self.view(plan._d_pred_mat)
+            plan._stage_views = {ch: self.view(mt) for ch, mt in plan._stage_in.items()}
             if len(self.plans) > 2048:
                 self.plans.clear()
             self.plans[key] = plan
@@ -1104,5 +1275,5 @@ class _EngineFn(torch.autograd.Function):
         for i, shp in enumerate(ctx.shapes):
             ch = m.modality_list[i]
             dm = plan._d_stage.get(ch) if hasattr(plan, "_d_stage") else None
-            outs.append(eng.arena.view(dm).view(shp).clone() if dm is not None else None)
+            outs.append(eng.view(dm).view(shp).clone() if dm is not None else None)
         return (None, None, None, *outs)
