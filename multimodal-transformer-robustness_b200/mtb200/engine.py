@@ -745,6 +745,9 @@ class Engine:
         self._layout = None
         self._regions: Dict[int, Region] = {}
         self._enc_cache: Dict[tuple, EncPlan] = {}
+        self._merge_cache: Dict[tuple, list] = {}
+        self._warmed = set()
+        self.prewarm = True
         _install_fast_attrs(model)
         self.params = [p for p in model.parameters()]
         total = 0
@@ -804,6 +807,7 @@ class Engine:
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.plans.clear()
         self._enc_cache.clear()
+        self._merge_cache.clear()
 
     # ------------------------------------------------------------------ plan construction
     def _key(self, shapes, training, need_grad):
@@ -867,6 +871,7 @@ class Engine:
             B, Ls = max(B, B0), tuple(max(l, l0) for l, l0 in zip(Ls, Ls0))
             self.plans.clear()
             self._enc_cache.clear()
+            self._merge_cache.clear()
         names = list(m.modality_list)
         length = dict(zip(names, Ls))
         off = 0
@@ -948,24 +953,89 @@ class Engine:
         e.saved = None                       # only the Mats on the spec are needed from here on
         if len(self._enc_cache) > 4096:
             self._enc_cache.clear()
+            self._merge_cache.clear()
         self._enc_cache[key] = ep
         self.stats["enc_plans"] = self.stats.get("enc_plans", 0) + 1
         return ep
 
-    @staticmethod
-    def _merge(lst, eps, which):
-        """lock-step merge: launch `what` of every encoder of the stage goes into one grouped Op"""
-        buckets = {}
-        for ep in eps:
-            for rk, op in (ep.fwd if which == "fwd" else ep.bwd):
-                b = buckets.get(rk)
-                if b is None:
-                    buckets[rk] = [op, list(op.descs)]
-                else:
-                    b[1].extend(op.descs)
-        for rk in sorted(buckets):
-            op, descs = buckets[rk]
-            lst.append(Op(op.fn, op.dtype, descs, op.what))
+    def _warm(self, px_meta, training, need_grad):
+        """Build the (memoised) launch descriptors of every encoder invocation the sampler can draw -- every depth of
+        the `mems0` stacks, every cross branch, every slot subset of the masked `mems` stacks, with and without
+        a backward pass -- once per (shapes, mode).  ~0.1 s; afterwards a new configuration only costs the
+        lock-step merge of cached encoder plans plus the head."""
+        import itertools
+        m = self.model
+        d = m.d
+        names = list(m.modality_list)
+        B = px_meta[0][1]
+        length = {ch: px_meta[i][0] for i, ch in enumerate(names)}
+
+        def src(mat: Mat):
+            return (mat.ptr, B * mat.ld, mat.ld, 1)
+
+        def home(name):
+            enc = m.trans_mems0['mems0' + name] if len(name) == 1 else m.trans['cross' + name]
+            return Mat(self._regions[id(enc)].out, length[name[-1]] * B, d)
+        for ch in names:
+            enc = m.trans_mems0['mems0' + ch]
+            L = length[ch]
+            stage = Mat(self._stage_ptr[ch], L * B, d)
+            for depth in range(len(enc._ll) + 1):
+                for want in (True, False):
+                    self._enc_plan("mems0", ch, f"trans_mems0.mems0{ch}.", enc, L, L, B, d, depth, None, src(stage), None, want,
+                                   training, need_grad)
+        for k, enc in m.trans.items():
+            n = k[len("cross"):]
+            Lq, Lk = length[n[-1]], length[n[:-1][-1]]
+            for want in (True, False):
+                self._enc_plan("cross", n, f"trans.cross{n}.", enc, Lq, Lk, B, d, enc.active_layer_num, None, src(home(n[-1])),
+                               src(home(n[:-1])), want, training, need_grad)
+        for i, ch in enumerate(names):
+            enc = m.trans_mems['mems' + ch]
+            slots = sorted(m.modality_index_list[i].items(), key=lambda kv: kv[1])
+            for r in range(1, len(slots) + 1):
+                for sub in itertools.combinations(slots, r):
+                    Ls_ = {length[n[-1]] for n, _ in sub}
+                    if len(Ls_) != 1:
+                        continue
+                    L = Ls_.pop()
+                    mask_idx: List[int] = []
+                    for _, kk in sub:
+                        mask_idx.extend(range(kk * d, (kk + 1) * d))
+                    w = d * len(sub)
+                    cb = Mat(self._regions[id(enc)].cat, L * B, w)
+                    self._enc_plan("mems", ch, f"trans_mems.mems{ch}.", enc, L, L, B, w, enc.active_layer_num,
+                                   make_mask(mask_idx, self.device), src(cb), None, True, training, need_grad)
+        # The caches now hold ~10^5 long-lived ctypes objects; left in the youngest generations they make every
+        # cyclic-GC pass (triggered by the per-step descriptor allocations) walk all of them: ~0.7 ms per step.
+        import gc
+        gc.collect()
+        gc.freeze()
+
+    def _merge(self, lst, eps, which):
+        """lock-step merge: launch `what` of every encoder of the stage goes into one grouped Op.  The finalised
+        Ops of a stage composition are memoised too (they only reference persistent addresses)."""
+        key = (which, tuple(id(ep) for ep in eps))
+        ops = self._merge_cache.get(key)
+        if ops is None:
+            buckets = {}
+            for ep in eps:
+                for rk, op in (ep.fwd if which == "fwd" else ep.bwd):
+                    b = buckets.get(rk)
+                    if b is None:
+                        buckets[rk] = [op, list(op.descs)]
+                    else:
+                        b[1].extend(op.descs)
+            ops = []
+            for rk in sorted(buckets):
+                op, descs = buckets[rk]
+                o = Op(op.fn, op.dtype, descs, op.what)
+                o.finalize()
+                ops.append(o)
+            if len(self._merge_cache) > 8192:
+                self._merge_cache.clear()
+            self._merge_cache[key] = ops
+        lst.extend(ops)
 
     def _build(self, px_meta, training, need_grad, arena) -> Plan:
         """px_meta: per modality (L, B) of the front-end output [L, B, d] (strided view); the input
@@ -1155,7 +1225,7 @@ class Engine:
             plan._d_stage = {ch: plan_of[ch].spec.d_q_in for ch in stage_in if plan_of[ch].spec.d_out is not None}
 
         for op in pb.fwd + pb.bwd:
-            if type(op) is Op:
+            if type(op) is Op and op.arr is None:
                 op.finalize()
         plan.fwd, plan.bwd = pb.fwd, pb.bwd
         sites = dict(pb.sites)
@@ -1182,6 +1252,10 @@ class Engine:
         plan = self.plans.get(key)
         if plan is None:
             self._ensure_layout(px_meta)
+            wkey = (tuple(px_meta), training, need_grad, lib.mtb_get_gemm_mode(), id(self.enc_buf))
+            if self.prewarm and training and need_grad and wkey not in self._warmed:
+                self._warmed.add(wkey)
+                self._warm(px_meta, training, need_grad)
             self.arena.reset()
             plan = self._build(px_meta, training, need_grad, self.arena)
             plan.pred = self.view(plan._pred_mat)

@@ -39,11 +39,12 @@ class Mask:
     """An ``active_mask``: int32 device index tensor plus (when the indices are a union of
     equally sized, aligned blocks -- the only kind the model produces, src/dynamic_models2.py:243-251)
     the block structure, which lets the tensor-core GEMM address the blocks through TMA."""
-    __slots__ = ("idx", "seg_len", "segs", "segs_c")
+    __slots__ = ("idx", "seg_len", "segs", "segs_c", "host")
 
-    def __init__(self, idx: torch.Tensor, seg_len: int = 0, segs=None):
+    def __init__(self, idx: torch.Tensor, seg_len: int = 0, segs=None, host=None):
         self.idx, self.seg_len, self.segs = idx, seg_len, segs
         self.segs_c = None            # cached ctypes form (plan executor)
+        self.host = host              # pinned source of the asynchronous upload (kept alive with the mask)
 
     def numel(self) -> int:
         return self.idx.numel()
@@ -79,7 +80,14 @@ def make_mask(indices: Sequence[int], device) -> Mask:
     m = _mask_cache.get(key)
     if m is None:
         ln, segs = _block_structure(key[0])
-        m = Mask(torch.tensor(key[0], dtype=torch.int32, device=device), ln, segs)
+        host = torch.tensor(key[0], dtype=torch.int32)
+        if torch.device(device).type == "cuda":
+            # a pageable-memory upload would block until the stream has drained (a hidden sync in the training
+            # loop: ~1 ms per new mask); pinned + non_blocking only enqueues the copy
+            host = host.pin_memory()
+            m = Mask(host.to(device, non_blocking=True), ln, segs, host)
+        else:
+            m = Mask(host.to(device), ln, segs)
         if len(_mask_cache) > 4096:
             _mask_cache.clear()
         _mask_cache[key] = m

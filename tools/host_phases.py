@@ -22,6 +22,9 @@ T = {}
 def tick(name, t0):
     T[name] = T.get(name, 0.0) + time.perf_counter() - t0
 N = 40
+import gc
+if os.environ.get("NOGC"):
+    gc.disable()
 for it in range(N + 5):
     if it == 5:
         T.clear(); torch.cuda.synchronize(); tall = time.perf_counter()
