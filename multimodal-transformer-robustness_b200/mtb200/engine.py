@@ -151,12 +151,15 @@ def _segs(m: Optional[Mask]) -> Segs:
 
 class Op:
     """one grouped launch: C function + prebuilt descriptor array"""
-    __slots__ = ("fn", "arr", "n", "what", "descs", "dtype")
+    __slots__ = ("fn", "arr", "n", "what", "descs", "dtype", "side")
 
     def __init__(self, fn, dtype, descs, what):
         self.fn, self.dtype, self.descs, self.what = fn, dtype, list(descs), what
         self.n = len(self.descs)
         self.arr = None
+        # deferred weight-gradient launches feed nothing downstream in the backward chain: they may run on a
+        # second stream next to the (latency-bound) dgrad / attention / LayerNorm chain
+        self.side = what.startswith("wgrad[")
 
     def finalize(self):
         out = []
@@ -692,16 +695,31 @@ class Plan:
         self.n_bwd_launches = 0
 
 
-def _run(ops, stream: int):
+def _run(ops, stream: int, side=None):
+    """side: optional (torch side stream, fork event, join event) -- ops flagged `side` are launched there, ordered
+    after everything issued so far on the main stream; the main stream re-joins at the end of the list."""
     sp = C.c_void_p(stream)
+    forked = False
+    if side is not None:
+        s2, ev_fork, ev_join = side
+        sp2 = C.c_void_p(s2.cuda_stream)
     for op in ops:
         if type(op) is ZeroOp:
             op.t.zero_()
             continue
+        tgt = sp
+        if side is not None and op.side:
+            ev_fork.record()
+            s2.wait_event(ev_fork)
+            tgt = sp2
+            forked = True
         for arr, n in op.arr:
-            rc = op.fn(arr, n, sp)
+            rc = op.fn(arr, n, tgt)
             if rc != 0:
                 raise _lib.MtbError(f"{op.what} failed ({rc}): {lib.mtb_last_error().decode()}")
+    if forked:
+        ev_join.record(s2)
+        torch.cuda.current_stream().wait_event(ev_join)
 
 
 def _install_fast_attrs(model):
@@ -748,6 +766,8 @@ class Engine:
         self._merge_cache: Dict[tuple, list] = {}
         self._warmed = set()
         self.prewarm = True
+        self.side_stream_wgrad = True
+        self._side = None
         _install_fast_attrs(model)
         self.params = [p for p in model.parameters()]
         total = 0
@@ -1291,7 +1311,12 @@ class Engine:
             except Exception:
                 setattr(plan, gattr, None)
                 self.graph_after = -1          # capture unsupported here: stay eager
-        _run(ops, stream)
+        side = None
+        if which == "bwd" and self.side_stream_wgrad and not torch.cuda.is_current_stream_capturing():
+            if self._side is None:
+                self._side = (torch.cuda.Stream(device=self.device), torch.cuda.Event(), torch.cuda.Event())
+            side = self._side
+        _run(ops, stream, side)
         self.stats["eager_runs"] += 1
 
     def forward(self, px: Sequence[torch.Tensor]) -> torch.Tensor:
