@@ -1275,7 +1275,11 @@ class Engine:
             wkey = (tuple(px_meta), training, need_grad, lib.mtb_get_gemm_mode(), id(self.enc_buf))
             if self.prewarm and training and need_grad and wkey not in self._warmed:
                 self._warmed.add(wkey)
-                self._warm(px_meta, training, need_grad)
+                try:
+                    self._warm(px_meta, training, need_grad)
+                except Exception as exc:          # pre-building is an optimisation only: plans still build on demand
+                    import warnings
+                    warnings.warn(f"mtb200 engine: encoder-plan prewarm skipped ({type(exc).__name__}: {exc})")
             self.arena.reset()
             plan = self._build(px_meta, training, need_grad, self.arena)
             plan.pred = self.view(plan._pred_mat)

@@ -270,3 +270,51 @@ def test_flat_adam_equals_torch_clip_plus_adam():
     assert len(seen) >= 4          # several different active sets were exercised
     st = opt.state_dict()
     assert int(st["steps"].max()) <= 25 and int(st["steps"].min()) >= 0
+
+
+def test_engine_memoised_plans_match_per_op_path_over_random_configs():
+    """Plans are assembled from memoised per-encoder launch descriptors living in persistent regions.  After the
+    caches are warm (several configurations drawn), every further random configuration must still equal the
+    per-op autograd path (same kernels, no plan executor) -- predictions and every gradient, fp32 engine."""
+    from mtb200 import ops
+    from mtb200.dynamic_models2 import DynamicMULTModel
+    from mtb200.train import ALL_POOL_3, HypParams, sample_next_config
+    torch.manual_seed(5)
+    ops.set_gemm_mode("fp32")
+    lens = (6, 14, 14)
+    m = DynamicMULTModel(origin_dimensions=[12, 7, 5], dimension=40, num_heads=8, head_dim=5, layers_single_attn=2,
+                         layers_hybrid_attn=2, layers_self_attn=1, attn_dropout=[0.1, 0.1, 0.0, 0.0], relu_dropout=0.1,
+                         res_dropout=0.3, out_dropout=0.1, embed_dropout=0.3, attn_mask=True, output_dim=1,
+                         modality_set=["l", "a", "v"], all_steps=False, front_end="conv1d").cuda()
+    hyp = HypParams(["l", "a", "v"], ALL_POOL_3, 2, 1, 2, 40, 8, 5, seq_lens=lens)
+    xs = [torch.randn(4, lens[i], d, device="cuda") for i, d in enumerate((12, 7, 5))]
+    y = torch.randn(4, 1, device="cuda")
+    m.train()                                   # prewarm + cache fill happen on the training path
+    for _ in range(6):
+        sample_next_config(m, hyp)
+        m.zero_grad()
+        pred, _ = m(xs)
+        torch.nn.functional.l1_loss(pred, y).backward()
+    eng = m.engine()
+    assert eng.stats.get("enc_plans", 0) > 0 and len(eng._merge_cache) > 0
+    m.eval()
+    seen = set()
+    for it in range(8):
+        sample_next_config(m, hyp)
+        seen.add((tuple(m.active_modality), str(m.active_cross_output)))
+        res = {}
+        for use in (True, False):
+            m.use_engine = use
+            m.zero_grad()
+            pred, _ = m(xs)
+            torch.nn.functional.l1_loss(pred, y).backward()
+            res[use] = (pred.detach().clone(), {k: (None if p.grad is None else p.grad.detach().clone()) for k, p in m.named_parameters()})
+        assert_rel(res[True][0], res[False][0], 2e-5, f"pred (config {it})")
+        for k in res[True][1]:
+            a, b = res[True][1][k], res[False][1][k]
+            assert (a is None) == (b is None) or (b is not None and float(b.abs().max()) == 0.0) or \
+                (a is not None and float(a.abs().max()) == 0.0), (it, k)
+            if a is not None and b is not None and float(b.abs().max()) > 0:
+                assert_rel(a, b, 1e-4, f"grad {k} (config {it})")
+    m.use_engine = True
+    assert len(seen) >= 3

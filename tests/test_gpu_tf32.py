@@ -21,7 +21,9 @@ def tf32():
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 208, 32), (800, 600, 200), (8000, 200, 200), (130, 64, 40), (8000, 800, 200),
-                                   (16, 3000, 600), (300, 200, 800), (1, 256, 512), (257, 1536, 512)])
+                                   (16, 3000, 600), (300, 200, 800), (1, 256, 512), (257, 1536, 512),
+                                   # few tiles + long reduction: split-K with the TMA reduce-add epilogue (the head's shapes)
+                                   (16, 200, 3000), (16, 416, 3008), (40, 64, 4096)])
 def test_tc_linear_fwd_dgrad_wgrad(tf32, M, N, K):
     ops = tf32
     g = torch.Generator().manual_seed(M + N + K)
