@@ -33,9 +33,9 @@ __device__ __forceinline__ bool a_mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"     // %3: suspend-time hint -- the warp sleeps in
+      "selp.u32 %0, 1, 0, p;\n\t}"                                        // hardware instead of spinning on issue slots
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
   return ok != 0;
 }
 __device__ __forceinline__ void a_mbar_wait(uint32_t bar, uint32_t parity) {
@@ -71,9 +71,10 @@ __device__ __forceinline__ void a_tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 // round-to-nearest TF32 (the tensor core would otherwise truncate the low 13 mantissa bits)
 __device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  // round-to-nearest (ties away) at the 10-bit TF32 mantissa: add half an ulp (bit 12) to the magnitude; the tensor core
+  // then truncates bits [0, 13).  Same result as cvt.rna.tf32.f32 for every finite input (all values rounded here are
+  // finite: probabilities and their products); one integer add instead of a compare + predicated add.
+  return __uint_as_float(__float_as_uint(x) + 0x1000u);
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -266,9 +267,9 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
   const int i_last = min(Lq, i0 + TQ) - 1;
   const int j_end = min(Lk, i_last + off + 1);
   const int T = (j_end + TK - 1) / TK;
-  stage_tile<false, AF_THREADS>(Qs, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TQ);
-  stage_tile<false, AF_THREADS>(KV, d.k, d.ldk, d.B, b, h, hd, 0, Lk, TK);
-  stage_tile<true, AF_THREADS>(KV + TK * 128, d.v, d.ldv, d.B, b, h, hd, 0, Lk, TK);
+  stage_rows256<false>(Qs, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TQ);
+  stage_rows256<false>(KV, d.k, d.ldk, d.B, b, h, hd, 0, Lk, TK);
+  stage_rows256<true>(KV + TK * 128, d.v, d.ldv, d.B, b, h, hd, 0, Lk, TK);
   stage_wait();
   fence_async_smem();
   tc_fence_before();
@@ -304,8 +305,8 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
     uint8_t* nxt = KV + ((t + 1) & 1) * (2 * TK * 128);
     ATRACE(8 + t * 8 + 0);
     if (t + 1 < T) {                         // prefetch the next key / value tile behind this tile's softmax
-      stage_tile<false, AF_THREADS>(nxt, d.k, d.ldk, d.B, b, h, hd, j0 + TK, Lk, TK);
-      stage_tile<true, AF_THREADS>(nxt + TK * 128, d.v, d.ldv, d.B, b, h, hd, j0 + TK, Lk, TK);
+      stage_rows256<false>(nxt, d.k, d.ldk, d.B, b, h, hd, j0 + TK, Lk, TK);
+      stage_rows256<true>(nxt + TK * 128, d.v, d.ldv, d.B, b, h, hd, j0 + TK, Lk, TK);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     ATRACE(8 + t * 8 + 1);

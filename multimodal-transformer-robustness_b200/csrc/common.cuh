@@ -52,9 +52,14 @@ struct Philox {
   uint32_t k0, k1;
   __host__ __device__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
   __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
-    const uint64_t p = (uint64_t)a * b;      // one IMAD.WIDE.U32
+#ifdef __CUDA_ARCH__
+    // exactly one IMAD.WIDE.U32 (the C++ form below makes the compiler append a 64-bit "+ 0" per product)
+    asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+#else
+    const uint64_t p = (uint64_t)a * b;
     hi = (uint32_t)(p >> 32);
     lo = (uint32_t)p;
+#endif
   }
   __host__ __device__ inline uint4 operator()(uint64_t ctr) const {
     uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x5bd1e995u, c3 = 0u;

@@ -74,9 +74,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"     // %3: suspend-time hint -- the warp sleeps in
+      "selp.u32 %0, 1, 0, p;\n\t}"                                        // hardware instead of spinning on issue slots
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
   return ok != 0;
 }
 // bounded wait: a protocol bug must trap, never hang the GPU
