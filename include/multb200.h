@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MTB_ABI_VERSION 10
+#define MTB_ABI_VERSION 11
 #define MTB_MAX_GROUP 24
 
 /* Dropout RNG: Philox4x32-7.  Element `i` of a dropout site is kept iff
@@ -212,6 +212,24 @@ typedef struct {
   float scale; float p; mtb_rng rng;
 } mtb_attn_bwd_desc;
 int mtb_attn_bwd(const mtb_attn_bwd_desc* d, int n, void* stream);
+
+/* ---- plan executor: a whole list of grouped launches in one call -----------------------
+ * North-star item (d) / SURVEY.md 8b `mtb_stage_launch`: the host plan executor (mtb200/engine.py) compiles one
+ * sampled configuration into flat lists of grouped launches; this entry point issues such a list natively, so the
+ * per-launch cost is one driver call instead of one interpreter round trip.  `kind` selects the entry point the
+ * descriptor array belongs to; ops flagged `side` (deferred weight gradients, which feed nothing downstream) are
+ * issued on `side_stream`, ordered after everything issued before them on `stream`; `stream` re-joins `side_stream`
+ * before the call returns.  side_stream == NULL runs everything on `stream`.  Stops at the first failing op. */
+enum { MTB_OP_EMBED_FWD = 0, MTB_OP_EMBED_BWD = 1, MTB_OP_ADDN = 2, MTB_OP_RESLN_FWD = 3, MTB_OP_RESLN_BWD = 4,
+       MTB_OP_LINEAR_FWD = 5, MTB_OP_LINEAR_BWD = 6, MTB_OP_ATTN_FWD = 7, MTB_OP_ATTN_BWD = 8 };
+typedef struct {
+  int32_t kind;          /* MTB_OP_* */
+  int32_t n;             /* descriptors in `descs` (<= MTB_MAX_GROUP) */
+  const void* descs;     /* host array of the matching descriptor type */
+  int32_t side;          /* 1: may run on the side stream */
+  int32_t reserved;
+} mtb_op;
+int mtb_run_ops(const mtb_op* ops, int n_ops, void* stream, void* side_stream);
 
 /* ---- fused gradient clip + Adam over the flat arenas --------------------------------
  * Replaces `torch.nn.utils.clip_grad_norm_(model.parameters(), clip); optimizer.step()` of

@@ -115,6 +115,46 @@ int mtb_attn_bwd(const mtb_attn_bwd_desc* d, int n, void* stream) {
   return mtb::attn_bwd_simt(d, n, (cudaStream_t)stream);
 }
 
+int mtb_run_ops(const mtb_op* ops, int n_ops, void* stream, void* side_stream) {
+  MTB_CHECK(ops != nullptr || n_ops == 0, "run_ops: null op list");
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t st = (cudaStream_t)stream, s2 = (cudaStream_t)side_stream;
+  if (s2 && !ev_fork) {
+    MTB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    MTB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
+  bool forked = false;
+  for (int i = 0; i < n_ops; ++i) {
+    const mtb_op& o = ops[i];
+    void* tgt = stream;
+    if (s2 && o.side) {
+      MTB_CUDA(cudaEventRecord(ev_fork, st));
+      MTB_CUDA(cudaStreamWaitEvent(s2, ev_fork, 0));
+      tgt = side_stream;
+      forked = true;
+    }
+    int rc;
+    switch (o.kind) {
+      case MTB_OP_EMBED_FWD: rc = mtb_embed_fwd((const mtb_embed_desc*)o.descs, o.n, tgt); break;
+      case MTB_OP_EMBED_BWD: rc = mtb_embed_bwd((const mtb_embed_desc*)o.descs, o.n, tgt); break;
+      case MTB_OP_ADDN: rc = mtb_addn((const mtb_addn_desc*)o.descs, o.n, tgt); break;
+      case MTB_OP_RESLN_FWD: rc = mtb_resln_fwd((const mtb_resln_desc*)o.descs, o.n, tgt); break;
+      case MTB_OP_RESLN_BWD: rc = mtb_resln_bwd((const mtb_resln_bwd_desc*)o.descs, o.n, tgt); break;
+      case MTB_OP_LINEAR_FWD: rc = mtb_linear_fwd((const mtb_linear_desc*)o.descs, o.n, tgt); break;
+      case MTB_OP_LINEAR_BWD: rc = mtb_linear_bwd((const mtb_linear_bwd_desc*)o.descs, o.n, tgt); break;
+      case MTB_OP_ATTN_FWD: rc = mtb_attn_fwd((const mtb_attn_desc*)o.descs, o.n, tgt); break;
+      case MTB_OP_ATTN_BWD: rc = mtb_attn_bwd((const mtb_attn_bwd_desc*)o.descs, o.n, tgt); break;
+      default: MTB_CHECK(false, "run_ops: unknown op kind %d at position %d", o.kind, i);
+    }
+    if (rc != 0) return (i + 1) * 16 + (rc < 0 ? -rc : rc);   // position of the failing op (message already set)
+  }
+  if (forked) {
+    MTB_CUDA(cudaEventRecord(ev_join, s2));
+    MTB_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+  }
+  return 0;
+}
+
 int mtb_adam_step(const mtb_adam_desc* d, void* stream) {
   MTB_CHECK(d != nullptr, "adam_step: null descriptor");
   return mtb::adam_step(d, (cudaStream_t)stream);

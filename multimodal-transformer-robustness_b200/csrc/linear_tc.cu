@@ -419,10 +419,17 @@ constexpr int COLSUM_ROWS = 64;
 struct ColsumArgs {
   const float* dY; int64_t ldy; float* db; int M, N, seg_len; uint8_t seg[TC_MAXSEG];
 };
-__global__ void __launch_bounds__(128) colsum_kernel(const ColsumArgs a) {
+struct ColsumGroup {
+  ColsumArgs a[MTB_MAX_GROUP];
+  int n;
+};
+// one launch for every bias gradient of a backward call: blockIdx.z selects the problem, the grid covers the
+// largest one (surplus blocks exit at once)
+__global__ void __launch_bounds__(128) colsum_kernel(const __grid_constant__ ColsumGroup g) {
+  const ColsumArgs& a = g.a[blockIdx.z];
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int m0 = blockIdx.y * COLSUM_ROWS, m1 = min(a.M, m0 + COLSUM_ROWS);
-  if (n >= a.N) return;
+  if (n >= a.N || m0 >= a.M) return;
   const float* p = a.dY + n;
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   int m = m0;
@@ -624,6 +631,9 @@ int linear_fwd_tc(const mtb_linear_desc* d, int n, cudaStream_t st) {
 int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
   TcProblem dg[MTB_MAX_GROUP], wg[MTB_MAX_GROUP];
   mtb_linear_bwd_desc rest[MTB_MAX_GROUP];
+  ColsumGroup cs;
+  cs.n = 0;
+  int cs_gx = 0, cs_gy = 0;
   int ndg = 0, nwg = 0, nrest = 0;
   for (int i = 0; i < n; ++i) {
     const mtb_linear_bwd_desc& x = d[i];
@@ -677,17 +687,19 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
     if (x.dX) dg[ndg++] = qd;
     if (x.dW) wg[nwg++] = qw;
     if (x.db && x.act != 1) {
-      ColsumArgs ca{};
+      ColsumArgs& ca = cs.a[cs.n++];
+      ca = ColsumArgs{};
       ca.dY = dYp; ca.ldy = ldyp; ca.db = x.db; ca.M = x.M; ca.N = x.N; ca.seg_len = an.len;
       for (int s = 0; s < TC_MAXSEG; ++s) ca.seg[s] = s < an.n ? an.phys[s] : 0;
-      dim3 grid((x.N + 127) / 128, (x.M + COLSUM_ROWS - 1) / COLSUM_ROWS);
-      colsum_kernel<<<grid, 128, 0, st>>>(ca);
-      mtb::note_launch();
-      MTB_CUDA(cudaGetLastError());
+      cs_gx = cs_gx > (x.N + 127) / 128 ? cs_gx : (x.N + 127) / 128;
+      cs_gy = cs_gy > (x.M + COLSUM_ROWS - 1) / COLSUM_ROWS ? cs_gy : (x.M + COLSUM_ROWS - 1) / COLSUM_ROWS;
     }
   }
-  // dgrad and wgrad problems are independent of each other: one launch carries both kinds
-  // (the kernel switches operand majors per problem), which fills the SMs better than two launches
+  if (cs.n > 0) {
+    colsum_kernel<<<dim3(cs_gx, cs_gy, cs.n), 128, 0, st>>>(cs);
+    mtb::note_launch();
+    MTB_CUDA(cudaGetLastError());
+  }
   // ---- launch-wide tiling policy (B operands are MN-major here: 32-wide TMA boxes, so BJ is free to change) ----
   int dg_ctas = 0;
   for (int i = 0; i < ndg; ++i) dg_ctas += tiles_of(dg[i].i_len, dg[i].i_nseg, dg[i].j_len, dg[i].j_nseg, dg[i].BJ);

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MTB_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libmultb200.so")   # MTB_LIB: instrumented debug builds
 
 MAX_GROUP = 24
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 
 class MtbError(RuntimeError):
@@ -98,6 +98,14 @@ class AdamDesc(C.Structure):
                 ("eps", C.c_float), ("weight_decay", C.c_float), ("max_norm", C.c_float)]
 
 
+class OpDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n", C.c_int32), ("descs", C.c_void_p), ("side", C.c_int32), ("reserved", C.c_int32)]
+
+
+OP_KIND = {"mtb_embed_fwd": 0, "mtb_embed_bwd": 1, "mtb_addn": 2, "mtb_resln_fwd": 3, "mtb_resln_bwd": 4,
+           "mtb_linear_fwd": 5, "mtb_linear_bwd": 6, "mtb_attn_fwd": 7, "mtb_attn_bwd": 8}
+
+
 # name -> (argtypes, restype); every symbol include/multb200.h declares
 SYMBOLS = {
     "mtb_abi_version": ([], C.c_int),
@@ -120,6 +128,7 @@ SYMBOLS = {
     "mtb_attn_fwd": ([C.POINTER(AttnDesc), C.c_int, C.c_void_p], C.c_int),
     "mtb_attn_bwd": ([C.POINTER(AttnBwdDesc), C.c_int, C.c_void_p], C.c_int),
     "mtb_adam_step": ([C.POINTER(AdamDesc), C.c_void_p], C.c_int),
+    "mtb_run_ops": ([C.POINTER(OpDesc), C.c_int, C.c_void_p, C.c_void_p], C.c_int),
 }
 
 
@@ -134,6 +143,7 @@ def _load():
         fn = getattr(lib, name)          # AttributeError here = ABI drift between header and library
         fn.argtypes = argtypes
         fn.restype = restype
+        fn.mtb_name = name
     v = lib.mtb_abi_version()
     if v != ABI_VERSION:
         raise ImportError(f"libmultb200.so ABI version {v} != binding version {ABI_VERSION}; rebuild")

@@ -170,6 +170,21 @@ class Op:
         self.descs = None
 
 
+class Batch:
+    """a run of finalised Ops packed for ONE native call (mtb_run_ops): [(kind, n, descriptor array, side)]"""
+    __slots__ = ("arr", "n", "ops", "launches")
+
+    def __init__(self, ops):
+        entries = []
+        for op in ops:
+            kind = _lib.OP_KIND[op.fn.mtb_name]
+            for arr, n in op.arr:
+                entries.append((kind, n, C.addressof(arr), 1 if op.side else 0, 0))
+        self.ops = ops                        # keeps the descriptor arrays alive
+        self.n = self.launches = len(entries)
+        self.arr = (_lib.OpDesc * len(entries))(*entries)
+
+
 class ZeroOp:
     __slots__ = ("t",)
 
@@ -704,7 +719,14 @@ def _run(ops, stream: int, side=None):
         s2, ev_fork, ev_join = side
         sp2 = C.c_void_p(s2.cuda_stream)
     for op in ops:
-        if type(op) is ZeroOp:
+        tp = type(op)
+        if tp is Batch:
+            rc = lib.mtb_run_ops(op.arr, op.n, sp, sp2 if side is not None else None)
+            if rc != 0:
+                what = op.ops[0].what
+                raise _lib.MtbError(f"batched launches starting at {what} failed ({rc}): {lib.mtb_last_error().decode()}")
+            continue
+        if tp is ZeroOp:
             op.t.zero_()
             continue
         tgt = sp
@@ -1036,8 +1058,8 @@ class Engine:
         """lock-step merge: launch `what` of every encoder of the stage goes into one grouped Op.  The finalised
         Ops of a stage composition are memoised too (they only reference persistent addresses)."""
         key = (which, tuple(id(ep) for ep in eps))
-        ops = self._merge_cache.get(key)
-        if ops is None:
+        ops = self._merge_cache.get(key, False)
+        if ops is False:
             buckets = {}
             for ep in eps:
                 for rk, op in (ep.fwd if which == "fwd" else ep.bwd):
@@ -1052,10 +1074,12 @@ class Engine:
                 o = Op(op.fn, op.dtype, descs, op.what)
                 o.finalize()
                 ops.append(o)
+            ops = Batch(ops) if ops else None
             if len(self._merge_cache) > 8192:
                 self._merge_cache.clear()
             self._merge_cache[key] = ops
-        lst.extend(ops)
+        if ops is not None:
+            lst.append(ops)
 
     def _build(self, px_meta, training, need_grad, arena) -> Plan:
         """px_meta: per modality (L, B) of the front-end output [L, B, d] (strided view); the input
@@ -1263,8 +1287,8 @@ class Engine:
                 aps.append(p_)
         plan.sites, plan.rng_span = sites, (STEP_SPAN if training else 0)
         plan.active_params = aps
-        plan.n_fwd_launches = sum(len(op.arr) if type(op) is Op else 1 for op in pb.fwd)
-        plan.n_bwd_launches = sum(len(op.arr) if type(op) is Op else 1 for op in pb.bwd)
+        count = lambda lst: sum(len(op.arr) if type(op) is Op else op.launches if type(op) is Batch else 1 for op in lst)
+        plan.n_fwd_launches, plan.n_bwd_launches = count(pb.fwd), count(pb.bwd)
         return plan
 
     def plan_for(self, px_meta, training, need_grad) -> Plan:

@@ -87,18 +87,20 @@ def train_step(model, optimizer, criterion, inputs, target, hyp: HypParams, grad
     loss = criterion(preds, target)
     sample_next_config(model, hyp)           # config of step n+1 is drawn between fwd and bwd of step n
     loss.backward()
-    if hasattr(model, "prefetch_plan"):
-        model.prefetch_plan(inputs)          # next step's plan is built while the GPU runs this step's backward
     eng = getattr(model, "_engine", None)
     live = eng is not None and getattr(eng, "_grads_live", False)
     if grad_sync is not None:
         grad_sync(eng if live else None)
     if hasattr(optimizer, "step_clipped"):     # mtb200.optim.FlatAdam: clip + Adam fused over the flat arenas
         optimizer.step_clipped(hyp.clip)
+        if hasattr(model, "prefetch_plan"):
+            model.prefetch_plan(inputs)      # next step's plan is built while the GPU still runs this step's backward + update
         return loss
     if live:   # same result as torch's clip over the active set, computed on the flat gradient arena
         eng.clip_grad_norm_(hyp.clip, [p.grad for p in model._outside_engine_params() if p.grad is not None])
     else:
         torch.nn.utils.clip_grad_norm_(model.parameters(), hyp.clip)
     optimizer.step()
+    if hasattr(model, "prefetch_plan"):
+        model.prefetch_plan(inputs)
     return loss

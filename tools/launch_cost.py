@@ -26,7 +26,10 @@ for c in range(12):
     sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     for which in (plan.fwd, plan.bwd):
         torch.cuda.synchronize()
+        flat = []
         for op in which:
+            flat.extend(op.ops if type(op) is E.Batch else [op])
+        for op in flat:
             if type(op) is E.ZeroOp:
                 continue
             for arr, n in op.arr:
