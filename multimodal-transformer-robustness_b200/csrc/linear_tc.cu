@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
+#include <time.h>
 
 namespace mtb {
 
@@ -55,9 +56,13 @@ struct alignas(64) TcProblem {
   int act; float p; mtb_rng rng;
 };
 
-struct TcGroup {
-  TcProblem d[MTB_MAX_GROUP];
-  int start[MTB_MAX_GROUP + 1];
+// The problem list travels in the kernel parameter block.  Parameter blocks above 4 KB take a slower launch path
+// (measured: ~6.5 us of GPU idle before every GEMM kernel with the 24-problem, 15 KB block vs ~2 us for the other
+// kernels), so the kernel is instantiated for several capacities and a launch uses the smallest that fits.
+template <int CAP>
+struct TcGroupT {
+  TcProblem d[CAP];
+  int start[CAP + 1];
   int n;
 };
 
@@ -142,7 +147,8 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #define TRACE(i) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ TcGroup g) {
+template <int CAP>
+__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ TcGroupT<CAP> g) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
@@ -464,8 +470,8 @@ static EncodeTiledFn get_encode() {
 
 // Row-major fp32 matrix with leading dimension ld seen as 4-D {col_in_block, col_block, row_in_block,
 // row_block}: column blocks of clen (ncb of them), row blocks of rlen (nrb of them); box = bx cols x by rows.
-static bool make_map(CUtensorMap* m, const float* ptr, int64_t ld, int64_t clen, int64_t ncb, int64_t rlen, int64_t nrb,
-                     int bx, int by, bool mn_major) {
+static bool encode_map(CUtensorMap* m, const float* ptr, int64_t ld, int64_t clen, int64_t ncb, int64_t rlen, int64_t nrb,
+                       int bx, int by, bool mn_major) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   if (ncb > 1 && (clen % 4) != 0) return false;
@@ -477,6 +483,36 @@ static bool make_map(CUtensorMap* m, const float* ptr, int64_t ld, int64_t clen,
                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+
+// A tensor map is a pure function of (address, shape, strides, box, swizzle).  The plan executor launches the same
+// operands step after step (persistent arenas), and cuTensorMapEncodeTiled costs ~0.4 us x 3 maps x every problem of
+// every GEMM launch -- on the critical path, because the GPU finishes these small kernels faster than the host issues
+// them.  Direct-mapped cache of encoded maps (single host thread per device context, like the rest of the library).
+struct MapKey {
+  const void* ptr; int64_t ld, clen, ncb, rlen, nrb; int32_t bx, by, mn, pad;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && ld == o.ld && clen == o.clen && ncb == o.ncb && rlen == o.rlen && nrb == o.nrb && bx == o.bx && by == o.by &&
+           mn == o.mn;
+  }
+};
+struct MapEntry { MapKey key; CUtensorMap map; bool valid; };
+constexpr int MAP_CACHE = 1 << 14;
+static MapEntry* g_map_cache = nullptr;
+
+static bool make_map(CUtensorMap* m, const float* ptr, int64_t ld, int64_t clen, int64_t ncb, int64_t rlen, int64_t nrb,
+                     int bx, int by, bool mn_major) {
+  if (!g_map_cache) g_map_cache = (MapEntry*)calloc(MAP_CACHE, sizeof(MapEntry));
+  MapKey k{ptr, ld, clen, ncb, rlen, nrb, bx, by, mn_major ? 1 : 0, 0};
+  uint64_t h = (uint64_t)(uintptr_t)ptr * 0x9E3779B97F4A7C15ull;
+  h ^= ((uint64_t)ld * 0xC2B2AE3D27D4EB4Full) ^ ((uint64_t)clen << 17) ^ ((uint64_t)rlen << 29) ^ ((uint64_t)ncb << 7) ^ ((uint64_t)nrb << 11) ^
+       ((uint64_t)bx << 41) ^ ((uint64_t)by << 47) ^ ((uint64_t)k.mn << 53);
+  h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+  MapEntry* e = g_map_cache ? &g_map_cache[h & (MAP_CACHE - 1)] : nullptr;
+  if (e && e->valid && e->key == k) { *m = e->map; return true; }
+  if (!encode_map(m, ptr, ld, clen, ncb, rlen, nrb, bx, by, mn_major)) return false;
+  if (e) { e->key = k; e->map = *m; e->valid = true; }
+  return true;
 }
 
 static bool tma_ok(const float* p, int64_t ld) { return p != nullptr && ((((uintptr_t)p) & 15) == 0) && (ld % 4 == 0) && ld > 0; }
@@ -540,25 +576,25 @@ static bool make_axis(Axis& a, int total, const int32_t* idx, const mtb_segs& sg
 static void ident(uint8_t* d, int n) { for (int s = 0; s < TC_MAXSEG; ++s) d[s] = (uint8_t)(s < n ? s : 0); }
 static void copy_phys(uint8_t* d, const Axis& a) { for (int s = 0; s < TC_MAXSEG; ++s) d[s] = s < a.n ? a.phys[s] : 0; }
 
-static bool g_attr_done = false;
-static int launch_tc(const TcProblem* probs, int n, cudaStream_t st) {
-  if (n == 0) return 0;
-  if (!g_attr_done) {
-    MTB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048));
-    g_attr_done = true;
+template <int CAP>
+static int launch_tc_cap(const TcProblem* probs, int n, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    MTB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048));
+    attr_done = true;
   }
-  TcGroup g;
+  TcGroupT<CAP> g;
   g.n = n;
   int tot = 0;
   size_t smem = 0;
   for (int i = 0; i < n; ++i) {
-    TcProblem q = probs[i];
+    TcProblem& q = g.d[i];
+    q = probs[i];
     const size_t stage = (size_t)TC_A_BYTES + (((size_t)(q.b_mn ? ((q.BJ + 31) / 32) * 32 : q.BJ) * 128 + 1023) & ~(size_t)1023);
     int stages = (int)(TC_SMEM_BUDGET / stage);
     stages = stages > TC_MAX_STAGES ? TC_MAX_STAGES : (stages < 2 ? 2 : stages);
     q.stages = stages;
     if (stage * stages + 1024 > smem) smem = stage * stages + 1024;
-    g.d[i] = q;
     g.start[i] = tot;
     tot += ((q.i_len + TC_BI - 1) / TC_BI) * q.i_nseg * ((q.j_len + q.BJ - 1) / q.BJ) * q.j_nseg * q.splits;
   }
@@ -572,13 +608,23 @@ static int launch_tc(const TcProblem* probs, int n, cudaStream_t st) {
               g.d[i].a_mn, g.d[i].b_mn, g.d[i].epi);
     fprintf(stderr, "\n");
   }
-  gemm_tc_kernel<<<tot, TC_THREADS, smem, st>>>(g);
+  gemm_tc_kernel<CAP><<<tot, TC_THREADS, smem, st>>>(g);
   mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
   return 0;
 }
+static int launch_tc(const TcProblem* probs, int n, cudaStream_t st) {
+  if (n == 0) return 0;
+  if (n <= 2) return launch_tc_cap<2>(probs, n, st);          // 1.3 KB of parameters
+  if (n <= 6) return launch_tc_cap<6>(probs, n, st);          // 3.9 KB: still on the fast launch path
+  if (n <= 12) return launch_tc_cap<12>(probs, n, st);
+  return launch_tc_cap<MTB_MAX_GROUP>(probs, n, st);
+}
 
 int linear_fwd_tc(const mtb_linear_desc* d, int n, cudaStream_t st) {
+  static const bool dbgt = getenv("MTB_TC_TIMING") != nullptr;
+  timespec ts0{}, ts1{}, ts2{};
+  if (dbgt) clock_gettime(CLOCK_MONOTONIC, &ts0);
   TcProblem tc[MTB_MAX_GROUP];
   mtb_linear_desc rest[MTB_MAX_GROUP];
   Axis ans[MTB_MAX_GROUP], aks[MTB_MAX_GROUP];
@@ -622,7 +668,14 @@ int linear_fwd_tc(const mtb_linear_desc* d, int n, cudaStream_t st) {
     }
     ++ntc;
   }
+  if (dbgt) clock_gettime(CLOCK_MONOTONIC, &ts1);
   int rc = launch_tc(tc, ntc, st);
+  if (dbgt) {
+    clock_gettime(CLOCK_MONOTONIC, &ts2);
+    const double a = (ts1.tv_sec - ts0.tv_sec) * 1e6 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-3;
+    const double b = (ts2.tv_sec - ts1.tv_sec) * 1e6 + (ts2.tv_nsec - ts1.tv_nsec) * 1e-3;
+    if (a + b > 30.0) fprintf(stderr, "[tc-timing] fwd n=%d ntc=%d nrest=%d build %.1f us launch %.1f us (N0 %d K0 %d M0 %d)\n", n, ntc, nrest, a, b, d[0].N, d[0].K, d[0].M);
+  }
   if (rc) return rc;
   if (nrest) return linear_fwd_simt(rest, nrest, st);
   return 0;
@@ -756,7 +809,10 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
 namespace mtb {
 int preload_linear_tc() {
   int bad = 0;
-  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, gemm_tc_kernel) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, gemm_tc_kernel<2>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, gemm_tc_kernel<6>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, gemm_tc_kernel<12>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, gemm_tc_kernel<MTB_MAX_GROUP>) != cudaSuccess) ++bad; }
   { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, actgrad_kernel) != cudaSuccess) ++bad; }
   { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, colsum_kernel) != cudaSuccess) ++bad; }
   return bad;
