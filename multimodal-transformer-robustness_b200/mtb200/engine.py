@@ -105,7 +105,7 @@ class Region:
 
 _FWD_RANK = {"ln0_kv": 0, "in_proj": 1, "attn": 2, "out_proj": 3, "res_ln1": 4, "fc1": 5, "fc2": 6, "res_ln2": 7}
 _BWD_RANK = {"res_ln2_bwd": 0, "fc2_bwd": 1, "fc1_bwd": 2, "res_ln1_bwd": 3, "out_proj_bwd": 4, "attn_bwd": 5, "in_proj_bwd": 6,
-             "wgrad": 7, "ln0_kv_bwd": 8}
+             "in_proj_bwd_q": 7, "wgrad": 8, "ln0_kv_bwd": 9}
 
 
 def _rank(what: str) -> Tuple[int, int]:
@@ -207,12 +207,24 @@ class EncSpec:
         self.kv_src = kv_src            # same for the key/value stream, or None
         self.out: Mat = out             # where the final LayerNorm writes [Lq*B, E] (ld may exceed E)
         self.cross = kv_src is not None
+        # last-row pruning: with all_steps=False only h[-1] of a `mems` stack reaches the head
+        # (src/dynamic_models2.py:257), so its FINAL layer only needs the last query step: keys / values still
+        # come from every step, everything on the query side (attention rows, out-projection, FFN, LayerNorms)
+        # runs on B rows instead of L*B.  Results-identical.
+        self.prune_last = False
         # filled by the forward builder (saved for backward)
         self.saved: dict = {}
         self.d_out: Optional[Mat] = None
         self.d_q_in: Optional[Mat] = None
         self.d_k_in: Optional[Mat] = None
         self.d_v_in: Optional[Mat] = None
+
+
+def _qrows(e, i):
+    """(first row, row count) of the query-side tensors of layer i"""
+    if e.prune_last and i == e.n_layers - 1:
+        return (e.Lq - 1) * e.B, e.B
+    return 0, e.Lq * e.B
 
 
 class PlanBuilder:
@@ -229,12 +241,14 @@ class PlanBuilder:
         self._active_ids = set()
 
     # -- helpers
-    def rng(self, tag: str, n_elems: int, p: float) -> Rng:
+    def rng(self, tag: str, n_elems: int, p: float, last_rows: bool = False) -> Rng:
+        """last_rows: the site only covers the LAST sequence step of the tensor the reference drops (pruned final
+        `mems` layer); recorded so tests can embed the mask into the full-size one the oracle expects."""
         if not (self.training and p > 0.0):
             return _NO_RNG
         off = self.rng_off
         self.rng_off += (n_elems + 3) // 4 + 1
-        self.sites[tag] = (off, n_elems, p)
+        self.sites[tag] = (off, n_elems, p, "last") if last_rows else (off, n_elems, p)
         return Rng(self.eng.seed, off, self.eng.rng_state_ptr)
 
     def p(self, tag, p):
@@ -328,7 +342,19 @@ class PlanBuilder:
                 Tq, Tk = e.Lq * e.B, e.Lk * e.B
                 W, b = sa.in_proj_weight, sa.in_proj_bias
                 S["xn_in"] = e.saved["xn"]
-                if not e.cross:
+                r0, Tr = _qrows(e, i)
+                if not e.cross and Tr != Tq:
+                    # pruned final layer: q from the last step only, k / v (packed) from every step
+                    cidx = e.mask.idx.data_ptr() if e.mask is not None else None
+                    xn = e.saved["xn"]
+                    xq = xn.rows_slice(r0, Tr)
+                    q, kv = A.mat(Tr, D), A.mat(Tq, 2 * D)
+                    S["q_last"], S["kv"] = q, kv
+                    descs.append(LinearDesc(xq.ptr, xq.ld, W.data_ptr(), W.stride(0), b.data_ptr(), None, cidx,
+                                            q.ptr, q.ld, Tr, D, e.E, 0, 0.0, _NO_RNG, _NO_SEGS, _segs(e.mask)))
+                    descs.append(LinearDesc(xn.ptr, xn.ld, W.data_ptr() + F4 * D * W.stride(0), W.stride(0), b.data_ptr() + F4 * D, None, cidx,
+                                            kv.ptr, kv.ld, Tq, 2 * D, e.E, 0, 0.0, _NO_RNG, _NO_SEGS, _segs(e.mask)))
+                elif not e.cross:
                     qkv = A.mat(Tq, 3 * D)
                     S["qkv"] = qkv
                     cidx = e.mask.idx.data_ptr() if e.mask is not None else None
@@ -351,19 +377,25 @@ class PlanBuilder:
                 H, hd = sa.num_heads, sa.head_dim
                 D = H * hd
                 Tq = e.Lq * e.B
-                o = A.mat(Tq, D)
-                lse = A.alloc(e.B * H * e.Lq)
+                r0, Tr = _qrows(e, i)
+                pruned = Tr != Tq
+                Lq_a = 1 if pruned else e.Lq          # pruned: one query step against all Lk keys (no key is masked for the last step)
+                o = A.mat(Tr, D)
+                lse = A.alloc(e.B * H * Lq_a)
                 S["o"], S["lse"] = o, lse
                 pa = self.p(e.tag, sa.attn_dropout)
-                r = self.rng(f"{e.tag}layers.{i}.attn", e.B * H * e.Lq * ((e.Lk + 3) // 4 * 4), pa)
+                r = self.rng(f"{e.tag}layers.{i}.attn", e.B * H * Lq_a * ((e.Lk + 3) // 4 * 4), pa, last_rows=pruned)
                 S["rng_attn"] = (r, pa)
-                if not e.cross:
+                if pruned:
+                    kv = S["kv"]
+                    qm, km, vm = S["q_last"], kv.cols_slice(0, D), kv.cols_slice(D, D)
+                elif not e.cross:
                     qkv = S["qkv"]
                     qm, km, vm = qkv.cols_slice(0, D), qkv.cols_slice(D, D), qkv.cols_slice(2 * D, D)
                 else:
                     qm, km, vm = S["q"], S["k"], S["v"]
                 S["qkv_mats"] = (qm, km, vm)
-                descs.append(AttnDesc(qm.ptr, qm.ld, km.ptr, km.ld, vm.ptr, vm.ld, o.ptr, o.ld, lse, e.Lq, e.Lk, e.B, H, hd,
+                descs.append(AttnDesc(qm.ptr, qm.ld, km.ptr, km.ld, vm.ptr, vm.ld, o.ptr, o.ld, lse, Lq_a, e.Lk, e.B, H, hd,
                                       hd ** -0.5, pa, r))
             self.emit(self.fwd, lib.mtb_attn_fwd, AttnDesc, descs, f"attn[{i}]")
             # d. out-projection ----------------------------------------------------------------
@@ -372,7 +404,7 @@ class PlanBuilder:
                 S = e.saved["layers"][i]
                 sa = e.enc._ll[i].self_attn
                 D = sa.num_heads * sa.head_dim
-                Tq = e.Lq * e.B
+                r0, Tq = _qrows(e, i)
                 a = A.mat(Tq, e.E)
                 S["a"] = a
                 Wo, bo = sa.out_proj.weight, sa.out_proj.bias
@@ -386,12 +418,13 @@ class PlanBuilder:
                 S = e.saved["layers"][i]
                 layer = e.enc._ll[i]
                 ln = layer._lns[1].ln
-                Tq = e.Lq * e.B
+                r0, Tq = _qrows(e, i)
                 x_prev = e.saved["x0"] if i == 0 else e.saved["layers"][i - 1]["x2"]
+                x_prev = x_prev.rows_slice(r0, Tq)
                 x1, xn1 = A.mat(Tq, e.E), A.mat(Tq, e.E)
                 st = (A.alloc(Tq), A.alloc(Tq)) if ng else (None, None)
                 pr = self.p(e.tag, layer.res_dropout)
-                r = self.rng(f"{e.tag}layers.{i}.res0", Tq * e.E, pr)
+                r = self.rng(f"{e.tag}layers.{i}.res0", Tq * e.E, pr, last_rows=r0 > 0)
                 S["x1"], S["xn1"], S["st1"], S["rng_res0"] = x1, xn1, st, (r, pr)
                 idx = e.mask.idx.data_ptr() if e.mask is not None else None
                 descs.append(ResLnDesc(x_prev.ptr, x_prev.ld, S["a"].ptr, S["a"].ld, x1.ptr, x1.ld, xn1.ptr, xn1.ld,
@@ -403,11 +436,11 @@ class PlanBuilder:
                 S = e.saved["layers"][i]
                 layer = e.enc._ll[i]
                 Fa = min(layer.active_hidden_out_fc1, layer.fc1.dim_out)
-                Tq = e.Lq * e.B
+                r0, Tq = _qrows(e, i)
                 h, y = A.mat(Tq, Fa), A.mat(Tq, e.E)
                 S["h"], S["y"], S["F"] = h, y, Fa
                 pl = self.p(e.tag, layer.relu_dropout)
-                r = self.rng(f"{e.tag}layers.{i}.relu", Tq * Fa, pl)
+                r = self.rng(f"{e.tag}layers.{i}.relu", Tq * Fa, pl, last_rows=r0 > 0)
                 S["p_relu"] = pl
                 W1, b1, W2, b2 = layer.fc1.l.weight, layer.fc1.l.bias, layer.fc2.l.weight, layer.fc2.l.bias
                 midx = e.mask.idx.data_ptr() if e.mask is not None else None
@@ -422,20 +455,40 @@ class PlanBuilder:
             for e in act:
                 S = e.saved["layers"][i]
                 layer = e.enc._ll[i]
-                Tq = e.Lq * e.B
+                r0, Tq = _qrows(e, i)
                 last = (i + 1 == e.n_layers)
                 ln = e.enc.layer_norm.ln if last else e.enc._ll[i + 1]._lns[0].ln
                 x2 = A.mat(Tq, e.E)
-                dst = e.out if last else A.mat(Tq, e.E)
+                dst = e.out.rows_slice(r0, Tq) if last else A.mat(Tq, e.E)       # pruned: only the last step of e.out is defined
                 st = (A.alloc(Tq), A.alloc(Tq)) if ng else (None, None)
                 pr = self.p(e.tag, layer.res_dropout)
-                r = self.rng(f"{e.tag}layers.{i}.res1", Tq * e.E, pr)
+                r = self.rng(f"{e.tag}layers.{i}.res1", Tq * e.E, pr, last_rows=r0 > 0)
                 S["x2"], S["xn_next"], S["st2"], S["rng_res1"], S["ln_next"] = x2, dst, st, (r, pr), ln
                 idx = e.mask.idx.data_ptr() if e.mask is not None else None
                 descs.append(ResLnDesc(S["x1"].ptr, S["x1"].ld, S["y"].ptr, S["y"].ld, x2.ptr, x2.ld, dst.ptr, dst.ld,
                                        ln.weight.data_ptr(), ln.bias.data_ptr(), idx, st[0], st[1], Tq, e.E, ln.eps, pr, r))
                 e.saved["xn"] = dst
             self.emit(self.fwd, lib.mtb_resln_fwd, ResLnDesc, descs, f"res_ln2[{i}]")
+
+    def _resln_bwd_descs(self, e, gxn: Mat, gx: Optional[Mat], gx_r0: int, x_new: Mat, st, gamma_ptr, idx_ptr, d_res: Mat,
+                         d_a: Optional[Mat], dgamma, dbeta, T: int, p: float, rng: Rng, dbias):
+        """ResLnBwdDesc(s) for rows [0, T).  If the residual-path gradient `gx` only exists for rows [gx_r0, T)
+        (it comes from a pruned final layer) the rows are split into two problems of the same launch: rows without
+        and rows with the extra gradient; dropout offsets, statistics and outputs are shifted accordingly."""
+        def one(r0, rows, gx_part):
+            sl = (lambda m: m.rows_slice(r0, rows)) if (r0 or rows != T) else (lambda m: m)
+            a, b2, c = sl(gxn), sl(x_new), sl(d_res)
+            da = sl(d_a) if d_a is not None else None
+            rr = rng
+            if r0 and (rng.dev is not None or rng.seed or rng.offset):
+                rr = Rng(rng.seed, rng.offset + (r0 * e.E) // 4, rng.dev)
+            return ResLnBwdDesc(a.ptr, a.ld, gx_part.ptr if gx_part is not None else None, gx_part.ld if gx_part is not None else 0,
+                                b2.ptr, b2.ld, st[0] + F4 * r0, st[1] + F4 * r0, gamma_ptr, idx_ptr, c.ptr, c.ld,
+                                da.ptr if da is not None else None, da.ld if da is not None else 0, dgamma, dbeta, rows, e.E, p, rr, dbias)
+        if gx is None or gx_r0 == 0:
+            return [one(0, T, gx)]
+        assert (gx_r0 * e.E) % 4 == 0
+        return [one(0, gx_r0, None), one(gx_r0, T - gx_r0, gx)]
 
     # ------------------------------------------------------------------ backward of a stage group
     def encoders_backward(self, group: Sequence[EncSpec]):
@@ -448,6 +501,7 @@ class PlanBuilder:
         for e in group:
             e.saved["g_xn"] = e.d_out
             e.saved["g_x"] = None
+            e.saved["g_x_r0"] = 0
             e.saved["g_xk"] = None
             e.saved["g_xv"] = None
         # Tensor-core engine: the weight-gradient GEMMs of a layer do not feed the backward chain, so they are
@@ -461,26 +515,25 @@ class PlanBuilder:
             descs = []
             for e in act:
                 S = e.saved["layers"][i]
-                Tq = e.Lq * e.B
+                r0, Tq = _qrows(e, i)
                 ln = S["ln_next"]
                 masked = e.mask is not None
                 g_x1r, g_y = A.mat(Tq, e.E), A.mat(Tq, e.E)
                 S["g_x1r"], S["g_y"] = g_x1r, g_y
                 gx = e.saved["g_x"]
-                gxn = e.saved["g_xn"]
+                gxn = e.saved["g_xn"].rows_slice(r0, Tq)          # pruned final layer: only the last step carries gradient
                 r, pr = S["rng_res1"]
-                descs.append(ResLnBwdDesc(gxn.ptr, gxn.ld, gx.ptr if gx else None, gx.ld if gx else 0, S["x2"].ptr, S["x2"].ld,
-                                          S["st2"][0], S["st2"][1], ln.weight.data_ptr(), e.mask.idx.data_ptr() if masked else None,
-                                          g_x1r.ptr, g_x1r.ld, g_y.ptr, g_y.ld,
-                                          None if masked else self.grad_ptr(ln.weight), None if masked else self.grad_ptr(ln.bias),
-                                          Tq, e.E, pr, r, self.grad_ptr(e.enc._ll[i].fc2.l.bias)))      # fc2 bias grad = colsum(g_y), fused
+                descs.extend(self._resln_bwd_descs(
+                    e, gxn, gx, e.saved["g_x_r0"], S["x2"], S["st2"], ln.weight.data_ptr(), e.mask.idx.data_ptr() if masked else None,
+                    g_x1r, g_y, None if masked else self.grad_ptr(ln.weight), None if masked else self.grad_ptr(ln.bias),
+                    Tq, pr, r, self.grad_ptr(e.enc._ll[i].fc2.l.bias)))      # fc2 bias grad = colsum(g_y), fused
             self.emit(self.bwd, lib.mtb_resln_bwd, ResLnBwdDesc, descs, f"res_ln2_bwd[{i}]")
             # g'. fc2 backward, f'. fc1 backward
             d2, d1 = [], []
             for e in act:
                 S = e.saved["layers"][i]
                 layer = e.enc._ll[i]
-                Tq, Fa = e.Lq * e.B, S["F"]
+                Tq, Fa = _qrows(e, i)[1], S["F"]
                 W1, b1, W2, b2 = layer.fc1.l.weight, layer.fc1.l.bias, layer.fc2.l.weight, layer.fc2.l.bias
                 midx = e.mask.idx.data_ptr() if e.mask is not None else None
                 g_h, g_xn1 = A.mat(Tq, Fa), A.mat(Tq, e.E)
@@ -513,11 +566,12 @@ class PlanBuilder:
                 S = e.saved["layers"][i]
                 layer = e.enc._ll[i]
                 ln = layer._lns[1].ln
-                Tq = e.Lq * e.B
+                r0, Tq = _qrows(e, i)
                 masked = e.mask is not None
                 g_xr, g_a = A.mat(Tq, e.E), A.mat(Tq, e.E)
                 S["g_a"] = g_a
                 e.saved["g_x"] = g_xr
+                e.saved["g_x_r0"] = r0                           # rows [r0, T) only when this layer was pruned
                 r, pr = S["rng_res0"]
                 descs.append(ResLnBwdDesc(S["g_xn1"].ptr, S["g_xn1"].ld, S["g_x1r"].ptr, S["g_x1r"].ld, S["x1"].ptr, S["x1"].ld,
                                           S["st1"][0], S["st1"][1], ln.weight.data_ptr(), e.mask.idx.data_ptr() if masked else None,
@@ -531,7 +585,7 @@ class PlanBuilder:
                 S = e.saved["layers"][i]
                 sa = e.enc._ll[i].self_attn
                 D = sa.num_heads * sa.head_dim
-                Tq = e.Lq * e.B
+                Tq = _qrows(e, i)[1]
                 Wo, bo = sa.out_proj.weight, sa.out_proj.bias
                 ridx = e.mask.idx.data_ptr() if e.mask is not None else None
                 g_o = A.mat(Tq, D)
@@ -555,21 +609,28 @@ class PlanBuilder:
                 D = H * hd
                 Tq, Tk = e.Lq * e.B, e.Lk * e.B
                 qm, km, vm = S["qkv_mats"]
-                if not e.cross:
+                Tr = _qrows(e, i)[1]
+                pruned = Tr != Tq
+                Lq_a = 1 if pruned else e.Lq
+                if pruned:
+                    dq, dkv = A.mat(Tr, D), A.mat(Tq, 2 * D)
+                    S["dq_last"], S["dkv"] = dq, dkv
+                    dk, dv = dkv.cols_slice(0, D), dkv.cols_slice(D, D)
+                elif not e.cross:
                     dqkv = A.mat(Tq, 3 * D)
                     S["dqkv"] = dqkv
                     dq, dk, dv = dqkv.cols_slice(0, D), dqkv.cols_slice(D, D), dqkv.cols_slice(2 * D, D)
                 else:
                     dq, dk, dv = A.mat(Tq, D), A.mat(Tk, D), A.mat(Tk, D)
                     S["dq"], S["dk"], S["dv"] = dq, dk, dv
-                delta = A.alloc(e.B * H * e.Lq)
+                delta = A.alloc(e.B * H * Lq_a)
                 r, pa = S["rng_attn"]
                 descs.append(AttnBwdDesc(qm.ptr, qm.ld, km.ptr, km.ld, vm.ptr, vm.ld, S["o"].ptr, S["o"].ld, S["g_o"].ptr, S["g_o"].ld,
-                                         S["lse"], delta, dq.ptr, dq.ld, dk.ptr, dk.ld, dv.ptr, dv.ld, e.Lq, e.Lk, e.B, H, hd,
+                                         S["lse"], delta, dq.ptr, dq.ld, dk.ptr, dk.ld, dv.ptr, dv.ld, Lq_a, e.Lk, e.B, H, hd,
                                          hd ** -0.5, pa, r))
             self.emit(self.bwd, lib.mtb_attn_bwd, AttnBwdDesc, descs, f"attn_bwd[{i}]")
             # b'. in-projection backward
-            descs = []
+            descs, descs_q = [], []
             for e in act:
                 S = e.saved["layers"][i]
                 sa = e.enc._ll[i].self_attn
@@ -580,7 +641,31 @@ class PlanBuilder:
                 xn_in = S["xn_in"]
                 g_xn = A.mat(Tq, e.E)
                 e.saved["g_xn"] = g_xn
-                if not e.cross:
+                r0, Tr = _qrows(e, i)
+                if not e.cross and Tr != Tq:
+                    # pruned final layer: d(xn) = dkv . W[D:3D]  (every step)  +  dq . W[0:D]  (last step, second launch)
+                    cidx = e.mask.idx.data_ptr() if e.mask is not None else None
+                    dq, dkv = S["dq_last"], S["dkv"]
+                    xq = xn_in.rows_slice(r0, Tr)
+                    g_q = g_xn.rows_slice(r0, Tr)
+                    Wkv = W.data_ptr() + F4 * D * W.stride(0)
+                    gWkv = (gW + F4 * D * W.stride(0)) if gW else None
+                    gbkv = (gb + F4 * D) if gb else None
+                    if defer:
+                        descs.append(LinearBwdDesc(dkv.ptr, dkv.ld, None, 0, None, 0, Wkv, W.stride(0), None, cidx,
+                                                   g_xn.ptr, g_xn.ld, 0, None, None, Tq, 2 * D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
+                        descs_q.append(LinearBwdDesc(dq.ptr, dq.ld, None, 0, None, 0, W.data_ptr(), W.stride(0), None, cidx,
+                                                     g_q.ptr, g_q.ld, 1, None, None, Tr, D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
+                        wg_descs.append(LinearBwdDesc(dkv.ptr, dkv.ld, None, 0, xn_in.ptr, xn_in.ld, Wkv, W.stride(0), None, cidx,
+                                                      None, 0, 0, gWkv, gbkv, Tq, 2 * D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
+                        wg_descs.append(LinearBwdDesc(dq.ptr, dq.ld, None, 0, xq.ptr, xq.ld, W.data_ptr(), W.stride(0), None, cidx,
+                                                      None, 0, 0, gW, gb, Tr, D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
+                    else:
+                        descs.append(LinearBwdDesc(dkv.ptr, dkv.ld, None, 0, xn_in.ptr, xn_in.ld, Wkv, W.stride(0), None, cidx,
+                                                   g_xn.ptr, g_xn.ld, 0, gWkv, gbkv, Tq, 2 * D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
+                        descs_q.append(LinearBwdDesc(dq.ptr, dq.ld, None, 0, xq.ptr, xq.ld, W.data_ptr(), W.stride(0), None, cidx,
+                                                     g_q.ptr, g_q.ld, 1, gW, gb, Tr, D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
+                elif not e.cross:
                     cidx = e.mask.idx.data_ptr() if e.mask is not None else None
                     if defer:
                         descs.append(LinearBwdDesc(S["dqkv"].ptr, S["dqkv"].ld, None, 0, None, 0, W.data_ptr(), W.stride(0), None, cidx,
@@ -607,6 +692,7 @@ class PlanBuilder:
                             descs.append(LinearBwdDesc(dy.ptr, dy.ld, None, 0, src.ptr, src.ld, Wp, W.stride(0),
                                                        None, None, dst.ptr, dst.ld, 0, gWp, gbp, T, D, e.E, 0, 0.0, None, _NO_SEGS, _NO_SEGS))
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, descs, f"in_proj_bwd[{i}]")
+            self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, descs_q, f"in_proj_bwd_q[{i}]")
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, wg_descs, f"wgrad[{i}]")
             # a'. LN0 backward on the key / value streams (gradients accumulate over layers, in place)
             descs = []
@@ -637,10 +723,10 @@ class PlanBuilder:
             g_x0 = A.mat(Tq, e.E)
             e.saved["g_x0"] = g_x0
             gxn, gx = e.saved["g_xn"], e.saved["g_x"]
-            descs.append(ResLnBwdDesc(gxn.ptr, gxn.ld, gx.ptr if gx else None, gx.ld if gx else 0, e.saved["x0"].ptr, e.E, st[0], st[1],
-                                      ln.weight.data_ptr(), e.mask.idx.data_ptr() if masked else None, g_x0.ptr, g_x0.ld, None, 0,
-                                      None if masked else self.grad_ptr(ln.weight), None if masked else self.grad_ptr(ln.bias),
-                                      Tq, e.E, 0.0, none_rng, None))
+            descs.extend(self._resln_bwd_descs(
+                e, gxn, gx, e.saved["g_x_r0"], e.saved["x0"], st, ln.weight.data_ptr(), e.mask.idx.data_ptr() if masked else None,
+                g_x0, None, None if masked else self.grad_ptr(ln.weight), None if masked else self.grad_ptr(ln.bias),
+                Tq, 0.0, none_rng, None))
         self.emit(self.bwd, lib.mtb_resln_bwd, ResLnBwdDesc, descs, "ln_first_bwd")
         # embed backward -> gradients wrt the encoder inputs (contiguous [L, B, E])
         descs = []
@@ -790,6 +876,7 @@ class Engine:
         self.prewarm = True
         self.side_stream_wgrad = True
         self._side = None
+        self.prune_last_rows = True        # final `mems` layer on the last sequence step only (results-identical)
         _install_fast_attrs(model)
         self.params = [p for p in model.parameters()]
         total = 0
@@ -974,13 +1061,15 @@ class Engine:
         activations, gradients, dropout-stream offsets) is a fixed function of the encoder and this key."""
         want_bwd = bool(want_bwd and need_grad)
         ffn = tuple(l.active_hidden_out_fc1 for l in enc._ll[:n_layers])
+        prune = bool(self.prune_last_rows and kind == "mems" and n_layers >= 1)
         key = (id(enc), Lq, Lk, B, E, n_layers, id(mask) if mask is not None else 0, q_src, kv_src, want_bwd, training, need_grad,
-               ffn, lib.mtb_get_gemm_mode())
+               ffn, lib.mtb_get_gemm_mode(), prune)
         ep = self._enc_cache.get(key)
         if ep is not None:
             return ep
         reg = self._regions[id(enc)]
         e = EncSpec(tag, enc, Lq, Lk, B, E, n_layers, mask, q_src, kv_src, Mat(reg.out, Lq * B, E), kind, name)
+        e.prune_last = prune
         pb = PlanBuilder(self, SubArena(reg.work, reg.work_cap), training, need_grad)
         pb.rng_off = self._enc_index[id(enc)] << 56
         pb.encoders_forward([e])

@@ -81,13 +81,24 @@ def test_engine_train_dropout_matches_oracle():
         base = eng.step_offset
 
         def provider(tag, shape, p, plan=plan, base=base, eng=eng):
-            off, n, pp = plan.sites[tag]
+            off, n, pp, *extra = plan.sites[tag]
             assert abs(pp - p) < 1e-7, (tag, pp, p)
+            last_only = bool(extra)          # pruned final `mems` layer: the kernel only draws the LAST sequence step
             if tag.endswith("attn"):
                 BH, Lq, Lk = shape
                 Lk4 = (Lk + 3) // 4 * 4
+                if last_only:                # every other query step is irrelevant to h[-1]: keep everything there
+                    assert n == BH * Lk4
+                    full = torch.ones(BH, Lq, Lk)
+                    full[:, -1, :] = ops.dropout_mask(eng.seed, base + off, p, n, "cuda").view(BH, Lk4)[:, :Lk].cpu()
+                    return full
                 assert n == BH * Lq * Lk4
                 return ops.dropout_mask(eng.seed, base + off, p, n, "cuda").view(BH, Lq, Lk4)[:, :, :Lk].cpu()
+            if last_only:
+                full = torch.ones(shape)
+                assert n == math.prod(shape[1:]), (tag, n, shape)      # seq-first [L, B, F]: one step
+                full[-1] = ops.dropout_mask(eng.seed, base + off, p, n, "cuda").view(shape[1:]).cpu()
+                return full
             assert n == math.prod(shape), (tag, n, shape)
             return ops.dropout_mask(eng.seed, base + off, p, n, "cuda").view(shape).cpu()
         w = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in G["weights"].items()}
