@@ -2,12 +2,14 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace mtb {
 
 static thread_local char g_err[512] = "";
 int g_gemm_mode = 0;
-int g_attn_mode = -1;   // -1 = follow the GEMM engine (tensor-core attention in tensor-core mode)
+int g_attn_mode = -1;
+int g_pdl = getenv("MTB_PDL") ? atoi(getenv("MTB_PDL")) : 1;   // programmatic dependent launch (common.cuh)   // -1 = follow the GEMM engine (tensor-core attention in tensor-core mode)
 static unsigned long long g_launches = 0;
 void note_launch() { ++g_launches; }
 unsigned long long launches() { return g_launches; }

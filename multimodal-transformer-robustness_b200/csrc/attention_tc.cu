@@ -230,6 +230,7 @@ __device__ __forceinline__ void fwd_softmax_half(float (&s)[32], const float c2,
 }
 
 __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid_constant__ Group<mtb_attn_desc> g) {
+  pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
@@ -425,6 +426,7 @@ __device__ __forceinline__ void dq_math(const float (&s)[32], const float (&dp)[
 }
 
 __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __grid_constant__ Group<mtb_attn_bwd_desc> g) {
+  pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_a, bar_b;
   __shared__ uint32_t tmem_slot;
@@ -612,6 +614,7 @@ __device__ __forceinline__ void dkv_math(const float (&st)[16], const float (&dp
 }
 
 __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __grid_constant__ Group<mtb_attn_bwd_desc> g) {
+  pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_a, bar_b;
   __shared__ uint32_t tmem_slot;
@@ -776,7 +779,7 @@ int attn_fwd_tc(const mtb_attn_desc* d, int n, cudaStream_t st) {
       MTB_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_FWD_SMEM));
       attr = true;
     }
-    attn_fwd_tc_kernel<<<tot, AF_THREADS, ATC_FWD_SMEM, st>>>(g);
+    MTB_CUDA(launch_k(attn_fwd_tc_kernel, dim3(tot), dim3(AF_THREADS), ATC_FWD_SMEM, st, g));
     mtb::note_launch();
     MTB_CUDA(cudaGetLastError());
   }
@@ -807,10 +810,10 @@ int attn_bwd_tc(const mtb_attn_bwd_desc* d, int n, cudaStream_t st) {
       MTB_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_DKV_SMEM));
       attr = true;
     }
-    attn_bwd_dq_tc_kernel<<<totq, AQ_THREADS, ATC_DQ_SMEM, st>>>(gq);
+    MTB_CUDA(launch_k(attn_bwd_dq_tc_kernel, dim3(totq), dim3(AQ_THREADS), ATC_DQ_SMEM, st, gq));
     mtb::note_launch();
     MTB_CUDA(cudaGetLastError());
-    attn_bwd_dkv_tc_kernel<<<totk, AB_THREADS, ATC_DKV_SMEM, st>>>(gk);
+    MTB_CUDA(launch_k(attn_bwd_dkv_tc_kernel, dim3(totk), dim3(AB_THREADS), ATC_DKV_SMEM, st, gk));
     mtb::note_launch();
     MTB_CUDA(cudaGetLastError());
   }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <utility>
 #include "../../include/multb200.h"
 
 #ifndef __CUDA_ARCH__
@@ -114,6 +115,28 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every hot kernel starts with pdl_sync(): it waits until the preceding kernel of the stream has completed and
+// flushed its writes, then lets the NEXT kernel's CTAs be scheduled while this one is still running (they park in
+// their own pdl_sync()).  Launched through launch_k() with the programmatic-stream-serialization attribute this
+// removes the ~2-3 us launch bubble between the small dependent kernels of a step; without the attribute (or after
+// a kernel that never triggers) both instructions are no-ops / the edge is a normal full serialisation.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+extern int g_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 int sm_count();

@@ -15,6 +15,7 @@ __device__ __forceinline__ float pe_freq(int c_half, float neg_step) {
 
 template <bool BWD>
 __global__ void __launch_bounds__(EW_THREADS) embed_kernel(const __grid_constant__ Group<mtb_embed_desc> g) {
+  pdl_sync();
   int local;
   const int pi = find_problem(g, blockIdx.x, local);
   const mtb_embed_desc& d = g.d[pi];
@@ -111,13 +112,14 @@ static int launch_embed(const mtb_embed_desc* d, int n, cudaStream_t st) {
   }
   g.start[n] = tot;
   if (tot == 0) return 0;
-  embed_kernel<BWD><<<tot, EW_THREADS, 0, st>>>(g);
+  MTB_CUDA(launch_k(embed_kernel<BWD>, dim3(tot), dim3(EW_THREADS), 0, st, g));
   mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
   return 0;
 }
 
 __global__ void __launch_bounds__(EW_THREADS) addn_kernel(const __grid_constant__ Group<mtb_addn_desc> g) {
+  pdl_sync();
   int local;
   const int pi = find_problem(g, blockIdx.x, local);
   const mtb_addn_desc& d = g.d[pi];
@@ -199,7 +201,7 @@ int mtb_addn(const mtb_addn_desc* d, int n, void* stream) {
   }
   g.start[n] = tot;
   if (tot == 0) return 0;
-  addn_kernel<<<tot, EW_THREADS, 0, (cudaStream_t)stream>>>(g);
+  MTB_CUDA(launch_k(addn_kernel, dim3(tot), dim3(EW_THREADS), 0, (cudaStream_t)stream, g));
   mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
   return 0;

@@ -29,6 +29,7 @@ __device__ __forceinline__ float4 keep4(const DropCtx& dc, uint64_t grp) {
 // ------------------------------------------------------------------ forward (vector path)
 template <int MAXV>
 __global__ void __launch_bounds__(LN_THREADS) resln_fwd_kernel(const __grid_constant__ Group<mtb_resln_desc> g) {
+  pdl_sync();
   int local;
   const int pi = find_problem(g, blockIdx.x, local);
   const mtb_resln_desc& d = g.d[pi];
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(LN_THREADS) resln_fwd_generic(const __grid_con
 template <int MAXV, bool AFFINE_GRAD>
 __global__ void __launch_bounds__(LN_THREADS) resln_bwd_kernel(const __grid_constant__ Group<mtb_resln_bwd_desc> g,
                                                                int rows_per_cta) {
+  pdl_sync();
   extern __shared__ float sred[];   // [3][E] when AFFINE_GRAD: dgamma, dbeta, dbias partials
   int local;
   const int pi = find_problem(g, blockIdx.x, local);
@@ -312,8 +314,8 @@ int mtb_resln_fwd(const mtb_resln_desc* d, int n, void* stream) {
   g.start[n] = tot;
   if (tot == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (vec && maxE <= 256) resln_fwd_kernel<2><<<tot, LN_THREADS, 0, st>>>(g);
-  else if (vec && maxE <= 1024) resln_fwd_kernel<8><<<tot, LN_THREADS, 0, st>>>(g);
+  if (vec && maxE <= 256) MTB_CUDA(launch_k(resln_fwd_kernel<2>, dim3(tot), dim3(LN_THREADS), 0, st, g));
+  else if (vec && maxE <= 1024) MTB_CUDA(launch_k(resln_fwd_kernel<8>, dim3(tot), dim3(LN_THREADS), 0, st, g));
   else resln_fwd_generic<<<tot, LN_THREADS, 0, st>>>(g);
   mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
@@ -351,11 +353,11 @@ int mtb_resln_bwd(const mtb_resln_bwd_desc* d, int n, void* stream) {
     if (tot == 0) return 0;
     const size_t smem = affine ? 3 * (size_t)maxE * sizeof(float) : 0;
     if (maxE <= 256) {
-      if (affine) resln_bwd_kernel<2, true><<<tot, LN_THREADS, smem, st>>>(g, rows);
-      else resln_bwd_kernel<2, false><<<tot, LN_THREADS, 0, st>>>(g, rows);
+      if (affine) MTB_CUDA(launch_k(resln_bwd_kernel<2, true>, dim3(tot), dim3(LN_THREADS), smem, st, g, rows));
+      else MTB_CUDA(launch_k(resln_bwd_kernel<2, false>, dim3(tot), dim3(LN_THREADS), 0, st, g, rows));
     } else {
-      if (affine) resln_bwd_kernel<8, true><<<tot, LN_THREADS, smem, st>>>(g, rows);
-      else resln_bwd_kernel<8, false><<<tot, LN_THREADS, 0, st>>>(g, rows);
+      if (affine) MTB_CUDA(launch_k(resln_bwd_kernel<8, true>, dim3(tot), dim3(LN_THREADS), smem, st, g, rows));
+      else MTB_CUDA(launch_k(resln_bwd_kernel<8, false>, dim3(tot), dim3(LN_THREADS), 0, st, g, rows));
     }
   } else {
     for (int i = 0; i < n; ++i) { g.d[i] = d[i]; g.start[i] = tot; tot += (d[i].T + LN_WARPS - 1) / LN_WARPS; }

@@ -149,6 +149,7 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 
 template <int CAP>
 __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ TcGroupT<CAP> g) {
+  pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
@@ -391,6 +392,7 @@ struct ActgradArgs {
 };
 constexpr int ACT_ROWS = 32;           // rows per block: 4 row-lanes x 8 rows, all 8 loads of a lane in flight
 __global__ void __launch_bounds__(512) actgrad_kernel(const ActgradArgs a) {
+  pdl_sync();
   __shared__ float part[4][128];
   const int n = blockIdx.x * 128 + threadIdx.x;
   const int m0 = blockIdx.y * ACT_ROWS + threadIdx.y * 8;
@@ -432,6 +434,7 @@ struct ColsumGroup {
 // one launch for every bias gradient of a backward call: blockIdx.z selects the problem, the grid covers the
 // largest one (surplus blocks exit at once)
 __global__ void __launch_bounds__(128) colsum_kernel(const __grid_constant__ ColsumGroup g) {
+  pdl_sync();
   const ColsumArgs& a = g.a[blockIdx.z];
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int m0 = blockIdx.y * COLSUM_ROWS, m1 = min(a.M, m0 + COLSUM_ROWS);
@@ -608,7 +611,7 @@ static int launch_tc_cap(const TcProblem* probs, int n, cudaStream_t st) {
               g.d[i].a_mn, g.d[i].b_mn, g.d[i].epi);
     fprintf(stderr, "\n");
   }
-  gemm_tc_kernel<CAP><<<tot, TC_THREADS, smem, st>>>(g);
+  MTB_CUDA(launch_k(gemm_tc_kernel<CAP>, dim3(tot), dim3(TC_THREADS), smem, st, g));
   mtb::note_launch();
   MTB_CUDA(cudaGetLastError());
   return 0;
@@ -733,7 +736,7 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
       aa.M = x.M; aa.N = x.N; aa.seg_len = an.len; aa.inv_keep = x.p > 0.f ? 1.f / (1.f - x.p) : 1.f;
       for (int s2 = 0; s2 < TC_MAXSEG; ++s2) aa.seg[s2] = s2 < an.n ? an.phys[s2] : 0;
       dim3 grid((x.N + 127) / 128, (x.M + ACT_ROWS - 1) / ACT_ROWS);
-      actgrad_kernel<<<grid, dim3(128, 4), 0, st>>>(aa);
+      MTB_CUDA(launch_k(actgrad_kernel, grid, dim3(128, 4), 0, st, aa));
       mtb::note_launch();
       MTB_CUDA(cudaGetLastError());
     }
@@ -749,7 +752,7 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
     }
   }
   if (cs.n > 0) {
-    colsum_kernel<<<dim3(cs_gx, cs_gy, cs.n), 128, 0, st>>>(cs);
+    MTB_CUDA(launch_k(colsum_kernel, dim3(cs_gx, cs_gy, cs.n), dim3(128), 0, st, cs));
     mtb::note_launch();
     MTB_CUDA(cudaGetLastError());
   }

@@ -18,6 +18,7 @@ namespace mtb {
 constexpr int AD_THREADS = 256;
 
 __global__ void __launch_bounds__(AD_THREADS) adam_sumsq_kernel(const mtb_adam_desc d) {
+  pdl_sync();
   const int c = blockIdx.x;
   const int pid = d.chunk_pid[c];
   __shared__ float red[AD_THREADS / 32];
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(AD_THREADS) adam_sumsq_kernel(const mtb_adam_d
 }
 
 __global__ void __launch_bounds__(1024) adam_finalize_kernel(const mtb_adam_desc d) {
+  pdl_sync();
   __shared__ double red[32];
   double s = 0.0;
   for (int i = threadIdx.x; i < d.n_chunks; i += 1024) s += (double)d.partial[i];
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(1024) adam_finalize_kernel(const mtb_adam_desc
 }
 
 __global__ void __launch_bounds__(AD_THREADS) adam_update_kernel(const mtb_adam_desc d) {
+  pdl_sync();
   const int c = blockIdx.x;
   const int pid = d.chunk_pid[c];
   if (!d.active[pid]) return;
@@ -118,11 +121,11 @@ int adam_step(const mtb_adam_desc* d, cudaStream_t st) {
   MTB_CHECK(d->n_chunks >= 1 && d->n_params >= 1, "adam_step: empty tables");
   MTB_CHECK(d->chunk_param && d->chunk_off && d->chunk_n && d->chunk_pid && d->active && d->steps && d->grad &&
             d->exp_avg && d->exp_avg_sq && d->partial && d->scalars, "adam_step: null table or arena pointer");
-  adam_sumsq_kernel<<<d->n_chunks, AD_THREADS, 0, st>>>(*d);
+  MTB_CUDA(launch_k(adam_sumsq_kernel, dim3(d->n_chunks), dim3(AD_THREADS), 0, st, *d));
   note_launch();
-  adam_finalize_kernel<<<1, 1024, 0, st>>>(*d);
+  MTB_CUDA(launch_k(adam_finalize_kernel, dim3(1), dim3(1024), 0, st, *d));
   note_launch();
-  adam_update_kernel<<<d->n_chunks, AD_THREADS, 0, st>>>(*d);
+  MTB_CUDA(launch_k(adam_update_kernel, dim3(d->n_chunks), dim3(AD_THREADS), 0, st, *d));
   note_launch();
   MTB_CUDA(cudaGetLastError());
   return 0;

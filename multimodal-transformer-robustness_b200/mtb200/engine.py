@@ -1322,7 +1322,8 @@ class Engine:
             items = []
             for (i, c0, w) in head_cols:
                 e = mems_of[i].spec
-                pb.bwd.append(ZeroOp(self.view(e.d_out)))
+                if not e.prune_last:          # a pruned stack only ever reads the last step of d_out
+                    pb.bwd.append(ZeroOp(self.view(e.d_out)))
                 items.append((e.d_out.rows_slice((e.Lq - 1) * B, B), [g_out.cols_slice(c0, w)], False))
             pb.addn(pb.bwd, items, "head_scatter_bwd")
             # stage groups in reverse; the gradient of every branch output is summed into its fixed home
