@@ -169,8 +169,10 @@ __device__ __forceinline__ unsigned long long a_gtime() { unsigned long long t; 
 extern "C" int mtb_debug_attn_trace(unsigned long long* out) {
   return (int)cudaMemcpyFromSymbol(out, g_attn_trace, sizeof(unsigned long long) * 128);
 }
+#define QTRACE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (i) < 128) g_attn_trace[(i)] = a_gtime(); } while (0)
 #else
 #define ATRACE(i) do { } while (0)
+#define QTRACE(i) do { } while (0)
 #endif
 
 // ---------------------------------------------------------------------------- forward
@@ -328,6 +330,8 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
     fence_async_smem();
     __syncthreads();                          // P written, S read by everyone, next K / V landed
     ATRACE(8 + t * 8 + 4);
+    // Issuing one of these small tcgen05.mma costs ~0.1 us of a single thread: the two independent MMA groups of a tile
+    // are issued by two threads of different warps in parallel (each commits to its own barrier).
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
@@ -335,12 +339,12 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
         a_mma_tf32(t_o + (kk >> 2) * 32, desc_kmajor(a_smem_u32(Ps) + (kk >> 2) * (TQ * 128) + (kk & 3) * 32),
                    desc_mnmajor(a_smem_u32(cur + TK * 128) + kk * 1024), id_o, (kk & 3) != 0 ? 1u : 0u);
       a_commit(a_smem_u32(&bar_o));
-      if (t + 1 < T) {
+    } else if (tid == 128 && t + 1 < T) {
+      tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < HP / 8; ++k)
-          a_mma_tf32(t_s, desc_kmajor(a_smem_u32(Qs) + k * 32), desc_kmajor(a_smem_u32(nxt) + k * 32), id_s, k != 0 ? 1u : 0u);
-        a_commit(a_smem_u32(&bar_s));
-      }
+      for (int k = 0; k < HP / 8; ++k)
+        a_mma_tf32(t_s, desc_kmajor(a_smem_u32(Qs) + k * 32), desc_kmajor(a_smem_u32(nxt) + k * 32), id_s, k != 0 ? 1u : 0u);
+      a_commit(a_smem_u32(&bar_s));
     }
     a_mbar_wait(a_smem_u32(&bar_o), ph);
     tc_fence_after();
@@ -506,10 +510,14 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
   uint32_t kbits = dc.on ? row_keep_bits32(dc, idx_row) : 0u;
   uint8_t* my_ds = dSs + half * (TQ * 128);
 
+  QTRACE(0);
   for (int t = 0; t < T; ++t) {
     const int j0 = t * TK;
     const uint32_t ph = (uint32_t)t & 1u;
-    a_mbar_wait(a_smem_u32(&bar_a), ph);       // S_t, dP_t ready; Ks / Vs and (dQ_{t-1} retired) the other Kmn buffer are free
+    QTRACE(8 + t * 8 + 0);
+    a_mbar_wait(a_smem_u32(&bar_a), ph);       // S_t, dP_t ready; Ks / Vs are free
+    if (t > 0) a_mbar_wait(a_smem_u32(&bar_b), (uint32_t)(t - 1) & 1u);   // dQ_{t-1} retired: dS and the other Kmn buffer are free
+    QTRACE(8 + t * 8 + 1);
     tc_fence_after();
     if (t + 1 < T) {
       stage_rows256<false>(Ks, d.k, d.ldk, d.B, b, h, hd, j0 + TK, Lk, TK);
@@ -517,29 +525,38 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
       stage_rows256<true>(Kmn + ((t + 1) & 1) * (TK * 128), d.k, d.ldk, d.B, b, h, hd, j0 + TK, Lk, TK);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    QTRACE(8 + t * 8 + 2);
     float s[32], dp[32];
     a_tmem_ld32(t_s + lane_addr + half * 32, s);
     a_tmem_ld32(t_dp + lane_addr + half * 32, dp);
     tc_fence_before();
+    QTRACE(8 + t * 8 + 3);
     const bool tile_open = (j0 + TK <= Lk) && (j0 + TK - 1 - i0 < 1 + off);      // CTA-uniform
     if (tile_open)
       dq_math<false>(s, dp, lse2, delta, kbits, dc.on, dc.inv_keep, c2, d.scale, i, j0 + half * 32, Lk, off, my_ds, row);
     else
       dq_math<true>(s, dp, lse2, delta, kbits, dc.on, dc.inv_keep, c2, d.scale, i, j0 + half * 32, Lk, off, my_ds, row);
+    QTRACE(8 + t * 8 + 4);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    QTRACE(8 + t * 8 + 5);
     fence_async_smem();
     __syncthreads();                           // dS written, S / dP read by everyone, next K / V / Kmn landed
-    if (tid == 0) {
+    QTRACE(8 + t * 8 + 6);
+    if (tid == 0) {                            // critical path first: the next tile's S / dP
+      tc_fence_after();
+      if (t + 1 < T) issue_s();
+    } else if (tid == 128) {                   // dQ_t on a second issuing thread (own barrier)
       tc_fence_after();
 #pragma unroll
       for (int kk = 0; kk < TK / 8; ++kk)
         a_mma_tf32(t_dq, desc_kmajor(a_smem_u32(dSs) + (kk >> 2) * (TQ * 128) + (kk & 3) * 32),
                    desc_mnmajor(a_smem_u32(Kmn + (t & 1) * (TK * 128)) + kk * 1024), id_q, (t | kk) != 0 ? 1u : 0u);
       a_commit(a_smem_u32(&bar_b));
-      if (t + 1 < T) issue_s();
     }
     if (dc.on && t + 1 < T) kbits = row_keep_bits32(dc, idx_row + (uint64_t)(j0 + TK));   // drawn while the MMAs run
+    QTRACE(8 + t * 8 + 7);
   }
+  QTRACE(1);
   {
     a_mbar_wait(a_smem_u32(&bar_b), (uint32_t)(T - 1) & 1u);
     tc_fence_after();
@@ -699,7 +716,8 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
     const int i0 = i_begin + t * TI;
     const uint32_t ph = (uint32_t)t & 1u;
     uint8_t* qb = QB + (t & 1) * (4 * TI * 128);
-    a_mbar_wait(a_smem_u32(&bar_a), ph);       // S^T_t, dP^T_t ready; every MMA issued before them (dV / dK of tile t-1) has retired too
+    a_mbar_wait(a_smem_u32(&bar_a), ph);       // S^T_t, dP^T_t ready
+    if (t > 0) a_mbar_wait(a_smem_u32(&bar_b), (uint32_t)(t - 1) & 1u);   // dV / dK of tile t-1 retired: P~^T / dS^T and the other operand buffer are free
     tc_fence_after();
     if (t + 1 < T) stage_q(t + 1);             // the other buffer was last read by tile t-1's MMAs
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -717,7 +735,10 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     fence_async_smem();
     __syncthreads();                           // P~^T / dS^T written, S^T / dP^T read by everyone, next operand tiles landed
-    if (tid == 0) {
+    if (tid == 0) {                            // critical path first: the next tile's S^T / dP^T
+      tc_fence_after();
+      if (t + 1 < T) issue_s(t + 1);
+    } else if (tid == 128) {                   // dV_t / dK_t on a second issuing thread (own barrier)
       tc_fence_after();
 #pragma unroll
       for (int kk = 0; kk < TI / 8; ++kk)
@@ -728,7 +749,6 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
         a_mma_tf32(t_dk, desc_kmajor(a_smem_u32(dSTs) + kk * 32), desc_mnmajor(a_smem_u32(qb + 2 * TI * 128) + kk * 1024), id_o,
                    (t | kk) != 0 ? 1u : 0u);
       a_commit(a_smem_u32(&bar_b));
-      if (t + 1 < T) issue_s(t + 1);
     }
     if (dc.on && t + 1 < T) dkv_keep_bits(dc, bh, Lq, Lk4, i0 + TI + half * 16, j, kw);   // drawn while the MMAs run
   }
