@@ -12,7 +12,7 @@ import torch
 from torch import nn
 
 from mtb200 import ops
-from mtb200.slicing import as_index, is_masked, mask_len
+from mtb200.slicing import as_index, in_proj_rows, is_masked, mask_len, out_proj_cols
 from modules.position_embedding import SinusoidalPositionalEmbedding
 from modules.multihead_attention import MultiheadAttention, mha_forward  # noqa: F401
 from modules.dynamic_multihead_attention import DynamicMultiheadAttention
@@ -33,6 +33,27 @@ def _attn_block(layer, xn, kn, vn, L, Lk, B, idx, training):
     return mha_forward(q, kn.view(Lk, B, -1), vn.view(Lk, B, -1), sa.in_proj_weight, sa.in_proj_bias,
                        sa.out_proj.weight, sa.out_proj.bias, sa.num_heads, sa.head_dim, sa.active_num_heads,
                        sa.active_head_dim, sa.attn_dropout, training, None).view(L * B, -1)
+
+
+def _attn_block_last(layer, xn, L, B, idx, training):
+    """Attention block of a FINAL layer whose consumer only reads the last sequence step (the `mems` stacks with
+    all_steps=False, src/dynamic_models2.py:257): queries from the last step, keys / values from every step.  The
+    causal-offset mask leaves every key open for the last query, so this equals row L-1 of the full block."""
+    sa = layer.self_attn
+    E = xn.shape[1]
+    H, hd, aH, ahd = sa.num_heads, sa.head_dim, sa.active_num_heads, sa.active_head_dim
+    D = aH * ahd
+    dev = xn.device
+    Wi, bi = sa.in_proj_weight, sa.in_proj_bias
+    rq, r0q = in_proj_rows(H, hd, aH, ahd, 0, 1, dev)
+    rkv, r0kv = in_proj_rows(H, hd, aH, ahd, 1, 3, dev)
+    q = ops.linear(xn[(L - 1) * B:], Wi, bi, N=D, K=E, row0=r0q, row_idx=rq, col_idx=idx)
+    kv = ops.linear(xn, Wi, bi, N=2 * D, K=E, row0=r0kv, row_idx=rkv, col_idx=idx)
+    o = ops.attention(q, kv[:, :D], kv[:, D:], Lq=1, Lk=L, B=B, H=aH, hd=ahd, scale=ahd ** -0.5, p=sa.attn_dropout,
+                      training=training)
+    cols = out_proj_cols(H, hd, aH, ahd, dev)
+    n_out = idx.numel() if idx is not None else sa.out_proj.weight.shape[0]
+    return ops.linear(o, sa.out_proj.weight, sa.out_proj.bias, N=n_out, K=D, row_idx=idx, col_idx=cols)
 
 
 def _ffn(layer, xn, idx, training):
@@ -68,9 +89,11 @@ class DynamicTransformerEncoder(TransformerEncoder):
         self.layer_norm = DynamicLayerNorm(embed_dim)
         self.active_layer_num = layers
 
-    def forward(self, x_in, x_in_k=None, x_in_v=None, active_mask=[None]):
+    def forward(self, x_in, x_in_k=None, x_in_v=None, active_mask=[None], last_only=False):
         """x_in: [L, B, E] (any strides); optional key/value streams [Lk, B, E]; ``active_mask``
-        gathers the input columns of every weight (masked `mems` stacks).  reference :56-88."""
+        gathers the input columns of every weight (masked `mems` stacks).  reference :56-88.
+        ``last_only`` (extension, self-attention stacks): the caller only consumes the last sequence step, so the
+        final layer's query side runs on that step alone and the result is returned as [1, B, E] (== out[-1:])."""
         masked = is_masked(active_mask)
         if masked:
             assert (x_in_k is None) and (x_in_v is None)
@@ -96,6 +119,12 @@ class DynamicTransformerEncoder(TransformerEncoder):
         for i in range(n):
             layer = self.layers[i]
             ln0, ln1 = layer.layer_norms[0].ln, layer.layer_norms[1].ln
+            if last_only and not cross and i + 1 == n:
+                a = _attn_block_last(layer, xn, L, B, idx, tr)
+                x1, xn1 = ops.res_drop_ln(x[(L - 1) * B:], a, ln1.weight, ln1.bias, idx, layer.res_dropout, tr, ln1.eps)
+                y = _ffn(layer, xn1, idx, tr)
+                _, out = ops.res_drop_ln(x1, y, fw, fb, idx, layer.res_dropout, tr, feps)
+                return out.view(1, B, E)
             kn = vn = None
             if cross:   # the SAME LN0 normalises the (never updated) key / value streams
                 kn = ops.layer_norm(xk, ln0.weight, ln0.bias, None, ln0.eps)

@@ -281,7 +281,9 @@ class DynamicMULTModel(nn.Module):
                 mask.extend(range(k * d, (k + 1) * d))
                 out_index.extend(range(d * slot * i + k * d, d * slot * i + (k + 1) * d))
             mask_t = make_mask(mask, dev)          # cached: no per-step host->device copy
-            h = self.trans_mems['mems' + self.modality_list[i]](h, active_mask=mask_t)
+            # evaluation (EA fitness): only h[-1] is consumed below -> final layer on the last step only
+            h = self.trans_mems['mems' + self.modality_list[i]](h, active_mask=mask_t,
+                                                                last_only=(not self.all_steps) and (not self.training))
             if self.all_steps:
                 hs.append(h)
             else:

@@ -131,3 +131,25 @@ def test_train_step_runs_and_resamples():
     y = torch.randn(4, 1, device="cuda")
     losses = [float(train_step(m, opt, torch.nn.L1Loss(), xs, y, hyp)) for _ in range(12)]
     assert all(torch.isfinite(torch.tensor(losses)))
+
+
+def test_per_op_last_only_equals_full_last_step():
+    """Evaluation path (EA fitness): a masked self-attention stack run with last_only=True (final layer on the last
+    sequence step only) returns exactly row L-1 of the full forward."""
+    import torch
+    from mtb200 import ops
+    from modules.dynamic_transformer import DynamicTransformerEncoder
+    ops.set_gemm_mode("fp32")
+    torch.manual_seed(3)
+    enc = DynamicTransformerEncoder(200, 25, 8, 2, attn_mask=True).cuda().eval()
+    enc.set_active(2, 200, 8, 25)
+    x = torch.randn(37, 5, 120, device="cuda")
+    mask = list(range(0, 40)) + list(range(80, 160))           # three of five 40-wide blocks
+    full = enc(x, active_mask=mask)
+    last = enc(x, active_mask=mask, last_only=True)
+    assert last.shape == (1, 5, 120)
+    err = float((last[0] - full[-1]).abs().max() / full[-1].abs().max())
+    assert err < 1e-5, err
+    enc1 = DynamicTransformerEncoder(200, 25, 8, 1, attn_mask=True).cuda().eval()      # single-layer stack, unmasked
+    x1 = torch.randn(9, 3, 200, device="cuda")
+    assert float((enc1(x1, last_only=True)[0] - enc1(x1)[-1]).abs().max()) < 1e-5
