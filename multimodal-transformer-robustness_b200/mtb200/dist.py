@@ -59,11 +59,24 @@ class GradSync:
         self.last_bytes = sum(hi - lo for lo, hi in rs) * 4
         if n == 1:
             return
-        works = []
-        for lo, hi in rs:
-            t = engine.grad_arena[lo:hi]
-            t.div_(n)
-            works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        ts = [engine.grad_arena[lo:hi] for lo, hi in rs]
+        if not ts:
+            return
+        if dist.get_backend(self.group) == "nccl":
+            # ONE NCCL group call for all ranges (ncclGroupStart/End) with in-network averaging: no per-range
+            # launch latency and no scaling kernels -- matters at 8 GPUs, where a step is only ~3 ms
+            try:
+                with dist._coalescing_manager(group=self.group, device=ts[0].device, async_ops=False):
+                    for t in ts:
+                        dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+                return
+            except Exception:
+                pass                                   # private API moved: fall back to one call per range
+            for t in ts:
+                dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+            return
+        torch._foreach_div_(ts, float(n))              # gloo (CPU tests) has no AVG
+        works = [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True) for t in ts]
         for w in works:
             w.wait()
 

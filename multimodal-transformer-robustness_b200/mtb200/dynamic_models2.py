@@ -18,11 +18,12 @@ from __future__ import annotations
 from typing import List
 
 import torch
+import torch.nn.functional as F
 from torch import nn
 
 from modules.dynamic_layers import DynamicLinear
 from modules.dynamic_transformer import DynamicTransformerEncoder
-from . import ops
+from . import _lib, ops
 from .models2 import AmnSum, ModalityStr, gen_subnet
 from .slicing import make_mask
 
@@ -71,7 +72,15 @@ class Conv1x1FrontEnd(nn.Module):
 
     def forward(self, x):
         B, L, D = x.shape
-        y = ops.linear(x.reshape(B * L, D), self.weight.view(self.d, self.d_in), None, N=self.d, K=self.d_in)
+        x2, W = x.reshape(B * L, D), self.weight.view(self.d, self.d_in)
+        K = self.d_in
+        if K % 4 != 0 and x.is_cuda and _lib.lib.mtb_get_gemm_mode() == 1:
+            # TMA needs 16-byte row pitches: feature counts such as 74 / 35 (MOSEI audio / video) are zero-padded to a
+            # multiple of 4 so the projection and its weight gradient run on the tcgen05 engine instead of the fp32
+            # fallback (the padded columns multiply zeros; autograd slices the weight gradient back)
+            pad = (-K) % 4
+            x2, W, K = F.pad(x2, (0, pad)), F.pad(W, (0, pad)), K + pad
+        y = ops.linear(x2, W, None, N=self.d, K=K)
         return y.view(B, L, self.d).transpose(1, 2)            # [B, d, L] view, like the conv output
 
 
