@@ -172,9 +172,10 @@ class Op:
 
 class Batch:
     """a run of finalised Ops packed for ONE native call (mtb_run_ops): [(kind, n, descriptor array, side)]"""
-    __slots__ = ("arr", "n", "ops", "launches")
+    __slots__ = ("arr", "n", "ops", "launches", "grad_params")
 
     def __init__(self, ops):
+        self.grad_params = None               # backward stage batches: parameters whose gradients are final afterwards
         entries = []
         for op in ops:
             kind = _lib.OP_KIND[op.fn.mtb_name]
@@ -796,7 +797,7 @@ class Plan:
         self.n_bwd_launches = 0
 
 
-def _run(ops, stream: int, side=None):
+def _run(ops, stream: int, side=None, stage_hook=None):
     """side: optional (torch side stream, fork event, join event) -- ops flagged `side` are launched there, ordered
     after everything issued so far on the main stream; the main stream re-joins at the end of the list."""
     sp = C.c_void_p(stream)
@@ -811,6 +812,8 @@ def _run(ops, stream: int, side=None):
             if rc != 0:
                 what = op.ops[0].what
                 raise _lib.MtbError(f"batched launches starting at {what} failed ({rc}): {lib.mtb_last_error().decode()}")
+            if stage_hook is not None and op.grad_params:
+                stage_hook(op.grad_params)        # data parallel: this stage's gradients can be reduced while earlier stages run
             continue
         if tp is ZeroOp:
             op.t.zero_()
@@ -876,6 +879,7 @@ class Engine:
         self.prewarm = True
         self.side_stream_wgrad = True
         self._side = None
+        self.stage_hook = None             # set by mtb200.dist.GradSync: called with the parameters of every finished backward stage
         self.prune_last_rows = True        # final `mems` layer on the last sequence step only (results-identical)
         _install_fast_attrs(model)
         self.params = [p for p in model.parameters()]
@@ -1164,6 +1168,14 @@ class Engine:
                 o.finalize()
                 ops.append(o)
             ops = Batch(ops) if ops else None
+            if ops is not None and which == "bwd":
+                seen_p, gp = set(), []
+                for ep in eps:
+                    for p_ in ep.active_params:
+                        if id(p_) not in seen_p:
+                            seen_p.add(id(p_))
+                            gp.append(p_)
+                ops.grad_params = gp
             if len(self._merge_cache) > 8192:
                 self._merge_cache.clear()
             self._merge_cache[key] = ops
@@ -1434,7 +1446,7 @@ class Engine:
             if self._side is None:
                 self._side = (torch.cuda.Stream(device=self.device), torch.cuda.Event(), torch.cuda.Event())
             side = self._side
-        _run(ops, stream, side)
+        _run(ops, stream, side, self.stage_hook if which == "bwd" else None)
         self.stats["eager_runs"] += 1
 
     def forward(self, px: Sequence[torch.Tensor]) -> torch.Tensor:
