@@ -31,7 +31,7 @@ def test_descriptor_layouts_match_header_sizes():
     names = {"mtb_rng": _lib.Rng, "mtb_embed_desc": _lib.EmbedDesc, "mtb_resln_desc": _lib.ResLnDesc, "mtb_addn_desc": _lib.AddNDesc, "mtb_segs": _lib.Segs,
              "mtb_resln_bwd_desc": _lib.ResLnBwdDesc, "mtb_linear_desc": _lib.LinearDesc,
              "mtb_linear_bwd_desc": _lib.LinearBwdDesc, "mtb_attn_desc": _lib.AttnDesc,
-             "mtb_attn_bwd_desc": _lib.AttnBwdDesc}
+             "mtb_attn_bwd_desc": _lib.AttnBwdDesc, "mtb_adam_desc": _lib.AdamDesc, "mtb_op": _lib.OpDesc}
     src = '#include <stdio.h>\n#include "multb200.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in names) + "return 0;}"
     with tempfile.TemporaryDirectory() as td:
@@ -136,3 +136,17 @@ def test_ea_search_visits_the_reference_candidates(golden):
     assert seen == ref
     assert best_valids == G["best_valids"]
     assert best_info[0] == G["best_info"][0]
+
+
+def test_plan_stage_merge_order():
+    """Memoised encoder plans are merged in lock-step by launch rank: forward by (layer, op), backward by
+    (-layer, op) with the pruned q-part dgrad after the k/v dgrad that initialises its buffer."""
+    from mtb200.engine import _rank
+    fwd = ["embed", "ln_first"] + [f"{n}[{i}]" for i in range(3)
+                                   for n in ("ln0_kv", "in_proj", "attn", "out_proj", "res_ln1", "fc1", "fc2", "res_ln2")]
+    assert sorted(fwd, key=_rank) == fwd
+    bwd = [f"{n}[{i}]" for i in (2, 1, 0)
+           for n in ("res_ln2_bwd", "fc2_bwd", "fc1_bwd", "res_ln1_bwd", "out_proj_bwd", "attn_bwd", "in_proj_bwd", "in_proj_bwd_q",
+                     "wgrad", "ln0_kv_bwd")] + ["ln_first_bwd", "embed_bwd"]
+    assert sorted(bwd, key=_rank) == bwd
+    assert all(_rank(a) != _rank(b) for a in fwd for b in fwd if a != b)
