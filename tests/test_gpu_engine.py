@@ -329,3 +329,46 @@ def test_engine_memoised_plans_match_per_op_path_over_random_configs():
                 assert_rel(a, b, 1e-4, f"grad {k} (config {it})")
     m.use_engine = True
     assert len(seen) >= 3
+
+
+def test_engine_two_modality_variant_matches_per_op_path():
+    """BASELINE configs[4] shape family: two modalities, d=512, 16 heads x 32 -- plan executor (memoised plans, last-row
+    pruning) vs the per-op autograd path, eval mode, fp32 engine; plus finite training steps on the tensor-core engine."""
+    from mtb200 import ops
+    from mtb200.dynamic_models2 import DynamicMULTModel
+    from mtb200.optim import FlatAdam
+    from mtb200.train import HypParams, sample_next_config, train_step
+    torch.manual_seed(11)
+    ops.set_gemm_mode("fp32")
+    lens = (49, 64)
+    m = DynamicMULTModel(origin_dimensions=[48, 40], dimension=512, num_heads=16, head_dim=32, layers_single_attn=2,
+                         layers_hybrid_attn=2, layers_self_attn=2, attn_dropout=[0.1, 0.1, 0.0], relu_dropout=0.1,
+                         res_dropout=0.1, out_dropout=0.1, embed_dropout=0.1, attn_mask=True, output_dim=10,
+                         modality_set=["p", "s"], all_steps=False, front_end="conv1d").cuda().eval()
+    hyp = HypParams(["p", "s"], [[0], [1], [0, 1]], 2, 2, 2, 512, 16, 32, seq_lens=lens)
+    xs = [torch.randn(2, lens[i], d, device="cuda") for i, d in enumerate((48, 40))]
+    y = torch.randn(2, 10, device="cuda")
+    seen = set()
+    for it in range(6):
+        sample_next_config(m, hyp)
+        seen.add((tuple(m.active_modality), str(m.active_cross_output)))
+        res = {}
+        for use in (True, False):
+            m.use_engine = use
+            m.zero_grad()
+            pred, _ = m(xs)
+            torch.nn.functional.l1_loss(pred, y).backward()
+            res[use] = (pred.detach().clone(), {k: (None if p.grad is None else p.grad.detach().clone()) for k, p in m.named_parameters()})
+        assert_rel(res[True][0], res[False][0], 2e-5, f"pred (config {it})")
+        for k in res[True][1]:
+            a, b = res[True][1][k], res[False][1][k]
+            if a is not None and b is not None and float(b.abs().max()) > 0:
+                assert_rel(a, b, 2e-4, f"grad {k} (config {it})")
+    assert len(seen) >= 2
+    m.use_engine = True
+    m.train()
+    ops.set_gemm_mode("tf32")
+    opt = FlatAdam(m, lr=1e-4)
+    losses = [float(train_step(m, opt, torch.nn.L1Loss(), xs, y, hyp)) for _ in range(8)]
+    assert all(math.isfinite(v) for v in losses)
+    ops.set_gemm_mode("fp32")

@@ -153,6 +153,8 @@ def test_tc_block_gathered_linear(tf32, which):
     (7, 7, 3, 8, 5, 0.0), (50, 50, 4, 8, 25, 0.1), (5, 9, 3, 4, 5, 0.1), (9, 4, 2, 4, 5, 0.0), (1, 1, 4, 8, 25, 0.1),
     (130, 70, 2, 2, 25, 0.1), (70, 130, 2, 2, 32, 0.1), (200, 50, 2, 8, 25, 0.0), (50, 200, 2, 8, 25, 0.1),
     (500, 500, 2, 8, 25, 0.1), (300, 129, 1, 3, 17, 0.0),
+    # BASELINE configs[4] (avMNIST-shaped variant): 16 heads x 32, long sequences
+    (784, 784, 1, 16, 32, 0.1), (196, 1024, 1, 16, 32, 0.0),
 ])
 def test_tc_attention_matches_oracle(tf32, Lq, Lk, B, H, hd, p):
     """tcgen05 flash attention (QK^T and PV on tensor cores, TF32) vs the fp32 oracle with the
