@@ -78,3 +78,17 @@ for mode in ("simt", "tc"):
         o = fn(); go = torch.randn_like(o)
         report(f"attn_bwd dq+dkv ({mode}) [Lq{Lq},Lk{Lk}]", timeit(lambda: torch.autograd.grad(o, qkv, go, retain_graph=True)), flops=2.5 * fl)
 ops.set_attn_mode("auto")
+# BASELINE configs[4]: long-sequence attention stress (16 heads x 32).  The reference materialises the [B*H, L, L] fp32
+# score tensor 4-5 times per layer: 8 x 16 x 4096^2 x 4 B = 8.6 GB per copy.
+if only == "attnlong":
+    ops.set_attn_mode("tc")
+    for (L, Bb, Hh, hdd) in [(784, 32, 16, 32), (2048, 8, 16, 32), (4096, 8, 16, 32)]:
+        D = Hh * hdd
+        qkv = [torch.randn(L * Bb, D, device=dev, generator=g).requires_grad_(True) for _ in range(3)]
+        U = L * (L + 1) // 2
+        fl = 4.0 * Bb * D * U
+        fn = lambda: ops.attention(qkv[0], qkv[1], qkv[2], Lq=L, Lk=L, B=Bb, H=Hh, hd=hdd, scale=hdd ** -0.5, p=0.1, training=True)
+        report(f"attn_fwd (tc) [L{L},B{Bb},H{Hh},hd{hdd}] p=0.1", timeit(fn, 5), bytes_=4 * D * Bb * 4 * L, flops=fl)
+        o = fn(); go = torch.randn_like(o)
+        report(f"attn_bwd dq+dkv (tc) [L{L},B{Bb},H{Hh},hd{hdd}]", timeit(lambda: torch.autograd.grad(o, qkv, go, retain_graph=True), 5), flops=2.5 * fl)
+    ops.set_attn_mode("auto")
