@@ -312,6 +312,65 @@ class DynamicMULTModel(nn.Module):
         y = ops.linear(z, self.out_layer.l.weight, self.out_layer.l.bias, N=self.output_dim, K=C, col_idx=idx)
         return y.view(*lead, self.output_dim), []
 
+    # ------------------------------------------------------------------ sub-network export
+    def get_active_subnet(self, active_self_attn_layer_num, active_single_attn_layer_num: list, active_hybrid_attn_layer_num,
+                          active_dimension, active_head_num, active_head_dim, active_modality: list, active_cross: list,
+                          active_cross_output: list):
+        """Static copy of ONE sub-network (reference :293-389, which cannot run at HEAD: SURVEY A.8).  Same arguments
+        as ``set_active``.  Returns a ``mtb200.models2.MULTModel`` whose forward takes the inputs of the needed
+        modalities only (``sub.modality_list``) and equals this model's forward under the same configuration."""
+        from .models2 import MULTModel
+        dev = next(self.parameters()).device
+        d = self.d
+        outs_of = [(i, list(active_cross_output[i])) for i in active_modality if active_cross_output[i]]
+        need = set()
+        for i, outs in outs_of:
+            for name in list(active_cross[i]) + outs:
+                need.update(name)
+        need_idx = [i for i, ch in enumerate(self.modality_list) if ch in need]
+        proj = []
+        for i in need_idx:
+            src = self.proj[i]
+            assert isinstance(src, Conv1x1FrontEnd), "sub-network export copies the sequence-preserving Conv1d(k=1) front-end"
+            fe = Conv1x1FrontEnd(src.d_in, src.d)
+            fe.weight.data.copy_(src.weight.data)
+            proj.append(fe)
+        trans_mems0 = {'mems0' + self.modality_list[i]: self.trans_mems0['mems0' + self.modality_list[i]].get_active_subnet(
+            active_layer_num=active_single_attn_layer_num[i], active_dimension=active_dimension, active_head_num=active_head_num,
+            active_head_dim=active_head_dim, active_mask=[None]) for i in need_idx}
+        trans = {}
+        for i, _ in outs_of:
+            for name in active_cross[i]:
+                if 'cross' + name not in trans:
+                    trans['cross' + name] = self.trans['cross' + name].get_active_subnet(
+                        active_layer_num=active_hybrid_attn_layer_num, active_dimension=active_dimension,
+                        active_head_num=active_head_num, active_head_dim=active_head_dim, active_mask=[None])
+        trans_mems, out_index = {}, []
+        for i, outs in outs_of:
+            slot = len(self.modality_index_list[i])
+            mask = []
+            for name in outs:
+                k = self.modality_index_list[i][name]
+                mask.extend(range(k * d, (k + 1) * d))
+                out_index.extend(range(d * slot * i + k * d, d * slot * i + (k + 1) * d))
+            trans_mems['mems' + self.modality_list[i]] = self.trans_mems['mems' + self.modality_list[i]].get_active_subnet(
+                active_layer_num=active_self_attn_layer_num, active_dimension=active_dimension, active_head_num=active_head_num,
+                active_head_dim=active_head_dim, active_mask=mask)
+        proj1 = self.proj1.copy(dim_in=None, dim_out=None, mask_in=out_index, mask_out=[None])
+        proj2 = self.proj2.copy(dim_in=None, dim_out=None, mask_in=[None], mask_out=out_index)
+        out_layer = self.out_layer.copy(dim_in=None, dim_out=None, mask_in=out_index, mask_out=[None])
+        sub = MULTModel(
+            proj=nn.ModuleList(proj), trans_mems0=nn.ModuleDict(trans_mems0), trans=nn.ModuleDict(trans),
+            trans_mems=nn.ModuleDict(trans_mems), proj1=proj1, proj2=proj2, out_layer=out_layer,
+            origin_dimensions=[self.orig_dimensions[i] for i in need_idx], dimension=d, num_heads=active_head_num,
+            head_dim=active_head_dim, layers_hybrid_attn=active_hybrid_attn_layer_num, layers_self_attn=active_self_attn_layer_num,
+            attn_dropout=[self.attn_dropout[i] for i in need_idx] + [self.attn_dropout[-1]], relu_dropout=self.relu_dropout,
+            res_dropout=self.res_dropout, out_dropout=self.out_dropout, embed_dropout=self.embed_dropout, attn_mask=self.attn_mask,
+            output_dim=self.output_dim, cross=[list(active_cross[i]) for i, _ in outs_of], cross_output=[o for _, o in outs_of],
+            modality_list=[self.modality_list[i] for i in need_idx], all_steps=self.all_steps,
+            out_modalities=[self.modality_list[i] for i, _ in outs_of])
+        return sub.to(dev)
+
     # ------------------------------------------------------------------ configuration
     def set_active(self, active_self_attn_layer_num, active_single_attn_layer_num: list, active_hybrid_attn_layer_num,
                    active_dimension, active_head_num, active_head_dim, active_modality: list, active_cross: list,

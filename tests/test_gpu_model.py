@@ -153,3 +153,44 @@ def test_per_op_last_only_equals_full_last_step():
     enc1 = DynamicTransformerEncoder(200, 25, 8, 1, attn_mask=True).cuda().eval()      # single-layer stack, unmasked
     x1 = torch.randn(9, 3, 200, device="cuda")
     assert float((enc1(x1, last_only=True)[0] - enc1(x1)[-1]).abs().max()) < 1e-5
+
+
+def test_model_level_subnet_export_equals_dynamic_forward():
+    """The author's invariant at model level: the static sub-network extracted by get_active_subnet computes exactly
+    what the supernet computes under the same configuration (eval mode, fp32 engine; both the plan executor and the
+    per-op path of the supernet)."""
+    import torch
+    from mtb200 import ops
+    from mtb200.dynamic_models2 import DynamicMULTModel
+    from mtb200.models2 import MULTModel
+    from mtb200.train import ALL_POOL_3, HypParams, sample_next_config
+    torch.manual_seed(21)
+    ops.set_gemm_mode("fp32")
+    lens = (6, 14, 14)
+    m = DynamicMULTModel(origin_dimensions=[12, 7, 5], dimension=40, num_heads=8, head_dim=5, layers_single_attn=2,
+                         layers_hybrid_attn=2, layers_self_attn=1, attn_dropout=[0.1, 0.1, 0.0, 0.0], relu_dropout=0.1,
+                         res_dropout=0.3, out_dropout=0.1, embed_dropout=0.3, attn_mask=True, output_dim=3,
+                         modality_set=["l", "a", "v"], all_steps=False, front_end="conv1d").cuda().eval()
+    hyp = HypParams(["l", "a", "v"], ALL_POOL_3, 2, 1, 2, 40, 8, 5, seq_lens=lens)
+    xs = [torch.randn(4, lens[i], d, device="cuda") for i, d in enumerate((12, 7, 5))]
+    kinds = set()
+    with torch.no_grad():
+        for it in range(8):
+            am, cross, outs, single = sample_next_config(m, hyp)
+            sub = m.get_active_subnet(active_self_attn_layer_num=1, active_single_attn_layer_num=single,
+                                      active_hybrid_attn_layer_num=2, active_dimension=40, active_head_num=8, active_head_dim=5,
+                                      active_modality=am, active_cross=cross, active_cross_output=outs).eval()
+            assert isinstance(sub, MULTModel)
+            kinds.add((len(sub.modality_list), len(sub.out_modalities)))
+            sub_in = [xs[["l", "a", "v"].index(ch)] for ch in sub.modality_list]
+            y_sub = sub(sub_in)
+            for use in (True, False):
+                m.use_engine = use
+                y_dyn, _ = m(xs)
+                err = float((y_sub - y_dyn).abs().max() / y_dyn.abs().max())
+                assert err < 2e-5, (it, use, err, am, outs)
+    m.use_engine = True
+    assert len(kinds) >= 2
+    # the extracted model holds copies: it survives changes to the supernet and pickles as a plain module
+    n_sub = sum(p.numel() for p in sub.parameters())
+    assert 0 < n_sub < sum(p.numel() for p in m.parameters())
