@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MTB_ABI_VERSION 11
+#define MTB_ABI_VERSION 12
 #define MTB_MAX_GROUP 24
 
 /* Dropout RNG: Philox4x32-7.  Element `i` of a dropout site is kept iff
@@ -194,6 +194,10 @@ typedef struct {
   float* lse;
   int Lq, Lk, B, H, hd;
   float scale; float p; mtb_rng rng;
+  /* optional [B*H*Lq, ceil(Lk/32)] words: when p > 0 the forward kernel stores the dropout keep bits of every score it
+   * computed (bit j%32 of word j/32 of row (b*H+h)*Lq + i); the backward kernels read them instead of re-drawing the
+   * Philox stream twice.  NULL: not stored / re-drawn.  Tensor-core engine only (the fp32 engine ignores it). */
+  uint32_t* keep_bits;
 } mtb_attn_desc;
 int mtb_attn_fwd(const mtb_attn_desc* d, int n, void* stream);
 
@@ -210,6 +214,7 @@ typedef struct {
   float* dv; int64_t lddv;
   int Lq, Lk, B, H, hd;
   float scale; float p; mtb_rng rng;
+  const uint32_t* keep_bits;   /* optional: the words the forward kernel stored (see mtb_attn_desc) */
 } mtb_attn_bwd_desc;
 int mtb_attn_bwd(const mtb_attn_bwd_desc* d, int n, void* stream);
 

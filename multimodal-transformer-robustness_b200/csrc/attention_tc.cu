@@ -190,10 +190,20 @@ __device__ __forceinline__ float fast_exp2(float x) {          // one MUFU.EX2; 
   return y;
 }
 
+__device__ __forceinline__ uint32_t row_keep_bits32(const DropCtx& dc, uint64_t idx0) {   // keep bits of 32 consecutive columns
+  uint32_t bits = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const uint4 r = drop_rand4(dc, (idx0 >> 2) + (uint64_t)q);
+    bits |= ((r.x >= dc.thr ? 1u : 0u) | (r.y >= dc.thr ? 2u : 0u) | (r.z >= dc.thr ? 4u : 0u) | (r.w >= dc.thr ? 8u : 0u)) << (4 * q);
+  }
+  return bits;
+}
+
 template <bool MASKED>
 __device__ __forceinline__ void fwd_softmax_half(float (&s)[32], const float c2, const int i, const int jb, const int Lk, const int off,
-                                                 float& m_run, float& l_run, float& corr, const DropCtx& dc, const uint64_t idx0,
-                                                 uint8_t* prow_region, const int row) {
+                                                 float& m_run, float& l_run, float& corr, const bool drop_on, const float inv_keep,
+                                                 const uint32_t kbits, uint8_t* prow_region, const int row) {
   float mx = -CUDART_INF_F;
 #pragma unroll
   for (int c = 0; c < 32; ++c) {
@@ -219,10 +229,9 @@ __device__ __forceinline__ void fwd_softmax_half(float (&s)[32], const float c2,
       pk[e] = fast_exp2(s[c4 + e] - m_use);                      // exp2(-inf) = 0 for masked entries
       rs += pk[e];
     }
-    if (dc.on) {
-      const uint4 r = drop_rand4(dc, (idx0 + (uint64_t)c4) >> 2);
-      pk[0] = r.x >= dc.thr ? pk[0] * dc.inv_keep : 0.f; pk[1] = r.y >= dc.thr ? pk[1] * dc.inv_keep : 0.f;
-      pk[2] = r.z >= dc.thr ? pk[2] * dc.inv_keep : 0.f; pk[3] = r.w >= dc.thr ? pk[3] * dc.inv_keep : 0.f;
+    if (drop_on) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) pk[e] = ((kbits >> (c4 + e)) & 1u) ? pk[e] * inv_keep : 0.f;
     }
     *reinterpret_cast<float4*>(prow_region + swz128(row, c4 * 4)) =
         make_float4(to_tf32(pk[0]), to_tf32(pk[1]), to_tf32(pk[2]), to_tf32(pk[3]));
@@ -299,6 +308,11 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
   float m_run = -CUDART_INF_F, l_run = 0.f;
   uint8_t* my_p = Ps + half * (TQ * 128);
   const uint64_t idx_row = ((uint64_t)((int64_t)bh * Lq + irow)) * (uint64_t)Lk4 + (uint64_t)(half * 32);
+  // dropout keep bits of my 32 columns of the current tile: drawn one tile ahead, while the MMAs run; optionally stored
+  // for the backward kernels (one word per thread and tile)
+  uint32_t kbits = dc.on ? row_keep_bits32(dc, idx_row) : 0u;
+  const int KW = (Lk + 31) >> 5;
+  uint32_t* wrow = (d.keep_bits != nullptr && dc.on && i < Lq) ? d.keep_bits + ((int64_t)bh * Lq + i) * KW : nullptr;
 
   ATRACE(0);
   for (int t = 0; t < T; ++t) {
@@ -322,9 +336,10 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
     float corr;
     const bool tile_open = (j0 + TK <= Lk) && (j0 + TK - 1 - i0 < 1 + off);     // CTA-uniform: no entry of this tile is masked
     if (tile_open)
-      fwd_softmax_half<false>(s, c2, i, j0 + half * 32, Lk, off, m_run, l_run, corr, dc, idx_row + (uint64_t)j0, my_p, row);
+      fwd_softmax_half<false>(s, c2, i, j0 + half * 32, Lk, off, m_run, l_run, corr, dc.on, dc.inv_keep, kbits, my_p, row);
     else
-      fwd_softmax_half<true>(s, c2, i, j0 + half * 32, Lk, off, m_run, l_run, corr, dc, idx_row + (uint64_t)j0, my_p, row);
+      fwd_softmax_half<true>(s, c2, i, j0 + half * 32, Lk, off, m_run, l_run, corr, dc.on, dc.inv_keep, kbits, my_p, row);
+    if (wrow != nullptr && 2 * t + half < KW) wrow[2 * t + half] = kbits;
     ATRACE(8 + t * 8 + 3);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     fence_async_smem();
@@ -346,6 +361,7 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
         a_mma_tf32(t_s, desc_kmajor(a_smem_u32(Qs) + k * 32), desc_kmajor(a_smem_u32(nxt) + k * 32), id_s, k != 0 ? 1u : 0u);
       a_commit(a_smem_u32(&bar_s));
     }
+    if (dc.on && t + 1 < T) kbits = row_keep_bits32(dc, idx_row + (uint64_t)(j0 + TK));     // next tile's bits, behind the PV MMAs
     a_mbar_wait(a_smem_u32(&bar_o), ph);
     tc_fence_after();
     ATRACE(8 + t * 8 + 5);
@@ -396,16 +412,6 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
 constexpr int ATC_DQ_TMEM = 256;
 constexpr int ATC_DQ_SMEM = 2 * TQ * 128 + 4 * TK * 128 + (TK / 32) * TQ * 128 + 1024;
 constexpr int AQ_THREADS = 256;
-
-__device__ __forceinline__ uint32_t row_keep_bits32(const DropCtx& dc, uint64_t idx0) {   // keep bits of 32 consecutive columns
-  uint32_t bits = 0;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const uint4 r = drop_rand4(dc, (idx0 >> 2) + (uint64_t)q);
-    bits |= ((r.x >= dc.thr ? 1u : 0u) | (r.y >= dc.thr ? 2u : 0u) | (r.z >= dc.thr ? 4u : 0u) | (r.w >= dc.thr ? 8u : 0u)) << (4 * q);
-  }
-  return bits;
-}
 
 template <bool MASKED>
 __device__ __forceinline__ void dq_math(const float (&s)[32], const float (&dp)[32], float lse2, float delta, uint32_t kbits, bool drop_on,
@@ -507,7 +513,9 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
   };
   if (tid == 0) issue_s();
   const uint64_t idx_row = ((uint64_t)((int64_t)bh * Lq + irow)) * (uint64_t)Lk4 + (uint64_t)(half * 32);
-  uint32_t kbits = dc.on ? row_keep_bits32(dc, idx_row) : 0u;
+  const int KW = (Lk + 31) >> 5;
+  const uint32_t* wrow = (d.keep_bits != nullptr && dc.on) ? d.keep_bits + ((int64_t)bh * Lq + irow) * KW : nullptr;
+  uint32_t kbits = !dc.on ? 0u : wrow != nullptr ? (half < KW ? wrow[half] : 0u) : row_keep_bits32(dc, idx_row);
   uint8_t* my_ds = dSs + half * (TQ * 128);
 
   QTRACE(0);
@@ -525,6 +533,8 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
       stage_rows256<true>(Kmn + ((t + 1) & 1) * (TK * 128), d.k, d.ldk, d.B, b, h, hd, j0 + TK, Lk, TK);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    uint32_t kbits_next = 0u;                  // stored keep bits of the next tile: loaded now, used one iteration later
+    if (wrow != nullptr && t + 1 < T && 2 * (t + 1) + half < KW) kbits_next = wrow[2 * (t + 1) + half];
     QTRACE(8 + t * 8 + 2);
     float s[32], dp[32];
     a_tmem_ld32(t_s + lane_addr + half * 32, s);
@@ -553,7 +563,8 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
                    desc_mnmajor(a_smem_u32(Kmn + (t & 1) * (TK * 128)) + kk * 1024), id_q, (t | kk) != 0 ? 1u : 0u);
       a_commit(a_smem_u32(&bar_b));
     }
-    if (dc.on && t + 1 < T) kbits = row_keep_bits32(dc, idx_row + (uint64_t)(j0 + TK));   // drawn while the MMAs run
+    if (dc.on && t + 1 < T)                    // forward kernel's bits if it stored them, else re-drawn while the MMAs run
+      kbits = wrow != nullptr ? kbits_next : row_keep_bits32(dc, idx_row + (uint64_t)(j0 + TK));
     QTRACE(8 + t * 8 + 7);
   }
   QTRACE(1);
@@ -603,6 +614,20 @@ __device__ __forceinline__ void dkv_keep_bits(const DropCtx& dc, int bh, int Lq,
   }
 #pragma unroll
   for (int m = 0; m < 4; ++m) w[m] = __shfl_sync(0xffffffffu, bits, (lane & ~3) + m) >> k;   // bit 4 q of w[m]: query 4 q + m
+}
+
+// same result from the words the forward kernel stored: query c of my 16 columns, bit (key j) of word (j / 32)
+__device__ __forceinline__ void dkv_keep_bits_stored(const uint32_t* bits, int KW, int bh, int Lq, int i0h, int jrow, uint32_t (&w)[4]) {
+  const int jw = jrow >> 5, jb = jrow & 31;
+  uint32_t wb[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const int ii = i0h + c;
+    wb[c] = (ii < Lq && jw < KW) ? __ldg(bits + ((int64_t)bh * Lq + ii) * KW + jw) : 0u;
+  }
+  w[0] = w[1] = w[2] = w[3] = 0u;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) w[c & 3] |= ((wb[c] >> jb) & 1u) << (c & ~3);
 }
 
 template <bool MASKED>
@@ -710,7 +735,12 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
   };
   if (tid == 0 && T > 0) issue_s(0);
   uint32_t kw[4] = {0u, 0u, 0u, 0u};
-  if (dc.on && T > 0) dkv_keep_bits(dc, bh, Lq, Lk4, i_begin + half * 16, j, kw);
+  const int KW = (Lk + 31) >> 5;
+  const uint32_t* kbits_g = dc.on ? d.keep_bits : nullptr;
+  if (dc.on && T > 0) {
+    if (kbits_g != nullptr) dkv_keep_bits_stored(kbits_g, KW, bh, Lq, i_begin + half * 16, j, kw);
+    else dkv_keep_bits(dc, bh, Lq, Lk4, i_begin + half * 16, j, kw);
+  }
 
   for (int t = 0; t < T; ++t) {
     const int i0 = i_begin + t * TI;
@@ -750,7 +780,10 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
                    (t | kk) != 0 ? 1u : 0u);
       a_commit(a_smem_u32(&bar_b));
     }
-    if (dc.on && t + 1 < T) dkv_keep_bits(dc, bh, Lq, Lk4, i0 + TI + half * 16, j, kw);   // drawn while the MMAs run
+    if (dc.on && t + 1 < T) {                  // next tile's keep bits while the MMAs run: stored words, else re-drawn
+      if (kbits_g != nullptr) dkv_keep_bits_stored(kbits_g, KW, bh, Lq, i0 + TI + half * 16, j, kw);
+      else dkv_keep_bits(dc, bh, Lq, Lk4, i0 + TI + half * 16, j, kw);
+    }
   }
   {
     float dv[16], dk[16];

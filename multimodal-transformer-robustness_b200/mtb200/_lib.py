@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MTB_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libmultb200.so")   # MTB_LIB: instrumented debug builds
 
 MAX_GROUP = 24
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 
 class MtbError(RuntimeError):
@@ -78,7 +78,7 @@ class AttnDesc(C.Structure):
     _fields_ = [("q", C.c_void_p), ("ldq", C.c_int64), ("k", C.c_void_p), ("ldk", C.c_int64),
                 ("v", C.c_void_p), ("ldv", C.c_int64), ("o", C.c_void_p), ("ldo", C.c_int64),
                 ("lse", C.c_void_p), ("Lq", C.c_int), ("Lk", C.c_int), ("B", C.c_int), ("H", C.c_int),
-                ("hd", C.c_int), ("scale", C.c_float), ("p", C.c_float), ("rng", Rng)]
+                ("hd", C.c_int), ("scale", C.c_float), ("p", C.c_float), ("rng", Rng), ("keep_bits", C.c_void_p)]
 
 
 class AttnBwdDesc(C.Structure):
@@ -87,7 +87,7 @@ class AttnBwdDesc(C.Structure):
                 ("d_o", C.c_void_p), ("lddo", C.c_int64), ("lse", C.c_void_p), ("delta", C.c_void_p),
                 ("dq", C.c_void_p), ("lddq", C.c_int64), ("dk", C.c_void_p), ("lddk", C.c_int64),
                 ("dv", C.c_void_p), ("lddv", C.c_int64), ("Lq", C.c_int), ("Lk", C.c_int), ("B", C.c_int),
-                ("H", C.c_int), ("hd", C.c_int), ("scale", C.c_float), ("p", C.c_float), ("rng", Rng)]
+                ("H", C.c_int), ("hd", C.c_int), ("scale", C.c_float), ("p", C.c_float), ("rng", Rng), ("keep_bits", C.c_void_p)]
 
 
 class AdamDesc(C.Structure):

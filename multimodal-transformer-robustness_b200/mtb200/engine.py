@@ -396,8 +396,11 @@ class PlanBuilder:
                 else:
                     qm, km, vm = S["q"], S["k"], S["v"]
                 S["qkv_mats"] = (qm, km, vm)
+                # keep bits of the attention dropout, stored by the forward kernel for the two backward kernels
+                bits = A.alloc(e.B * H * Lq_a * ((e.Lk + 31) // 32)) if (ng and pa > 0.0 and lib.mtb_get_gemm_mode() == 1) else None
+                S["keep_bits"] = bits
                 descs.append(AttnDesc(qm.ptr, qm.ld, km.ptr, km.ld, vm.ptr, vm.ld, o.ptr, o.ld, lse, Lq_a, e.Lk, e.B, H, hd,
-                                      hd ** -0.5, pa, r))
+                                      hd ** -0.5, pa, r, bits))
             self.emit(self.fwd, lib.mtb_attn_fwd, AttnDesc, descs, f"attn[{i}]")
             # d. out-projection ----------------------------------------------------------------
             descs = []
@@ -628,7 +631,7 @@ class PlanBuilder:
                 r, pa = S["rng_attn"]
                 descs.append(AttnBwdDesc(qm.ptr, qm.ld, km.ptr, km.ld, vm.ptr, vm.ld, S["o"].ptr, S["o"].ld, S["g_o"].ptr, S["g_o"].ld,
                                          S["lse"], delta, dq.ptr, dq.ld, dk.ptr, dk.ld, dv.ptr, dv.ld, Lq_a, e.Lk, e.B, H, hd,
-                                         hd ** -0.5, pa, r))
+                                         hd ** -0.5, pa, r, S.get("keep_bits")))
             self.emit(self.bwd, lib.mtb_attn_bwd, AttnBwdDesc, descs, f"attn_bwd[{i}]")
             # b'. in-projection backward
             descs, descs_q = [], []
