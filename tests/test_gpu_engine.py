@@ -372,3 +372,63 @@ def test_engine_two_modality_variant_matches_per_op_path():
     losses = [float(train_step(m, opt, torch.nn.L1Loss(), xs, y, hyp)) for _ in range(8)]
     assert all(math.isfinite(v) for v in losses)
     ops.set_gemm_mode("fp32")
+
+
+def test_engine_layout_grows_with_batch_and_flat_adam_generic_path():
+    """(1) A larger batch than the persistent layout was sized for rebuilds the regions (all caches dropped) and keeps
+    matching the per-op path; going back to the smaller batch re-uses the larger layout.  (2) FlatAdam also serves
+    gradients produced OUTSIDE the plan executor (per-op autograd path): same update as torch.optim.Adam."""
+    from mtb200 import ops
+    from mtb200.dynamic_models2 import DynamicMULTModel
+    from mtb200.optim import FlatAdam
+    from mtb200.train import ALL_POOL_3, HypParams, sample_next_config
+    torch.manual_seed(31)
+    ops.set_gemm_mode("fp32")
+    lens = (6, 14, 14)
+    m = DynamicMULTModel(origin_dimensions=[12, 7, 5], dimension=40, num_heads=8, head_dim=5, layers_single_attn=2,
+                         layers_hybrid_attn=2, layers_self_attn=1, attn_dropout=[0.1, 0.1, 0.0, 0.0], relu_dropout=0.1,
+                         res_dropout=0.3, out_dropout=0.1, embed_dropout=0.3, attn_mask=True, output_dim=1,
+                         modality_set=["l", "a", "v"], all_steps=False, front_end="conv1d").cuda().eval()
+    hyp = HypParams(["l", "a", "v"], ALL_POOL_3, 2, 1, 2, 40, 8, 5, seq_lens=lens)
+    sample_next_config(m, hyp)
+    layouts = []
+    for B in (3, 7, 3, 5):
+        xs = [torch.randn(B, lens[i], d, device="cuda") for i, d in enumerate((12, 7, 5))]
+        y = torch.randn(B, 1, device="cuda")
+        res = {}
+        for use in (True, False):
+            m.use_engine = use
+            m.zero_grad()
+            pred, _ = m(xs)
+            torch.nn.functional.l1_loss(pred, y).backward()
+            res[use] = (pred.detach().clone(), {k: (None if p.grad is None else p.grad.detach().clone()) for k, p in m.named_parameters()})
+        assert_rel(res[True][0], res[False][0], 2e-5, f"pred B={B}")
+        for k in res[True][1]:
+            a, b = res[True][1][k], res[False][1][k]
+            if a is not None and b is not None and float(b.abs().max()) > 0:
+                assert_rel(a, b, 1e-4, f"grad {k} B={B}")
+        layouts.append(m.engine()._layout[0])
+    assert layouts == [3, 7, 7, 7]                      # grew once, then stayed
+    # (2) per-op path + FlatAdam vs torch Adam
+    m.use_engine = False
+    shadow = [p.detach().clone().requires_grad_(True) for p in m.parameters()]
+    ref = torch.optim.Adam(shadow, lr=2e-3)
+    opt = FlatAdam(m, lr=2e-3)
+    xs = [torch.randn(4, lens[i], d, device="cuda") for i, d in enumerate((12, 7, 5))]
+    y = torch.randn(4, 1, device="cuda")
+    for it in range(4):
+        sample_next_config(m, hyp)
+        m.zero_grad()
+        pred, _ = m(xs)
+        torch.nn.functional.l1_loss(pred, y).backward()
+        for s_, p in zip(shadow, m.parameters()):
+            s_.grad = None if p.grad is None else p.grad.detach().clone()
+        n_ref = torch.nn.utils.clip_grad_norm_(shadow, 0.5)
+        ref.step()
+        n = opt.step_clipped(0.5)
+        assert abs(float(n) - float(n_ref)) <= 1e-5 * float(n_ref)
+        for s_, p in zip(shadow, m.parameters()):
+            assert float((p.detach() - s_.detach()).abs().max()) <= 2e-6 + 1e-5 * float(s_.detach().abs().max())
+    sd = opt.state_dict()
+    opt.load_state_dict(sd)
+    m.use_engine = True
