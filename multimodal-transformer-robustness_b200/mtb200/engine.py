@@ -115,6 +115,8 @@ def _rank(what: str) -> Tuple[int, int]:
         return (-2, 0)
     if what == "ln_first":
         return (-1, 0)
+    if what == "ln0_kv_all":
+        return (-1, 1)
     if what == "ln_first_bwd":
         return (1, 0)
     if what == "embed_bwd":
@@ -313,25 +315,27 @@ class PlanBuilder:
         self.emit(self.fwd, lib.mtb_resln_fwd, ResLnDesc, descs, "ln_first")
 
         max_layers = max((e.n_layers for e in group), default=0)
-        for i in range(max_layers):
-            act = [e for e in group if e.n_layers > i]
-            for e in act:
-                e.saved.setdefault("layers", []).append({})
-            # a. LN0 on the key / value streams (cross only; streams are never updated) ------
-            descs = []
-            for e in act:
-                if not e.cross:
-                    continue
+        for e in group:
+            e.saved["layers"] = [{} for _ in range(e.n_layers)]
+        # a. LN0 of EVERY layer on the key / value streams (cross only).  The streams are never updated, so all layers'
+        #    normalised copies only depend on the embed output: one grouped launch instead of one per layer.
+        descs = []
+        for e in group:
+            if not e.cross:
+                continue
+            Tk = e.Lk * e.B
+            for i in range(e.n_layers):
                 S = e.saved["layers"][i]
                 ln = e.enc._ll[i]._lns[0].ln
-                Tk = e.Lk * e.B
                 for nm in ("k", "v"):
                     dst = A.mat(Tk, e.E)
                     st = (A.alloc(Tk), A.alloc(Tk)) if ng else (None, None)
                     S[nm + "n"] = (dst, st)
                     descs.append(ResLnDesc(e.saved["x" + nm].ptr, e.E, None, 0, None, 0, dst.ptr, e.E, ln.weight.data_ptr(),
                                            ln.bias.data_ptr(), None, st[0], st[1], Tk, e.E, ln.eps, 0.0, _NO_RNG))
-            self.emit(self.fwd, lib.mtb_resln_fwd, ResLnDesc, descs, f"ln0_kv[{i}]")
+        self.emit(self.fwd, lib.mtb_resln_fwd, ResLnDesc, descs, "ln0_kv_all")
+        for i in range(max_layers):
+            act = [e for e in group if e.n_layers > i]
             # b. in-projection ----------------------------------------------------------------
             descs = []
             for e in act:

@@ -142,8 +142,8 @@ def test_plan_stage_merge_order():
     """Memoised encoder plans are merged in lock-step by launch rank: forward by (layer, op), backward by
     (-layer, op) with the pruned q-part dgrad after the k/v dgrad that initialises its buffer."""
     from mtb200.engine import _rank
-    fwd = ["embed", "ln_first"] + [f"{n}[{i}]" for i in range(3)
-                                   for n in ("ln0_kv", "in_proj", "attn", "out_proj", "res_ln1", "fc1", "fc2", "res_ln2")]
+    fwd = ["embed", "ln_first", "ln0_kv_all"] + [f"{n}[{i}]" for i in range(3)
+                                                 for n in ("in_proj", "attn", "out_proj", "res_ln1", "fc1", "fc2", "res_ln2")]
     assert sorted(fwd, key=_rank) == fwd
     bwd = [f"{n}[{i}]" for i in (2, 1, 0)
            for n in ("res_ln2_bwd", "fc2_bwd", "fc1_bwd", "res_ln1_bwd", "out_proj_bwd", "attn_bwd", "in_proj_bwd", "in_proj_bwd_q",
