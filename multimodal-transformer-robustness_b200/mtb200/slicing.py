@@ -74,6 +74,17 @@ def _block_structure(ix: Sequence[int]):
 _mask_cache: dict = {}
 
 
+_pin_pool = []          # [pinned int32 tensor, elements used]; slices are never reused (masks are cached for good)
+
+
+def _pinned_slice(n: int) -> torch.Tensor:
+    if not _pin_pool or _pin_pool[-1][1] + n > _pin_pool[-1][0].numel():
+        _pin_pool.append([torch.empty(max(1 << 20, n), dtype=torch.int32).pin_memory(), 0])
+    buf, used = _pin_pool[-1]
+    _pin_pool[-1][1] = used + n
+    return buf[used:used + n]
+
+
 def make_mask(indices: Sequence[int], device) -> Mask:
     """Cached Mask from a Python index list (no device synchronisation)."""
     key = (tuple(indices), str(device))
@@ -83,9 +94,11 @@ def make_mask(indices: Sequence[int], device) -> Mask:
         host = torch.tensor(key[0], dtype=torch.int32)
         if torch.device(device).type == "cuda":
             # a pageable-memory upload would block until the stream has drained (a hidden sync in the training
-            # loop: ~1 ms per new mask); pinned + non_blocking only enqueues the copy
-            host = host.pin_memory()
-            m = Mask(host.to(device, non_blocking=True), ln, segs, host)
+            # loop: ~1 ms per new mask); pinned + non_blocking only enqueues the copy.  The pinned staging comes from a
+            # pool: cudaHostAlloc per mask is itself a device-wide synchronisation point.
+            staged = _pinned_slice(host.numel())
+            staged.copy_(host)
+            m = Mask(staged.to(device, non_blocking=True), ln, segs, staged)
         else:
             m = Mask(host.to(device), ln, segs)
         if len(_mask_cache) > 4096:
