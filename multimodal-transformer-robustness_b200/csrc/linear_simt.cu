@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(G_THREADS) gemm_simt_kernel(const __grid_const
       const int gj = j0 + tx * 4 + v;
       if (gj >= P.J) continue;
       float val = acc[u][v];
-      if (P.bias) val += P.bias[P.mapBias ? P.mapBias[gj] : gj];
+      if (P.bias && split == 0) val += P.bias[P.mapBias ? P.mapBias[gj] : gj];     // split-R: the bias joins once
       if (P.act == 1) {
         val = fmaxf(val, 0.f);
         if (dc.on) val = drop_keep1(dc, (uint64_t)gi * P.J + gj) ? val * dc.inv_keep : 0.f;
@@ -177,6 +177,16 @@ int linear_fwd_simt(const mtb_linear_desc* d, int n, cudaStream_t st) {
     q.bias = x.bias; q.mapBias = x.row_idx;
     q.I = x.M; q.J = x.N; q.R = x.K;
     q.epi = 0; q.act = x.act; q.splits = 1; q.p = x.p; q.rng = x.rng;
+    // A single tile with a long, index-gathered reduction (the head's [B, C] x [C] -> [B, 1] output layer) is one
+    // CTA walking the slabs serially (~2.5 us each): split the reduction, partial sums meet through atomics.
+    const int tiles = ((x.M + GB - 1) / GB) * ((x.N + GB - 1) / GB);
+    const int slabs = (x.K + GK - 1) / GK;
+    if (x.act == 0 && tiles <= 4 && slabs >= 8 && x.ldy == x.N) {
+      int sp = slabs / 2;
+      if (sp > 48) sp = 48;
+      q.splits = sp; q.epi = 2;
+      MTB_CUDA(cudaMemsetAsync(x.Y, 0, (size_t)x.M * x.N * sizeof(float), st));
+    }
   }
   return launch_gemm_simt(p, n, st);
 }
