@@ -224,7 +224,9 @@ int mtb_attn_bwd(const mtb_attn_bwd_desc* d, int n, void* stream);
  * per-launch cost is one driver call instead of one interpreter round trip.  `kind` selects the entry point the
  * descriptor array belongs to; ops flagged `side` (deferred weight gradients, which feed nothing downstream) are
  * issued on `side_stream`, ordered after everything issued before them on `stream`; `stream` re-joins `side_stream`
- * before the call returns.  side_stream == NULL runs everything on `stream`.  Stops at the first failing op. */
+ * before the call returns.  side_stream == NULL runs everything on `stream`.  Stops at the first failing op.
+ * The fork / join events are created once per process on the current device: one device per process (the model this
+ * library is built for: one rank per GPU), calls from a single host thread. */
 enum { MTB_OP_EMBED_FWD = 0, MTB_OP_EMBED_BWD = 1, MTB_OP_ADDN = 2, MTB_OP_RESLN_FWD = 3, MTB_OP_RESLN_BWD = 4,
        MTB_OP_LINEAR_FWD = 5, MTB_OP_LINEAR_BWD = 6, MTB_OP_ATTN_FWD = 7, MTB_OP_ATTN_BWD = 8 };
 typedef struct {
