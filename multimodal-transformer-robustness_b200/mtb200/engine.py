@@ -871,8 +871,9 @@ class Engine:
         self.model = model
         self.device = torch.device(device)
         from . import ops as _ops
-        with torch.cuda.device(self.device):
-            _ops.preload()
+        if self.device.type == "cuda":
+            with torch.cuda.device(self.device):
+                _ops.preload()
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.graph_after = graph_after
         self.plans: Dict[tuple, Plan] = {}
@@ -1040,9 +1041,10 @@ class Engine:
             r.work_cap = int(self._measure(kind, name, enc, Lq, Lk, B, E, mask) * 1.02) + (1 << 20)
             r.work = take(r.work_cap // F4)
             regs[id(enc)] = r
-        free, _ = torch.cuda.mem_get_info(self.device)
-        if off > free * 0.9:
-            raise MemoryError(f"mtb200 engine: encoder buffer needs {off >> 20} MB, {free >> 20} MB free")
+        if self.device.type == "cuda":          # (plans can be BUILT on any device -- CPU structure tests -- but only run on CUDA)
+            free, _ = torch.cuda.mem_get_info(self.device)
+            if off > free * 0.9:
+                raise MemoryError(f"mtb200 engine: encoder buffer needs {off >> 20} MB, {free >> 20} MB free")
         self.enc_buf = None
         self.enc_buf = torch.empty(off, dtype=torch.uint8, device=self.device)
         base = self.enc_buf.data_ptr()
