@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MTB_ABI_VERSION 12
+#define MTB_ABI_VERSION 13
 #define MTB_MAX_GROUP 24
 
 /* Dropout RNG: Philox4x32-7.  Element `i` of a dropout site is kept iff
@@ -52,6 +52,7 @@ int mtb_get_gemm_mode(void);
 /* which attention core mtb_attn_* uses: 0 = fp32 CUDA-core flash kernels, 1 = tcgen05 / TMEM flash
  * kernels (TF32 QK^T, PV, dP, dQ, dK, dV on the tensor core), -1 (default) = follow the GEMM engine. */
 int mtb_set_attn_mode(int mode);
+int mtb_get_attn_mode(void);
 /* force-load every kernel of the library into the current CUDA context (CUDA loads modules lazily;
  * without this the first use of each kernel variant stalls a training step by milliseconds) */
 int mtb_preload(void);

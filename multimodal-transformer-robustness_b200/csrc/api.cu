@@ -73,6 +73,7 @@ int mtb_set_attn_mode(int mode) {
   mtb::g_attn_mode = mode < 0 ? -1 : (mode ? 1 : 0);
   return prev;
 }
+int mtb_get_attn_mode(void) { return mtb::g_attn_mode; }
 uint64_t mtb_launch_count(void) { return mtb::launches(); }
 
 int mtb_linear_fwd(const mtb_linear_desc* d, int n, void* stream) {

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MTB_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libmultb200.so")   # MTB_LIB: instrumented debug builds
 
 MAX_GROUP = 24
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 
 class MtbError(RuntimeError):
@@ -114,6 +114,7 @@ SYMBOLS = {
     "mtb_set_gemm_mode": ([C.c_int], C.c_int),
     "mtb_get_gemm_mode": ([], C.c_int),
     "mtb_set_attn_mode": ([C.c_int], C.c_int),
+    "mtb_get_attn_mode": ([], C.c_int),
     "mtb_launch_count": ([], C.c_uint64),
     "mtb_preload": ([], C.c_int),
     "mtb_dropout_mask": ([Rng, C.c_float, C.c_int64, C.c_void_p, C.c_void_p], C.c_int),

@@ -73,7 +73,9 @@ class GradSync:
         rank, n = world()
         if n == 1 or not self.overlap or dist.get_backend(self.group) != "nccl":
             return
-        for lo, hi in self._ranges_of(engine, params):
+        # max_gap = 0: a merged gap could cover parameters of EARLIER stages whose weight gradients are still being
+        # written by the compute stream -- an in-place async all-reduce over them would race with those writes
+        for lo, hi in self._ranges_of(engine, params, max_gap=0):
             self._pending.append(dist.all_reduce(engine.grad_arena[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True))
         self._done.update(id(p) for p in params)
 

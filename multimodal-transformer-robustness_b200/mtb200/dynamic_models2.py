@@ -204,8 +204,13 @@ class DynamicMULTModel(nn.Module):
             for p in self._outside_engine_params():
                 p.grad = None
             eng._grads_live = False
+            eng._grads_dirty = False
             return
         super().zero_grad(set_to_none=set_to_none)
+        if eng is not None:
+            eng._grads_live = False
+            if set_to_none:
+                eng._grads_dirty = False
 
     def _outside_engine_params(self):
         ps = getattr(self, "_outside_cache", None)

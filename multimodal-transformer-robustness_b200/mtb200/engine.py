@@ -174,10 +174,13 @@ class Op:
 
 class Batch:
     """a run of finalised Ops packed for ONE native call (mtb_run_ops): [(kind, n, descriptor array, side)]"""
-    __slots__ = ("arr", "n", "ops", "launches", "grad_params")
+    __slots__ = ("arr", "n", "ops", "launches", "grad_params", "keep", "graph", "hits")
 
     def __init__(self, ops):
         self.grad_params = None               # backward stage batches: parameters whose gradients are final afterwards
+        self.keep = None                      # EncPlans (and through them the Masks) whose device addresses the descriptors hold
+        self.graph = None                     # CUDA graph of this stage batch once it has been hit often enough
+        self.hits = 0
         entries = []
         for op in ops:
             kind = _lib.OP_KIND[op.fn.mtb_name]
@@ -905,6 +908,10 @@ class Engine:
         self._param_ptr0 = self.params[0].data_ptr() if self.params else 0
         self.last_plan: Optional[Plan] = None
         self.step_offset = 0       # host mirror of rng_state[1]
+        self.generation = 0        # bumped by every forward: all plans share the persistent activation buffer, the scratch
+                                   # arena and the dropout counter, so a backward is only valid for the LATEST forward
+        self._grads_live = False   # p.grad of exactly last_plan.active_params are views of the gradient arena
+        self._grads_dirty = False  # some p.grad may alias the arena (a backward ran since the last model.zero_grad())
         self._enc_index = {id(enc): j for j, (_, _, enc) in enumerate(self._all_encoders())}
         self.stats = {"plans": 0, "graph_replays": 0, "eager_runs": 0}
 
@@ -952,13 +959,20 @@ class Engine:
 
     # ------------------------------------------------------------------ plan construction
     def _key(self, shapes, training, need_grad):
+        """Everything a plan's launches depend on: engine modes, shapes, the fusion configuration and -- per encoder that
+        can run under it -- the (depth, per-layer FFN width) the drop-in `set_active` API may have set individually."""
         m = self.model
-        depth = tuple(m.trans_mems0['mems0' + ch].active_layer_num for ch in m.modality_list)
-        cross_depth = tuple(sorted({m.trans['cross' + n].active_layer_num for i in m.active_modality for n in m.active_cross[i]}))
-        self_depth = tuple(m.trans_mems['mems' + ch].active_layer_num for ch in m.modality_list)
-        ffn = m.trans_mems0['mems0' + m.modality_list[0]].layers[0].active_hidden_out_fc1 if m.layers_single_attn > 0 else 0
-        return (lib.mtb_get_gemm_mode(), tuple(shapes), training, need_grad, tuple(m.active_modality), tuple(tuple(c) for c in m.active_cross),
-                tuple(tuple(o) for o in m.active_cross_output), depth, cross_depth, self_depth, ffn)
+        names = m.modality_list
+
+        def enc_key(enc):
+            n = enc.active_layer_num
+            return (n, tuple(l.active_hidden_out_fc1 for l in enc._ll[:n]))
+        depth = tuple(enc_key(m.trans_mems0['mems0' + ch]) for ch in names)
+        cross_depth = tuple((n, enc_key(m.trans['cross' + n])) for i in m.active_modality for n in m.active_cross[i])
+        self_depth = tuple(enc_key(m.trans_mems['mems' + ch]) for ch in names)
+        return (lib.mtb_get_gemm_mode(), lib.mtb_get_attn_mode(), bool(self.prune_last_rows), bool(m.prune_dead_branches),
+                tuple(shapes), training, need_grad, tuple(m.active_modality), tuple(tuple(c) for c in m.active_cross),
+                tuple(tuple(o) for o in m.active_cross_output), depth, cross_depth, self_depth)
 
     # -- persistent layout -------------------------------------------------------------------------
     def _all_encoders(self):
@@ -976,11 +990,11 @@ class Engine:
         """bytes one invocation of `enc` allocates at full depth (forward + backward), from a dry run"""
         layers = enc._ll
         saved = [l.__dict__.get("active_hidden_out_fc1") for l in layers]
+        mode0 = lib.mtb_get_gemm_mode()
         try:
             for l in layers:
                 l.__dict__["active_hidden_out_fc1"] = l.fc1.dim_out
             peak = 0
-            mode0 = lib.mtb_get_gemm_mode()
             for mode in (0, 1):                  # the two GEMM engines allocate different scratch
                 lib.mtb_set_gemm_mode(mode)
                 ca = CountingArena()
@@ -992,9 +1006,9 @@ class Engine:
                 e.d_out = Mat(1 << 20, Lq * B, E)
                 pb.encoders_backward([e])
                 peak = max(peak, ca.peak)
-            lib.mtb_set_gemm_mode(mode0)
             return peak
         finally:
+            lib.mtb_set_gemm_mode(mode0)
             for l, v in zip(layers, saved):
                 l.__dict__["active_hidden_out_fc1"] = v
 
@@ -1152,9 +1166,13 @@ class Engine:
                                    make_mask(mask_idx, self.device), src(cb), None, True, training, need_grad)
         # The caches now hold ~10^5 long-lived ctypes objects; left in the youngest generations they make every
         # cyclic-GC pass (triggered by the per-step descriptor allocations) walk all of them: ~0.7 ms per step.
+        # gc.freeze() moves every object alive right now (the host program's too) into the permanent generation: they
+        # are never collected by the cyclic GC again (reference counting still frees them).  MTB_GC_FREEZE=0 opts out.
         import gc
-        gc.collect()
-        gc.freeze()
+        import os
+        if os.environ.get("MTB_GC_FREEZE", "1") != "0":
+            gc.collect()
+            gc.freeze()
 
     def _merge(self, lst, eps, which):
         """lock-step merge: launch `what` of every encoder of the stage goes into one grouped Op.  The finalised
@@ -1177,6 +1195,8 @@ class Engine:
                 o.finalize()
                 ops.append(o)
             ops = Batch(ops) if ops else None
+            if ops is not None:
+                ops.keep = list(eps)
             if ops is not None and which == "bwd":
                 seen_p, gp = set(), []
                 for ep in eps:
@@ -1398,6 +1418,10 @@ class Engine:
                 aps.append(p_)
         plan.sites, plan.rng_span = sites, (STEP_SPAN if training else 0)
         plan.active_params = aps
+        # The launch descriptors hold RAW device addresses of index arrays: the plan owns the Mask objects (head gather
+        # + every encoder's active_mask through its EncPlan), so evicting the mask / encoder-plan caches can never
+        # free memory a cached plan still launches with.
+        plan._keep = [hmask] + [ep for g in groups for ep in g]
         count = lambda lst: sum(len(op.arr) if type(op) is Op else op.launches if type(op) is Batch else 1 for op in lst)
         plan.n_fwd_launches, plan.n_bwd_launches = count(pb.fwd), count(pb.bwd)
         return plan
@@ -1468,6 +1492,7 @@ class Engine:
         meta = tuple((int(t.shape[0]), int(t.shape[1])) for t in px)
         plan = self.plan_for(meta, training, need_grad)
         plan.hits += 1
+        self.generation += 1
         for i, mt in plan.inputs:
             ch = m.modality_list[i]
             L, B = meta[i]
@@ -1487,6 +1512,7 @@ class _EngineFn(torch.autograd.Function):
     def forward(ctx, eng: Engine, plan: Plan, anchor, *px):
         eng._launch(plan, "fwd")
         ctx.eng, ctx.plan = eng, plan
+        ctx.gen = eng.generation
         ctx.shapes = [tuple(t.shape) for t in px]
         return plan.pred.clone()
 
@@ -1494,21 +1520,36 @@ class _EngineFn(torch.autograd.Function):
     def backward(ctx, d_pred):
         eng, plan = ctx.eng, ctx.plan
         m = eng.model
+        if ctx.gen != eng.generation:
+            raise RuntimeError(
+                "mtb200 engine: backward() of a forward pass that is no longer the engine's latest one.  All plans share one "
+                "persistent activation buffer and one dropout counter, so a later forward (a second micro-batch, a validation "
+                "or EA pass) has overwritten what this backward needs.  Call backward() before the next forward of this model, "
+                "or set model.use_engine = False for workloads that keep several graphs alive.")
         eng.last_plan = plan
+        # Gradient accumulation (a backward while earlier gradients are still attached: no zero_grad, set_to_none=False,
+        # retain_graph): earlier results that live in the arena are moved out BEFORE the arena is re-zeroed, and the
+        # new gradients are added to them afterwards -- p.grad == g_old + g_new like torch's AccumulateGrad.
+        prev = {}
+        if eng._grads_dirty:
+            for p in eng.params:
+                g = p.grad
+                if g is not None and g.data_ptr() == eng.grad_views[id(p)].data_ptr():
+                    p.grad = g.clone()
+        for p in plan.active_params:
+            if p.grad is not None:
+                prev[id(p)] = p.grad
         rs = eng.active_ranges()              # only the regions this plan exposes are (re)zeroed; see active_ranges
         if rs:
             torch._foreach_zero_([eng.grad_arena[lo:hi] for lo, hi in rs])
         plan.d_pred.copy_(d_pred)
         eng._launch(plan, "bwd")
-        live = True
         for p in plan.active_params:
             g = eng.grad_views[id(p)]
-            if p.grad is None:
-                p.grad = g
-            else:                                  # gradient accumulation over several backward passes:
-                p.grad = p.grad + g                # the sum lives outside the arena
-                live = False
-        eng._grads_live = live
+            old = prev.get(id(p))
+            p.grad = g if old is None else old + g          # an accumulated sum lives outside the arena
+        eng._grads_live = not prev
+        eng._grads_dirty = True               # some p.grad may alias the arena until zero_grad()
         outs = []
         for i, shp in enumerate(ctx.shapes):
             ch = m.modality_list[i]

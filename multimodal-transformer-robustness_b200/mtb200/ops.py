@@ -122,6 +122,9 @@ def preload():
         _preloaded = True
 
 
+GEMM_MODES = ("fp32", "tf32")
+
+
 def set_gemm_mode(mode: str) -> str:
     """'fp32' = CUDA-core parity engine, 'tf32' = tcgen05 tensor-core engine."""
     prev = lib.mtb_set_gemm_mode({"fp32": 0, "tf32": 1}[mode])

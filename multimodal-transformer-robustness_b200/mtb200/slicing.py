@@ -74,14 +74,16 @@ def _block_structure(ix: Sequence[int]):
 _mask_cache: dict = {}
 
 
-_pin_pool = []          # [pinned int32 tensor, elements used]; slices are never reused (masks are cached for good)
+_pin_pool = []          # the CURRENT pinned chunk only: [pinned int32 tensor, elements used].  Slices are views, so a full
+                        # chunk stays alive exactly as long as a Mask still references one of its slices and is returned
+                        # to the pinned allocator when the last of them dies (nothing is leaked when masks are evicted).
 
 
 def _pinned_slice(n: int) -> torch.Tensor:
-    if not _pin_pool or _pin_pool[-1][1] + n > _pin_pool[-1][0].numel():
-        _pin_pool.append([torch.empty(max(1 << 20, n), dtype=torch.int32).pin_memory(), 0])
-    buf, used = _pin_pool[-1]
-    _pin_pool[-1][1] = used + n
+    if not _pin_pool or _pin_pool[0][1] + n > _pin_pool[0][0].numel():
+        _pin_pool[:] = [[torch.empty(max(1 << 18, n), dtype=torch.int32).pin_memory(), 0]]
+    buf, used = _pin_pool[0]
+    _pin_pool[0][1] = used + n
     return buf[used:used + n]
 
 
@@ -101,6 +103,9 @@ def make_mask(indices: Sequence[int], device) -> Mask:
             m = Mask(staged.to(device, non_blocking=True), ln, segs, staged)
         else:
             m = Mask(host.to(device), ln, segs)
+        # Eviction only drops the CACHE's reference: everything that hands mask.idx.data_ptr() to a kernel (plans,
+        # encoder plans, autograd contexts) holds the Mask object itself, so device index memory is never freed
+        # under a cached launch descriptor.
         if len(_mask_cache) > 4096:
             _mask_cache.clear()
         _mask_cache[key] = m

@@ -289,12 +289,116 @@ def gen_ea(m):
                os.path.join(OUT, "ea_trace.pt"))
 
 
+# ----------------------------------------------------------------------------- 7. BASELINE dims (E=200, 8 x 25)
+REAL = dict(dims=(300, 74, 35), d=200, H=8, hd=25, layers=(3, 4, 2), names=["l", "a", "v"],
+            drops=([0.1, 0.1, 0.0, 0.0], 0.1, 0.3, 0.1, 0.3), seed=1111, proj_seed=5, affine_seed=6)
+
+
+def grad_fingerprint(g, n=257):
+    """(L2 norm, max |g|, strided sample): 61 M gradient values do not fit a fixture, their fingerprint does"""
+    if g is None:
+        return None
+    f = g.detach().reshape(-1)
+    step = max(1, f.numel() // n)
+    return dict(norm=float(f.double().norm()), absmax=float(f.abs().max()), step=step, sample=f[::step][:n].clone())
+
+
+def weight_checksums(m):
+    return {k: (float(v.double().sum()), float(v.double().abs().sum())) for k, v in m.state_dict().items()
+            if v.dtype.is_floating_point and "_float_tensor" not in k}
+
+
+def gen_real_dims():
+    """Encoder and supernet at the BASELINE.json shape (d=200, 8 heads x 25, layers single/cross/self = 3/4/2) run by the
+    UNMODIFIED reference (modules/dynamic_transformer.py:56-88, src/dynamic_models2.py:222-291).  Weights are not stored:
+    both sides rebuild them from the recipe below (constructor under `seed`, Conv1d(k=1) front-ends under `proj_seed`,
+    bias / LayerNorm perturbation under `affine_seed`) and the fixture carries per-tensor checksums, so the test also
+    pins constructor RNG parity at the real shape."""
+    import contextlib
+    import io
+    R = REAL
+    # --- encoder: cross-modal, 2 layers, ragged 9 x 14, and a masked `mems`-style stack (3 of 5 slots)
+    enc_cases = []
+    for spec in (dict(name="cross_E200", E=200, layers=2, Lq=9, Lk=14, B=2, mask=None),
+                 dict(name="mems_E1000_masked", E=1000, layers=1, Lq=7, Lk=None, B=2,
+                      mask=list(range(0, 200)) + list(range(400, 600)) + list(range(800, 1000)))):
+        torch.manual_seed(R["seed"])
+        enc = DynamicTransformerEncoder(spec["E"], R["hd"], R["H"], spec["layers"], attn_mask=True)
+        randomize_affine(enc, torch.Generator().manual_seed(R["affine_seed"]))
+        enc.set_active(spec["layers"], R["d"], R["H"], R["hd"])
+        enc.eval()
+        g = torch.Generator().manual_seed(71)
+        Ein = len(spec["mask"]) if spec["mask"] else spec["E"]
+        x = torch.randn(spec["Lq"], spec["B"], Ein, generator=g)
+        x[spec["Lq"] // 2:, 0, :] = 0.0
+        x.requires_grad_(True)
+        xk = None
+        if spec["Lk"]:
+            xk = torch.randn(spec["Lk"], spec["B"], spec["E"], generator=g)
+            xk[-3:, 1, :] = 0.0
+            xk.requires_grad_(True)
+        out = enc(x, xk, xk) if xk is not None else enc(x, active_mask=torch.tensor(spec["mask"], dtype=torch.int32))
+        Rw = torch.randn(out.shape, generator=g)
+        (out * Rw).sum().backward()
+        enc_cases.append(dict(spec=spec, checksums=weight_checksums(enc), x=x.detach().clone(),
+                              xk=None if xk is None else xk.detach().clone(), R=Rw, out=out.detach().clone(),
+                              dx=x.grad.clone(), dxk=None if xk is None else xk.grad.clone(),
+                              grads={k: grad_fingerprint(v) for k, v in grads_of(enc).items()}))
+    # --- supernet
+    torch.manual_seed(R["seed"])
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = DynamicMULTModel(origin_dimensions=list(R["dims"]), dimension=R["d"], num_heads=R["H"], head_dim=R["hd"],
+                             layers_single_attn=R["layers"][0], layers_hybrid_attn=R["layers"][1], layers_self_attn=R["layers"][2],
+                             attn_dropout=R["drops"][0], relu_dropout=R["drops"][1], res_dropout=R["drops"][2],
+                             out_dropout=R["drops"][3], embed_dropout=R["drops"][4], attn_mask=True, output_dim=1,
+                             modality_set=list(R["names"]), all_steps=False, stride=0, padding=0, kernel_size=0,
+                             experiment_type="random_sample")
+    torch.manual_seed(R["proj_seed"])
+    m.proj = nn.ModuleList([nn.Sequential(Transpose(1, 2), nn.Conv1d(R["dims"][i], R["d"], kernel_size=1, bias=False))
+                            for i in range(3)])
+    randomize_affine(m, torch.Generator().manual_seed(R["affine_seed"]))
+    g = torch.Generator().manual_seed(72)
+    B, Ls = 2, (5, 12, 12)
+    xs = [torch.randn(B, Ls[i], R["dims"][i], generator=g) for i in range(3)]
+    xs[1][0, 8:, :] = 0.0
+    xs[2][1, 10:, :] = 0.0
+    y = torch.randn(B, 1, generator=g)
+    configs = [
+        dict(name="two_level_unaligned", am=[0, 1, 2], cross=[["la", "lv"], ["av"], ["va"]],
+             outs=[["la", "lv"], ["a", "av"], ["v", "va"]], single=[3, 2, 3], train=False),
+        dict(name="three_level_unaligned", am=[0, 1, 2], cross=[["la", "lv", "lav"], ["av"], ["va", "val"]],
+             outs=[["lav", "lv"], ["a", "av"], ["val"]], single=[1, 3, 0], train=False),
+        dict(name="train_dropout_cpu_generator", am=[0, 1], cross=[["la"], ["al"], []], outs=[["la"], ["a"], []],
+             single=[2, 1, 0], train=True),
+    ]
+    cases = []
+    for c in configs:
+        m.set_active(active_self_attn_layer_num=R["layers"][2], active_single_attn_layer_num=c["single"],
+                     active_hybrid_attn_layer_num=R["layers"][1], active_dimension=R["d"], active_head_num=R["H"],
+                     active_head_dim=R["hd"], active_modality=c["am"], active_cross=c["cross"], active_cross_output=c["outs"])
+        m.train(c["train"])
+        m.zero_grad()
+        torch.manual_seed(4321)
+        pred, _ = m(xs)
+        loss = nn.L1Loss()(pred, y)
+        loss.backward()
+        cases.append(dict(cfg=c, pred=pred.detach().clone(), loss=loss.detach().clone(), dropout_seed=4321,
+                          grads={k: grad_fingerprint(v) for k, v in grads_of(m).items()}))
+    torch.save(dict(recipe=R, enc_cases=enc_cases, checksums=weight_checksums(m), xs=xs, y=y, cases=cases),
+               os.path.join(OUT, "real_dims.pt"))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "real_dims":
+        gen_real_dims()
+        print("real_dims.pt", os.path.getsize(os.path.join(OUT, "real_dims.pt")))
+        sys.exit(0)
     gen_pe_mask()
     gen_attention()
     gen_encoder()
     mm = gen_model()
     gen_sampler(mm)
     gen_ea(mm)
+    gen_real_dims()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

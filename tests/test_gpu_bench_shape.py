@@ -1,0 +1,140 @@
+"""GPU: the EXACT path bench.py times -- plan executor, training mode, Philox dropout on, tcgen05 GEMMs + tcgen05 flash
+attention -- against the CPU oracle at the bench's own shape: d=200, 8 heads x 25, layers single/cross/self = 3/4/2,
+MOSEI unaligned L=(50, 500, 500), B=16 (BASELINE.json configs[1]) and the aligned L=50 `test_single` configuration of
+configs[0].  The oracle is fed the very masks the kernels drew (replayed Philox streams), so training-mode logits and
+EVERY parameter gradient are compared, in the max-norm  max|a-b| / max|b|  per tensor:
+
+    fp32 engine           logits 1e-5 (north star), gradients 1e-4
+    tensor-core engines   logits and gradients 2e-2 (north star's reduced-precision bound)
+
+Reference semantics: src/dynamic_models2.py:222-291 (fusion DAG + head), modules/dynamic_transformer.py:56-88,159-188,
+modules/dynamic_multihead_attention.py:56-119, src/train.py:82-190 (loss / backward)."""
+import os
+import time
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import mult_oracle as O  # noqa: E402
+from engine_util import dump_report, engine_mask_provider, l2_rel, max_rel  # noqa: E402
+
+# name, L, active_modality, active_cross, active_cross_output, mems0 depths
+CASES = [
+    # one modality: mems0 stack -> masked `mems` stack (1 of 5 slots) -> head
+    ("single_modality_audio", (50, 500, 500), [1], [[], [], []], [[], ["a"], []], [2, 3, 1]),
+    # two-level fusion (the survey's legal unaligned subset): 4 cross branches, three masked `mems` stacks with 2 slots
+    ("two_level", (50, 500, 500), [0, 1, 2], [["la", "lv"], ["av"], ["va"]], [["la", "lv"], ["a", "av"], ["v", "va"]], [3, 2, 3]),
+    # three-level branches ('lav' reads 'la', 'val' reads 'va'), a depth-0 mems0 stack, ragged 50 <-> 500 attention both ways
+    ("three_level_masked_mems", (50, 500, 500), [0, 1, 2], [["la", "lv", "lav"], ["av"], ["va", "val"]],
+     [["lav", "lv"], ["a", "av"], ["val"]], [1, 3, 0]),
+    # configs[0]: aligned L=50, test_single over [[0,1,2]] = all six two-level branches
+    ("cfg1_aligned_test_single", (50, 50, 50), [0, 1, 2], [["la", "lv"], ["al", "av"], ["vl", "va"]],
+     [["la", "lv"], ["al", "av"], ["vl", "va"]], [3, 3, 3]),
+]
+TOL = {"fp32": (1e-5, 1e-4), "tf32": (2e-2, 2e-2), "bf16": (2e-2, 2e-2)}
+BASE0 = 7 << 34
+
+
+def _modes():
+    from mtb200 import ops
+    return [m for m in ("fp32", "tf32", "bf16") if m in ops.GEMM_MODES]
+
+
+@pytest.fixture(scope="module")
+def model():
+    import bench
+    from mtb200 import ops
+    ops.manual_seed(2024)
+    m = bench.build_model().cuda().train()
+    m.reset_engine()
+    return m
+
+
+def _oracle_weights(m, dtype=torch.float32):
+    w = {}
+    for k, v in m.state_dict().items():
+        if v.dtype.is_floating_point and "_float_tensor" not in k and not k.startswith("translation"):
+            w[k] = v.detach().cpu().to(dtype).clone().requires_grad_(True)
+    return w
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_benched_path_matches_oracle_at_bench_shape(model, case):
+    import bench
+    from mtb200 import ops
+    name, seq, am, cross, outs, single = case
+    m = model
+    B = 16
+    gen = torch.Generator().manual_seed(4321)
+    xs_h, y_h = bench.synth_batch(B, seq, gen)
+    xs, y = [x.cuda() for x in xs_h], y_h.cuda()
+    m.set_active(active_self_attn_layer_num=bench.LAYERS["self"], active_single_attn_layer_num=single,
+                 active_hybrid_attn_layer_num=bench.LAYERS["cross"], active_dimension=bench.D, active_head_num=bench.H,
+                 active_head_dim=bench.HD, active_modality=am, active_cross=cross, active_cross_output=outs)
+    results, sites0, ref = {}, None, None
+    report = {"case": name, "seq": seq, "batch": B, "modes": {}}
+    for mode in _modes():
+        ops.set_gemm_mode(mode)
+        eng = m.engine()
+        eng.rng_state[1] = BASE0                  # same Philox offsets in every mode: one oracle run serves all of them
+        eng.step_offset = BASE0
+        m.zero_grad()
+        pred, _ = m(xs)
+        torch.nn.functional.l1_loss(pred, y).backward()
+        torch.cuda.synchronize()
+        plan, base = eng.last_plan, eng.step_offset
+        assert plan.n_fwd_launches > 0 and eng.stats["eager_runs"] + eng.stats["graph_replays"] > 0
+        if sites0 is None:
+            sites0 = dict(plan.sites)
+            w = _oracle_weights(m)
+
+            def front(i, x, w=w):
+                return torch.einsum("bld,ed->lbe", x, w[f"proj.{i}.weight"][:, :, 0])
+            t0 = time.time()
+            torch.set_num_threads(os.cpu_count() or 1)
+            ref = O.model_forward(w, xs_h, modality_list=bench.NAMES, d=bench.D, H=bench.H, hd=bench.HD, layers_single=single,
+                                  layers_cross=bench.LAYERS["cross"], layers_self=bench.LAYERS["self"],
+                                  attn_dropout=bench.DROPS["attn"], relu_dropout=bench.DROPS["relu"], res_dropout=bench.DROPS["res"],
+                                  out_dropout=bench.DROPS["out"], embed_dropout=bench.DROPS["embed"], active_modality=am,
+                                  active_cross=cross, active_cross_output=outs,
+                                  drop=O.Drop("inject", engine_mask_provider(ops, eng, plan, base)), front_end=front, ffn=bench.D)
+            torch.nn.functional.l1_loss(ref, y_h).backward()
+            report["oracle_seconds"] = time.time() - t0
+        else:
+            assert dict(plan.sites) == sites0, "dropout sites differ between engines: the oracle run cannot be shared"
+        results[mode] = (pred.detach().cpu().clone(), {k: (None if p.grad is None else p.grad.detach().cpu().clone())
+                                                        for k, p in m.named_parameters()})
+    ops.set_gemm_mode("fp32")
+    failures = []
+    for mode, (pred, grads) in results.items():
+        tol_p, tol_g = TOL[mode]
+        e = max_rel(pred, ref)
+        rows = {"pred_max": e}
+        if not e <= tol_p:
+            failures.append(f"{mode} logits: max-norm rel err {e:.3e} > {tol_p:.0e}")
+        worst = (0.0, "")
+        n_cmp = 0
+        for k, g in grads.items():
+            if k.startswith("translation"):
+                assert g is None
+                continue
+            gr = w[k].grad
+            if gr is None:
+                assert g is None or float(g.abs().max()) == 0.0, (mode, k)
+                continue
+            if float(gr.abs().max()) == 0.0:
+                assert g is not None and float(g.abs().max()) < 1e-7, (mode, k)
+                continue
+            assert g is not None, (mode, k)
+            eg = max_rel(g, gr)
+            n_cmp += 1
+            if eg > worst[0]:
+                worst = (eg, k)
+            if not eg <= tol_g:
+                failures.append(f"{mode} grad {k}: max-norm rel err {eg:.3e} (L2 {l2_rel(g, gr):.3e}) > {tol_g:.0e}")
+        rows.update(grad_worst_max=worst[0], grad_worst_name=worst[1], grads_compared=n_cmp)
+        report["modes"][mode] = rows
+    dump_report(f"parity_bench_shape_{name}.json", report)
+    assert not failures, f"{name}: " + "; ".join(failures[:12]) + f"  [{len(failures)} failures] report={report}"

@@ -432,3 +432,60 @@ def test_engine_layout_grows_with_batch_and_flat_adam_generic_path():
     sd = opt.state_dict()
     opt.load_state_dict(sd)
     m.use_engine = True
+
+
+def test_engine_gradient_accumulation_over_two_configurations():
+    """Two backward passes without zero_grad (micro-batch accumulation, and the second one under a DIFFERENT sub-network):
+    p.grad == g_A + g_B with the None pattern of the union, against the reference's gradients (golden)."""
+    from mtb200 import ops
+    ops.set_gemm_mode("fp32")
+    G = _golden()
+    m = _build(G, use_engine=True)
+    xs = [x.cuda() for x in G["xs"]]
+    y = G["y"].cuda()
+    evals = [c for c in G["cases"] if not c["cfg"]["train"]]
+    for ca, cb in ((evals[0], evals[0]), (evals[0], evals[1]), (evals[2], evals[3])):
+        m.eval()
+        m.zero_grad()
+        for c in (ca, cb):
+            _set(m, G, c["cfg"])
+            pred, _ = m(xs)
+            torch.nn.functional.l1_loss(pred, y).backward()
+        for k, p in m.named_parameters():
+            if k.startswith("translation"):
+                continue
+            ga, gb = ca["grads"][_key(k)], cb["grads"][_key(k)]
+            if ga is None and gb is None:
+                assert p.grad is None, k
+                continue
+            want = (ga if ga is not None else torch.zeros_like(gb)) + (gb if gb is not None else torch.zeros_like(ga))
+            assert p.grad is not None, k
+            if float(want.abs().max()) == 0.0:
+                assert float(p.grad.abs().max()) < 1e-7, k
+            else:
+                assert_rel(p.grad, want, 1e-4, f"accumulated grad {k}")
+    # zero_grad(set_to_none=False) keeps zero-filled tensors attached; the next backward must still give g, not 2 g
+    m.zero_grad(set_to_none=False)
+    _set(m, G, evals[0]["cfg"])
+    pred, _ = m(xs)
+    torch.nn.functional.l1_loss(pred, y).backward()
+    for k, p in m.named_parameters():
+        g = evals[0]["grads"].get(_key(k))
+        if g is not None and float(g.abs().max()) > 0:
+            assert_rel(p.grad, g, 1e-4, f"after zero_grad(set_to_none=False): {k}")
+
+
+def test_engine_backward_of_a_stale_forward_raises():
+    """All plans share the persistent activation buffer: backward of anything but the latest forward must fail loudly."""
+    from mtb200 import ops
+    ops.set_gemm_mode("fp32")
+    G = _golden()
+    m = _build(G, use_engine=True)
+    xs = [x.cuda() for x in G["xs"]]
+    _set(m, G, G["cases"][0]["cfg"])
+    m.eval()
+    p1, _ = m(xs)
+    p2, _ = m(xs)                      # overwrites the activations p1's backward would read
+    with pytest.raises(RuntimeError, match="no longer the engine's latest"):
+        p1.sum().backward()
+    p2.sum().backward()                # the latest forward is fine

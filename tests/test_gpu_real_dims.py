@@ -1,0 +1,84 @@
+"""GPU: CUDA path vs outputs of the UNMODIFIED reference at the BASELINE shape (d=200, 8 heads x 25, layers 3/4/2),
+tests/golden/real_dims.pt -- no oracle in between.  Weights are rebuilt from the fixture's recipe (checksummed against
+the reference's).  Encoder: modules/dynamic_transformer.py:56-88; supernet: src/dynamic_models2.py:222-291."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from engine_util import (build_real_dims_encoder, build_real_dims_model, check_checksums, check_fingerprint, max_rel,  # noqa: E402
+                         ref_key)
+
+TOL = {"fp32": (2e-5, 1e-4), "tf32": (2e-2, 2e-2), "bf16": (2e-2, 2e-2)}
+
+
+def _G():
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "real_dims.pt"), weights_only=False)
+
+
+def _modes():
+    from mtb200 import ops
+    return [m for m in ("fp32", "tf32", "bf16") if m in ops.GEMM_MODES]
+
+
+def test_encoders_match_reference_at_real_dims():
+    from mtb200 import ops
+    G = _G()
+    R = G["recipe"]
+    for c in G["enc_cases"]:
+        spec = c["spec"]
+        enc = build_real_dims_encoder(R, spec)
+        check_checksums(enc, c["checksums"])
+        enc = enc.cuda().eval()
+        for mode in _modes():
+            ops.set_gemm_mode(mode)
+            tp, tg = TOL[mode]
+            enc.zero_grad()
+            x = c["x"].cuda().requires_grad_(True)
+            xk = None if c["xk"] is None else c["xk"].cuda().requires_grad_(True)
+            out = enc(x, xk, xk) if xk is not None else enc(x, active_mask=spec["mask"])
+            assert max_rel(out, c["out"]) <= tp, (spec["name"], mode, max_rel(out, c["out"]))
+            (out * c["R"].cuda()).sum().backward()
+            assert max_rel(x.grad, c["dx"]) <= tg, (spec["name"], mode, "dx", max_rel(x.grad, c["dx"]))
+            if xk is not None:
+                assert max_rel(xk.grad, c["dxk"]) <= tg, (spec["name"], mode, "dxk", max_rel(xk.grad, c["dxk"]))
+            for k, p in enc.named_parameters():
+                check_fingerprint(p.grad, c["grads"][k], tg, f"{spec['name']} {mode} {k}")
+    ops.set_gemm_mode("fp32")
+
+
+@pytest.mark.parametrize("use_engine", [True, False], ids=["plan_executor", "per_op"])
+def test_supernet_matches_reference_at_real_dims(use_engine):
+    from mtb200 import ops
+    G = _G()
+    R = G["recipe"]
+    m = build_real_dims_model(R)
+    check_checksums(m, G["checksums"])
+    m = m.cuda().eval()
+    m.use_engine = use_engine
+    xs = [x.cuda() for x in G["xs"]]
+    y = G["y"].cuda()
+    for c in G["cases"]:
+        cfg = c["cfg"]
+        if cfg["train"]:
+            continue                     # drawn from torch's CPU generator: pinned on the oracle side (test_oracle_golden.py)
+        m.set_active(active_self_attn_layer_num=R["layers"][2], active_single_attn_layer_num=cfg["single"],
+                     active_hybrid_attn_layer_num=R["layers"][1], active_dimension=R["d"], active_head_num=R["H"],
+                     active_head_dim=R["hd"], active_modality=cfg["am"], active_cross=cfg["cross"], active_cross_output=cfg["outs"])
+        for mode in _modes():
+            ops.set_gemm_mode(mode)
+            tp, tg = TOL[mode]
+            m.zero_grad()
+            pred, _ = m(xs)
+            e = max_rel(pred, c["pred"])
+            assert e <= tp, (cfg["name"], mode, e)
+            torch.nn.functional.l1_loss(pred, y).backward()
+            for k, p in m.named_parameters():
+                fp = c["grads"][ref_key(k)]
+                if k.startswith("translation"):
+                    assert p.grad is None and fp is None
+                    continue
+                check_fingerprint(p.grad, fp, tg, f"{cfg['name']} {mode} {k}")
+    ops.set_gemm_mode("fp32")

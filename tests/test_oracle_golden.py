@@ -166,3 +166,56 @@ def test_sampler_bit_exact(golden):
 
 def test_perm_counts():
     assert [O.perm_count_sum(n) for n in (1, 2, 3, 4)] == [1, 4, 15, 64]
+
+
+def test_real_dims_fixture_pins_oracle_and_constructor(golden):
+    """tests/golden/real_dims.pt: the UNMODIFIED reference at the BASELINE shape (d=200, 8 heads x 25, layers 3/4/2).
+    (1) the product's constructors rebuild the reference's weights bit-for-bit from the recipe (per-tensor checksums);
+    (2) the oracle reproduces the reference's logits and the fingerprint of every parameter gradient, the train-mode
+    case bit-pinned through the shared CPU generator."""
+    from engine_util import build_real_dims_encoder, build_real_dims_model, check_checksums, check_fingerprint, ref_key
+    G = golden("real_dims.pt")
+    R = G["recipe"]
+    for c in G["enc_cases"]:
+        spec = c["spec"]
+        enc = build_real_dims_encoder(R, spec)
+        check_checksums(enc, c["checksums"])
+        w = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in enc.state_dict().items()}
+        x = c["x"].clone().requires_grad_(True)
+        xk = None if c["xk"] is None else c["xk"].clone().requires_grad_(True)
+        mask = torch.tensor(spec["mask"], dtype=torch.int64) if spec["mask"] else None
+        out = O.encoder(w, "", x, xk, xk, embed_dim=spec["E"], H=R["H"], hd=R["hd"], n_layers=spec["layers"], ffn=R["d"], mask=mask)
+        torch.testing.assert_close(out, c["out"], rtol=1e-4, atol=1e-5)
+        (out * c["R"]).sum().backward()
+        torch.testing.assert_close(x.grad, c["dx"], rtol=1e-4, atol=2e-5)
+        if xk is not None:
+            torch.testing.assert_close(xk.grad, c["dxk"], rtol=1e-4, atol=2e-5)
+        for k, fp in c["grads"].items():
+            check_fingerprint(w[k].grad, fp, 1e-4, f"{spec['name']} {k}")
+    m = build_real_dims_model(R)
+    check_checksums(m, G["checksums"])
+    sd = {ref_key(k): v for k, v in m.state_dict().items()}
+    for c in G["cases"]:
+        cfg = c["cfg"]
+        w = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+             if v.dtype.is_floating_point and "_float_tensor" not in k and not k.startswith("translation")}
+
+        def front(i, x, w=w):
+            return torch.einsum("bld,ed->bel", x, w[f"proj.{i}.1.weight"][:, :, 0]).contiguous().permute(2, 0, 1)
+        if cfg["train"]:
+            torch.manual_seed(c["dropout_seed"])
+            drop = O.Drop("torch")
+        else:
+            drop = O.NO_DROP
+        pred = O.model_forward(w, G["xs"], modality_list=R["names"], d=R["d"], H=R["H"], hd=R["hd"], layers_single=cfg["single"],
+                               layers_cross=R["layers"][1], layers_self=R["layers"][2], attn_dropout=R["drops"][0],
+                               relu_dropout=R["drops"][1], res_dropout=R["drops"][2], out_dropout=R["drops"][3],
+                               embed_dropout=R["drops"][4], active_modality=cfg["am"], active_cross=cfg["cross"],
+                               active_cross_output=cfg["outs"], drop=drop, front_end=front, ffn=R["d"])
+        torch.testing.assert_close(pred, c["pred"], rtol=1e-4, atol=1e-5, msg=lambda s, n=cfg["name"]: f"{n}: {s}")
+        torch.nn.functional.l1_loss(pred, G["y"]).backward()
+        for k, fp in c["grads"].items():
+            if k.startswith("translation"):
+                assert fp is None
+                continue
+            check_fingerprint(w[k].grad, fp, 2e-4, f"{cfg['name']} {k}")
