@@ -183,6 +183,14 @@ class DynamicMULTModel(nn.Module):
         state.pop("_outside_cache", None)
         return state
 
+    def __setstate__(self, state):
+        """also the entry point of reference-written checkpoints (mtb200.compat): back-fill what the reference lacks"""
+        super().__setstate__(state)
+        d = self.__dict__
+        d.setdefault("prune_dead_branches", True)
+        d.setdefault("use_engine", True)
+        d["_engine"] = None
+
     # ------------------------------------------------------------------ plan-executor path
     def reset_engine(self):
         self._engine = None

@@ -79,6 +79,10 @@ class EvolutionSearch:
         return new_sample, 0
 
     # ------------------------------------------------------------------ fitness
+    def reset_memo(self):
+        """drop the memoised branch outputs (new weights or new validation data)"""
+        self._caches.clear()
+
     def _replay_loader_draw(self):
         torch.empty((), dtype=torch.int64).random_()      # the DataLoader-iterator draw of EA.py:157
 

@@ -142,6 +142,28 @@ def get_gemm_mode() -> str:
     return "tf32" if lib.mtb_get_gemm_mode() else "fp32"
 
 
+# -- bench.py's isolated-kernel roofline probe: the GEMM of the given engine on its native operand types
+def gemm_elem_size(mode: str) -> int:
+    return 4
+
+
+def bench_operand(x: Tensor, mode: str) -> Tensor:
+    return x
+
+
+def bench_linear(x: Tensor, W: Tensor, b: Optional[Tensor], mode: str):
+    """closure launching Y = X W^T + b once on the current stream with engine ``mode``"""
+    N, K = W.shape
+
+    def fn():
+        prev = set_gemm_mode(mode)
+        try:
+            return linear(x, W, b, N=N, K=K)
+        finally:
+            set_gemm_mode(prev)
+    return fn
+
+
 # ----------------------------------------------------------------------------- embed
 class _Embed(torch.autograd.Function):
     @staticmethod

@@ -1,6 +1,9 @@
 """Import shims that let the UNMODIFIED reference (/root/reference or a private
-copy under baseline/_ref/) import in this image.  TEST INFRASTRUCTURE ONLY -- used
-by oracle/gen_golden.py (build container) and baseline/measure_reference.py.
+copy under baseline/_ref/) import in this image.  Standalone: imports neither mtb200 nor
+the kernels' library, so the reference arm of bench.py can use it without loading any
+product code.  Users: INTEGRATION.md (binding a reference checkout to the product's
+`modules` package), baseline/ref_harness.py (reference arm / CPU baseline),
+oracle/gen_golden.py (fixtures, build container), tools/verify_dropin.py.
 
 Why each stub exists:
   matplotlib*            imported at module scope by modules/dynamic_multihead_attention.py:295-297
@@ -70,8 +73,7 @@ def install(ref_root: str | None = None, use_product_modules: bool = False) -> s
 
     transformers.BertModel = _DummyBert
     if use_product_modules:
-        prod = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                            "multimodal-transformer-robustness_b200")
+        prod = os.path.dirname(os.path.abspath(__file__))
         sys.path.insert(0, prod)
         sys.path.insert(1, ref_root)
     else:

@@ -15,8 +15,12 @@ import os
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, HERE)
-import ref_shims  # noqa: E402
+import importlib.util  # noqa: E402
+
+_spec = importlib.util.spec_from_file_location(
+    "ref_shims", os.path.join(os.path.dirname(HERE), "multimodal-transformer-robustness_b200", "ref_shims.py"))
+ref_shims = importlib.util.module_from_spec(_spec)      # loaded by path: the product package must NOT shadow the reference's `modules`
+_spec.loader.exec_module(ref_shims)
 
 ref_shims.install()
 
@@ -388,7 +392,59 @@ def gen_real_dims():
                os.path.join(OUT, "real_dims.pt"))
 
 
+# ----------------------------------------------------------------------------- 8. whole-model checkpoint
+def gen_checkpoint():
+    """src/train.py:508-511: `torch.save(model, path)` of the reference's own model object (GRU front-ends as at HEAD),
+    plus its eval-mode prediction on seeded inputs -- what a checkpoint reader (EA.py:264) must reproduce."""
+    import contextlib
+    import io
+    torch.manual_seed(50)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = DynamicMULTModel(origin_dimensions=[6, 5, 4], dimension=8, num_heads=2, head_dim=4, layers_single_attn=2,
+                             layers_hybrid_attn=2, layers_self_attn=1, attn_dropout=[0.1, 0.1, 0.0, 0.0], relu_dropout=0.1,
+                             res_dropout=0.3, out_dropout=0.1, embed_dropout=0.3, attn_mask=True, output_dim=1,
+                             modality_set=["l", "a", "v"], all_steps=False, stride=0, padding=0, kernel_size=0,
+                             experiment_type="random_sample")
+    randomize_affine(m, torch.Generator().manual_seed(51))
+    cfg = dict(am=[0, 1, 2], cross=[["la", "lav"], ["av"], ["vl"]], outs=[["l", "lav"], ["a", "av"], ["vl"]], single=[2, 1, 2])
+    m.set_active(active_self_attn_layer_num=1, active_single_attn_layer_num=cfg["single"], active_hybrid_attn_layer_num=2,
+                 active_dimension=8, active_head_num=2, active_head_dim=4, active_modality=cfg["am"], active_cross=cfg["cross"],
+                 active_cross_output=cfg["outs"])
+    m.eval()
+    g = torch.Generator().manual_seed(52)
+    xs = [torch.randn(3, 7, d, generator=g) for d in (6, 5, 4)]
+    with torch.no_grad():
+        pred, _ = m(xs)
+    buf = io.BytesIO()
+    torch.save(m, buf)                                   # the reference's checkpoint format: the pickled object
+    torch.save(dict(pickle=buf.getvalue(), state_dict=sd(m), cfg=cfg, xs=xs, pred=pred.clone()),
+               os.path.join(OUT, "ref_checkpoint.pt"))
+
+
+def check_export(path):
+    """container-only check (needs the reference): a checkpoint written by mtb200.compat.save_reference_checkpoint loads
+    into the UNMODIFIED reference classes with torch.load (EA.py:264) and carries the same weights"""
+    blob = torch.load(path, weights_only=False)
+    m = torch.load(blob["file"], weights_only=False)
+    assert type(m).__module__ == "src.dynamic_models2" and "reference" in sys.modules[type(m).__module__].__file__
+    ref_sd = m.state_dict()
+    for k, v in blob["state_dict"].items():
+        assert torch.equal(ref_sd[k], v), k
+    m.eval()
+    with torch.no_grad():
+        pred, _ = m(blob["xs"])          # runs in the reference's own eager code
+    print("export check ok:", type(m), "pred", pred.flatten().tolist())
+    return pred
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "check_export":
+        check_export(sys.argv[2])
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "checkpoint":
+        gen_checkpoint()
+        print("ref_checkpoint.pt", os.path.getsize(os.path.join(OUT, "ref_checkpoint.pt")))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "real_dims":
         gen_real_dims()
         print("real_dims.pt", os.path.getsize(os.path.join(OUT, "real_dims.pt")))
@@ -400,5 +456,6 @@ if __name__ == "__main__":
     gen_sampler(mm)
     gen_ea(mm)
     gen_real_dims()
+    gen_checkpoint()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

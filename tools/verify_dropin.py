@@ -6,7 +6,7 @@ git-ignored copy baseline/_ref or /root/reference) trains for one epoch on CUDA 
 import argparse, contextlib, io, os, sys, tempfile, types
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "multimodal-transformer-robustness_b200"))
 import ref_shims
 
 ap = argparse.ArgumentParser()
