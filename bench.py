@@ -364,8 +364,9 @@ def ea_throughput(args, model, dev, world, rank):
     import torch
     import torch.distributed as dist
     from mtb200.ea import EvolutionSearch
-    was_training = model.training
+    was_training, was_engine = model.training, model.use_engine
     model.eval()
+    model.use_engine = False          # EA fitness runs on the per-op path (inference at B=2048; branch memoisation)
     gen = torch.Generator().manual_seed(1)
     seq = (50, 50, 50)
     xs, y = synth_batch(args.ea_valid, seq, gen)
@@ -404,6 +405,7 @@ def ea_throughput(args, model, dev, world, rank):
         out["memo" if memo else "nomemo"] = (n_eval / sec, sec, n_eval, float(sum(scores)))
         ea.reset_memo()
     model.train(was_training)
+    model.use_engine = was_engine
     v, sec, n, chk = out["memo"]
     return {"metric": "ea_subnets_evaluated_per_s", "value": v, "unit": "subnets/s", "population": n, "valid": args.ea_valid,
             "seq": list(seq), "memoize": True, "n_gpus": world, "seconds": sec, "score_checksum": chk,

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MTB_ABI_VERSION 13
+#define MTB_ABI_VERSION 14
 #define MTB_MAX_GROUP 24
 
 /* Dropout RNG: Philox4x32-7.  Element `i` of a dropout site is kept iff
@@ -46,7 +46,9 @@ int mtb_abi_version(void);
 const char* mtb_last_error(void);
 int mtb_sm_count(void);
 /* which GEMM engine mtb_linear_* uses: 0 = fp32 CUDA-core (parity mode, 1e-5),
- * 1 = tcgen05 TF32 tensor-core (TMA + TMEM).  Returns the previous mode. */
+ * 1 = tcgen05 TF32 tensor-core (TMA + TMEM), 2 = the same engine for callers that keep activations in bf16: problems
+ * flagged in_bf16 / out_bf16 run tcgen05.mma.kind::f16 on bf16 operands, unflagged ones run as in mode 1.
+ * Returns the previous mode. */
 int mtb_set_gemm_mode(int mode);
 int mtb_get_gemm_mode(void);
 /* which attention core mtb_attn_* uses: 0 = fp32 CUDA-core flash kernels, 1 = tcgen05 / TMEM flash
@@ -88,6 +90,7 @@ typedef struct {
   const float* src[3]; int64_t ld_src[3]; int n_src;
   float* dst; int64_t ld_dst;
   int T, E; int accumulate;
+  int src_bf16[3]; int dst_bf16;   /* bf16 data path: that operand is bfloat16 (sums are formed in fp32; doubles as the cast op) */
 } mtb_addn_desc;
 int mtb_addn(const mtb_addn_desc* d, int n, void* stream);
 
@@ -106,6 +109,8 @@ typedef struct {
   float* mean; float* rstd;
   int T, E;
   float eps; float p; mtb_rng rng;
+  int a_bf16, y_bf16;   /* bf16 data path: `a` (a GEMM output) / `y` (a GEMM input) are bfloat16; the residual stream
+                           (res, x_new) and the statistics always stay fp32, like autocast's LayerNorm */
 } mtb_resln_desc;
 int mtb_resln_fwd(const mtb_resln_desc* d, int n, void* stream);
 
@@ -127,6 +132,7 @@ typedef struct {
   float p; mtb_rng rng;
   float* dbias;    /* optional: dbias[idx[c]] += sum_t d_a[t, c] -- the bias gradient of the linear layer that
                       produced `a` (out-projection / fc2), fused here so no separate column-sum pass is needed */
+  int dy_bf16, da_bf16;   /* bf16 data path: dy (a dgrad GEMM output) / d_a (a GEMM input) are bfloat16 */
 } mtb_resln_bwd_desc;
 int mtb_resln_bwd(const mtb_resln_bwd_desc* d, int n, void* stream);
 
@@ -155,6 +161,10 @@ typedef struct {
   int M, N, K;
   int act; float p; mtb_rng rng;
   mtb_segs row_segs, col_segs;
+  /* bf16 data path (tensor-core engine only, gemm mode 2): in_bf16 -- X and W point to bfloat16 data (W: the bf16 shadow
+   * of the fp32 master weight, same shape and leading dimension in ELEMENTS); out_bf16 -- Y is bfloat16.  Accumulation,
+   * bias, ReLU and dropout stay fp32; the result is rounded to nearest even once.  bias is always fp32. */
+  int in_bf16, out_bf16;
 } mtb_linear_desc;
 int mtb_linear_fwd(const mtb_linear_desc* d, int n, void* stream);
 
@@ -176,6 +186,9 @@ typedef struct {
   int act; float p;
   float* scratch;   /* [M*N] floats, required by the tensor-core engine when act == 1 (holds dY') */
   mtb_segs row_segs, col_segs;
+  /* bf16 data path: in_bf16 -- dY, Yact, X, W and scratch are bfloat16; dx_bf16 -- dX is bfloat16.  dW / db are ALWAYS
+   * fp32 (accumulated into the fp32 gradient arena, like autocast's weight gradients after the cast back). */
+  int in_bf16, dx_bf16;
 } mtb_linear_bwd_desc;
 int mtb_linear_bwd(const mtb_linear_bwd_desc* d, int n, void* stream);
 
@@ -199,6 +212,7 @@ typedef struct {
    * computed (bit j%32 of word j/32 of row (b*H+h)*Lq + i); the backward kernels read them instead of re-drawing the
    * Philox stream twice.  NULL: not stored / re-drawn.  Tensor-core engine only (the fp32 engine ignores it). */
   uint32_t* keep_bits;
+  int bf16;   /* bf16 data path (tensor-core engine only): q, k, v, o are bfloat16; scores, softmax, lse stay fp32 */
 } mtb_attn_desc;
 int mtb_attn_fwd(const mtb_attn_desc* d, int n, void* stream);
 
@@ -216,6 +230,7 @@ typedef struct {
   int Lq, Lk, B, H, hd;
   float scale; float p; mtb_rng rng;
   const uint32_t* keep_bits;   /* optional: the words the forward kernel stored (see mtb_attn_desc) */
+  int bf16;   /* bf16 data path: q, k, v, o, d_o, dq, dk, dv are bfloat16; lse / delta stay fp32 */
 } mtb_attn_bwd_desc;
 int mtb_attn_bwd(const mtb_attn_bwd_desc* d, int n, void* stream);
 
@@ -262,6 +277,8 @@ typedef struct {
   float* scalars;                /* out [2] */
   int n_chunks, n_params;
   float lr, beta1, beta2, eps, weight_decay, max_norm;
+  uint16_t* shadow;              /* optional bf16 shadow arena (same offsets as grad): shadow[off + i] = bf16(param[i]) is
+                                    rewritten for every updated element, so the bf16 data path needs no separate cast pass */
 } mtb_adam_desc;
 int mtb_adam_step(const mtb_adam_desc* d, void* stream);
 

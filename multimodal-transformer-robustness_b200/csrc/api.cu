@@ -58,7 +58,7 @@ const char* mtb_last_error(void) { return mtb::g_err; }
 int mtb_sm_count(void) { return mtb::sm_count(); }
 int mtb_set_gemm_mode(int mode) {
   const int prev = mtb::g_gemm_mode;
-  mtb::g_gemm_mode = mode ? 1 : 0;
+  mtb::g_gemm_mode = mode <= 0 ? 0 : (mode >= 2 ? 2 : 1);
   return prev;
 }
 int mtb_get_gemm_mode(void) { return mtb::g_gemm_mode; }
@@ -83,7 +83,7 @@ int mtb_linear_fwd(const mtb_linear_desc* d, int n, void* stream) {
     MTB_CHECK(d[i].M >= 0 && d[i].N >= 0 && d[i].K >= 0, "linear_fwd: negative size in problem %d", i);
     MTB_CHECK(d[i].act == 0 || d[i].act == 1, "linear_fwd: unknown activation %d", d[i].act);
   }
-  if (mtb::g_gemm_mode == 1) return mtb::linear_fwd_tc(d, n, (cudaStream_t)stream);
+  if (mtb::g_gemm_mode >= 1) return mtb::linear_fwd_tc(d, n, (cudaStream_t)stream);
   return mtb::linear_fwd_simt(d, n, (cudaStream_t)stream);
 }
 
@@ -91,12 +91,12 @@ int mtb_linear_bwd(const mtb_linear_bwd_desc* d, int n, void* stream) {
   MTB_CHECK(n >= 1 && n <= MTB_MAX_GROUP, "linear_bwd: group size %d out of range", n);
   for (int i = 0; i < n; ++i) {
     MTB_CHECK(d[i].dY && d[i].W, "linear_bwd: null operand in problem %d", i);
-    MTB_CHECK(!d[i].db || d[i].dW || mtb::g_gemm_mode == 1,
+    MTB_CHECK(!d[i].db || d[i].dW || mtb::g_gemm_mode >= 1,
               "linear_bwd: the fp32 engine computes the bias gradient inside the weight-gradient GEMM (problem %d)", i);
     MTB_CHECK(!d[i].dW || d[i].X, "linear_bwd: weight gradient needs the forward input (problem %d)", i);
     MTB_CHECK(d[i].act == 0 || d[i].Yact, "linear_bwd: act=1 needs the forward output (problem %d)", i);
   }
-  if (mtb::g_gemm_mode == 1) return mtb::linear_bwd_tc(d, n, (cudaStream_t)stream);
+  if (mtb::g_gemm_mode >= 1) return mtb::linear_bwd_tc(d, n, (cudaStream_t)stream);
   return mtb::linear_bwd_simt(d, n, (cudaStream_t)stream);
 }
 
@@ -105,7 +105,7 @@ int mtb_attn_fwd(const mtb_attn_desc* d, int n, void* stream) {
   for (int i = 0; i < n; ++i)
     MTB_CHECK(d[i].q && d[i].k && d[i].v && d[i].o && d[i].Lq > 0 && d[i].Lk > 0 && d[i].hd > 0,
               "attn_fwd: bad problem %d", i);
-  if (mtb::g_attn_mode == 1 || (mtb::g_attn_mode < 0 && mtb::g_gemm_mode == 1)) return mtb::attn_fwd_tc(d, n, (cudaStream_t)stream);
+  if (mtb::g_attn_mode == 1 || (mtb::g_attn_mode < 0 && mtb::g_gemm_mode >= 1)) return mtb::attn_fwd_tc(d, n, (cudaStream_t)stream);
   return mtb::attn_fwd_simt(d, n, (cudaStream_t)stream);
 }
 
@@ -114,7 +114,7 @@ int mtb_attn_bwd(const mtb_attn_bwd_desc* d, int n, void* stream) {
   for (int i = 0; i < n; ++i)
     MTB_CHECK(d[i].q && d[i].k && d[i].v && d[i].o && d[i].d_o && d[i].lse && d[i].delta && d[i].dq && d[i].dk && d[i].dv,
               "attn_bwd: null operand in problem %d", i);
-  if (mtb::g_attn_mode == 1 || (mtb::g_attn_mode < 0 && mtb::g_gemm_mode == 1)) return mtb::attn_bwd_tc(d, n, (cudaStream_t)stream);
+  if (mtb::g_attn_mode == 1 || (mtb::g_attn_mode < 0 && mtb::g_gemm_mode >= 1)) return mtb::attn_bwd_tc(d, n, (cudaStream_t)stream);
   return mtb::attn_bwd_simt(d, n, (cudaStream_t)stream);
 }
 

@@ -446,7 +446,7 @@ int attn_fwd_simt(const mtb_attn_desc* d, int n, cudaStream_t st) {
   g.start[n] = tot;
   if (tot == 0) return 0;
   MTB_CHECK(maxhd <= 64, "attention: head_dim %d > 64 not supported", maxhd);
-  if (g_gemm_mode == 1) return maxhd <= 32 ? launch_fwd<32, true>(g, tot, st) : launch_fwd<64, true>(g, tot, st);
+  if (g_gemm_mode >= 1) return maxhd <= 32 ? launch_fwd<32, true>(g, tot, st) : launch_fwd<64, true>(g, tot, st);
   return maxhd <= 32 ? launch_fwd<32, false>(g, tot, st) : launch_fwd<64, false>(g, tot, st);
 }
 
@@ -464,7 +464,7 @@ int attn_bwd_simt(const mtb_attn_bwd_desc* d, int n, cudaStream_t st) {
   gq.start[n] = totq; gk.start[n] = totk;
   if (totq == 0 || totk == 0) return 0;
   MTB_CHECK(maxhd <= 64, "attention: head_dim %d > 64 not supported", maxhd);
-  if (g_gemm_mode == 1) return maxhd <= 32 ? launch_bwd<32, true>(gq, totq, gk, totk, st) : launch_bwd<64, true>(gq, totq, gk, totk, st);
+  if (g_gemm_mode >= 1) return maxhd <= 32 ? launch_bwd<32, true>(gq, totq, gk, totk, st) : launch_bwd<64, true>(gq, totq, gk, totk, st);
   return maxhd <= 32 ? launch_bwd<32, false>(gq, totq, gk, totk, st) : launch_bwd<64, false>(gq, totq, gk, totk, st);
 }
 

@@ -133,20 +133,39 @@ __device__ __forceinline__ int a_round4(int x) { return (x + 3) & ~3; }
 // source offset are computed once; each copy is then a compare, a select and a cp.async.
 template <bool MNSW>
 __device__ __forceinline__ void stage_rows256(uint8_t* tile, const float* base, int64_t ld, int B, int b, int h, int hd, int l0, int L,
-                                              int rows) {
+                                              int rows, bool bf = false) {
   const int c = threadIdx.x & 31, r0 = threadIdx.x >> 5;
   const bool ok_c = c < hd;
-  const float* src = base + ((int64_t)(l0 + r0) * B + b) * ld + h * hd + c;
-  const int64_t sstep = (int64_t)8 * B * ld;
   uint32_t dst = a_smem_u32(tile) + (MNSW ? swz128_32(r0, c * 4) : swz128(r0, c * 4));
+  if (!bf) {
+    const float* src = base + ((int64_t)(l0 + r0) * B + b) * ld + h * hd + c;
+    const int64_t sstep = (int64_t)8 * B * ld;
 #pragma unroll 4
-  for (int r = r0; r < rows; r += 8) {
-    const bool ok = ok_c && (l0 + r < L);
-    const float* sp = ok ? src : base;
-    const int nbytes = ok ? 4 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(sp), "r"(nbytes) : "memory");
-    src += sstep;
-    dst += 8 * 128;
+    for (int r = r0; r < rows; r += 8) {
+      const bool ok = ok_c && (l0 + r < L);
+      const float* sp = ok ? src : base;
+      const int nbytes = ok ? 4 : 0;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(sp), "r"(nbytes) : "memory");
+      src += sstep;
+      dst += 8 * 128;
+    }
+  } else {
+    // bf16 activations (bf16 data path): rows are 2 * hd bytes at 2-byte aligned offsets, below cp.async's 4-byte
+    // granularity -- each element is loaded through a register, widened to fp32 (exact: a 16-bit shift; a bf16 value is
+    // also a valid tf32 operand) and stored into the same swizzled slot.  The loads of one call are independent and
+    // issued back to back (one L2 latency per tile).
+    const uint16_t* base16 = reinterpret_cast<const uint16_t*>(base);
+    const uint16_t* src = base16 + ((int64_t)(l0 + r0) * B + b) * ld + h * hd + c;
+    const int64_t sstep = (int64_t)8 * B * ld;
+#pragma unroll 8
+    for (int r = r0; r < rows; r += 8) {
+      const bool ok = ok_c && (l0 + r < L);
+      uint32_t v = 0;
+      if (ok) v = (uint32_t)__ldg(src) << 16;
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(v) : "memory");
+      src += sstep;
+      dst += 8 * 128;
+    }
   }
 }
 __device__ __forceinline__ void a_tmem_ld16(uint32_t taddr, float (&v)[16]) {
@@ -258,6 +277,7 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
   const int off = abs(Lk - Lq);
   const int Lk4 = a_round4(Lk);
   const DropCtx dc = make_drop(d.rng, d.p);
+  const bool bf = d.bf16 != 0;                      // q / k / v / o are bfloat16 in HBM
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, half = warp >> 2;
   const int row = quad * 32 + lane;                 // query row inside the tile = TMEM lane
@@ -279,9 +299,9 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
   const int i_last = min(Lq, i0 + TQ) - 1;
   const int j_end = min(Lk, i_last + off + 1);
   const int T = (j_end + TK - 1) / TK;
-  stage_rows256<false>(Qs, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TQ);
-  stage_rows256<false>(KV, d.k, d.ldk, d.B, b, h, hd, 0, Lk, TK);
-  stage_rows256<true>(KV + TK * 128, d.v, d.ldv, d.B, b, h, hd, 0, Lk, TK);
+  stage_rows256<false>(Qs, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TQ, bf);
+  stage_rows256<false>(KV, d.k, d.ldk, d.B, b, h, hd, 0, Lk, TK, bf);
+  stage_rows256<true>(KV + TK * 128, d.v, d.ldv, d.B, b, h, hd, 0, Lk, TK, bf);
   stage_wait();
   fence_async_smem();
   tc_fence_before();
@@ -322,8 +342,8 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
     uint8_t* nxt = KV + ((t + 1) & 1) * (2 * TK * 128);
     ATRACE(8 + t * 8 + 0);
     if (t + 1 < T) {                         // prefetch the next key / value tile behind this tile's softmax
-      stage_rows256<false>(nxt, d.k, d.ldk, d.B, b, h, hd, j0 + TK, Lk, TK);
-      stage_rows256<true>(nxt + TK * 128, d.v, d.ldv, d.B, b, h, hd, j0 + TK, Lk, TK);
+      stage_rows256<false>(nxt, d.k, d.ldk, d.B, b, h, hd, j0 + TK, Lk, TK, bf);
+      stage_rows256<true>(nxt + TK * 128, d.v, d.ldv, d.B, b, h, hd, j0 + TK, Lk, TK, bf);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     ATRACE(8 + t * 8 + 1);
@@ -389,10 +409,10 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
     const float wa = fast_exp2(m_run - m), wb = fast_exp2(m_b - m);
     const float l = l_run * wa + l_b * wb;
     const float inv = 1.f / l;
-    float* op = d.o + ((int64_t)i * d.B + b) * d.ldo + h * hd;
+    const int64_t oo = ((int64_t)i * d.B + b) * d.ldo + h * hd;
 #pragma unroll
     for (int c = 0; c < HP; ++c)
-      if (c < hd) op[c] = (o[c] * wa + e[4 + c] * wb) * inv;
+      if (c < hd) st1_any(d.o, oo + c, (o[c] * wa + e[4 + c] * wb) * inv, bf);
     if (d.lse) d.lse[(int64_t)bh * Lq + i] = m * 0.6931471805599453f + logf(l);
   }
   tc_fence_before();
@@ -452,6 +472,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
   const int off = abs(Lk - Lq);
   const int Lk4 = a_round4(Lk);
   const DropCtx dc = make_drop(d.rng, d.p);
+  const bool bf = d.bf16 != 0;                      // q / k / v / o / d_o / dq are bfloat16 in HBM
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, half = warp >> 2;
   const int row = quad * 32 + lane;
@@ -473,18 +494,17 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(&tmem_slot)), "r"(ATC_DQ_TMEM) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  stage_rows256<false>(Qs, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TQ);
-  stage_rows256<false>(dOs, d.d_o, d.lddo, d.B, b, h, hd, i0, Lq, TQ);
-  stage_rows256<false>(Ks, d.k, d.ldk, d.B, b, h, hd, 0, Lk, TK);
-  stage_rows256<false>(Vs, d.v, d.ldv, d.B, b, h, hd, 0, Lk, TK);
-  stage_rows256<true>(Kmn, d.k, d.ldk, d.B, b, h, hd, 0, Lk, TK);
+  stage_rows256<false>(Qs, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TQ, bf);
+  stage_rows256<false>(dOs, d.d_o, d.lddo, d.B, b, h, hd, i0, Lq, TQ, bf);
+  stage_rows256<false>(Ks, d.k, d.ldk, d.B, b, h, hd, 0, Lk, TK, bf);
+  stage_rows256<false>(Vs, d.v, d.ldv, d.B, b, h, hd, 0, Lk, TK, bf);
+  stage_rows256<true>(Kmn, d.k, d.ldk, d.B, b, h, hd, 0, Lk, TK, bf);
   const int i = i0 + row;
   const int irow = min(i, Lq - 1);
   float delta = 0.f, lse2 = 0.f;
   if (i < Lq) {
-    const float* op = d.o + ((int64_t)i * d.B + b) * d.ldo + h * hd;
-    const float* gp = d.d_o + ((int64_t)i * d.B + b) * d.lddo + h * hd;
-    for (int c = 0; c < hd; ++c) delta = fmaf(op[c], gp[c], delta);
+    const int64_t oo = ((int64_t)i * d.B + b) * d.ldo + h * hd, og = ((int64_t)i * d.B + b) * d.lddo + h * hd;
+    for (int c = 0; c < hd; ++c) delta = fmaf(ld1_any(d.o, oo + c, bf), ld1_any(d.d_o, og + c, bf), delta);
     lse2 = d.lse[(int64_t)bh * Lq + i] * 1.4426950408889634f;
     if (half == 0) d.delta[(int64_t)bh * Lq + i] = delta;
   }
@@ -528,9 +548,9 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
     QTRACE(8 + t * 8 + 1);
     tc_fence_after();
     if (t + 1 < T) {
-      stage_rows256<false>(Ks, d.k, d.ldk, d.B, b, h, hd, j0 + TK, Lk, TK);
-      stage_rows256<false>(Vs, d.v, d.ldv, d.B, b, h, hd, j0 + TK, Lk, TK);
-      stage_rows256<true>(Kmn + ((t + 1) & 1) * (TK * 128), d.k, d.ldk, d.B, b, h, hd, j0 + TK, Lk, TK);
+      stage_rows256<false>(Ks, d.k, d.ldk, d.B, b, h, hd, j0 + TK, Lk, TK, bf);
+      stage_rows256<false>(Vs, d.v, d.ldv, d.B, b, h, hd, j0 + TK, Lk, TK, bf);
+      stage_rows256<true>(Kmn + ((t + 1) & 1) * (TK * 128), d.k, d.ldk, d.B, b, h, hd, j0 + TK, Lk, TK, bf);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     uint32_t kbits_next = 0u;                  // stored keep bits of the next tile: loaded now, used one iteration later
@@ -574,10 +594,10 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
     float dq[16];
     a_tmem_ld16(t_dq + lane_addr + half * 16, dq);
     if (i < Lq) {
-      float* qp = d.dq + ((int64_t)i * d.B + b) * d.lddq + h * hd + half * 16;
+      const int64_t qo = ((int64_t)i * d.B + b) * d.lddq + h * hd + half * 16;
 #pragma unroll
       for (int c = 0; c < 16; ++c)
-        if (half * 16 + c < hd) qp[c] = dq[c];
+        if (half * 16 + c < hd) st1_any(d.dq, qo + c, dq[c], bf);
     }
   }
   tc_fence_before();
@@ -673,6 +693,7 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
   const int off = abs(Lk - Lq);
   const int Lk4 = a_round4(Lk);
   const DropCtx dc = make_drop(d.rng, d.p);
+  const bool bf = d.bf16 != 0;                      // q / k / v / d_o / dk / dv are bfloat16 in HBM
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, half = warp >> 2;
   const int row = quad * 32 + lane;                 // key row inside the tile = TMEM lane
@@ -700,18 +721,18 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
   auto stage_q = [&](int t) {                 // operand tiles + per-query-row lse / delta of query tile t
     uint8_t* qb = QB + (t & 1) * (4 * TI * 128);
     const int i0 = i_begin + t * TI;
-    stage_rows256<false>(qb, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TI);
-    stage_rows256<false>(qb + TI * 128, d.d_o, d.lddo, d.B, b, h, hd, i0, Lq, TI);
-    stage_rows256<true>(qb + 2 * TI * 128, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TI);
-    stage_rows256<true>(qb + 3 * TI * 128, d.d_o, d.lddo, d.B, b, h, hd, i0, Lq, TI);
+    stage_rows256<false>(qb, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TI, bf);
+    stage_rows256<false>(qb + TI * 128, d.d_o, d.lddo, d.B, b, h, hd, i0, Lq, TI, bf);
+    stage_rows256<true>(qb + 2 * TI * 128, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TI, bf);
+    stage_rows256<true>(qb + 3 * TI * 128, d.d_o, d.lddo, d.B, b, h, hd, i0, Lq, TI, bf);
     if (tid < TI) {
       const int ii = i0 + tid;
       col_lse2[t & 1][tid] = ii < Lq ? d.lse[(int64_t)bh * Lq + ii] * 1.4426950408889634f : 0.f;
       col_delta[t & 1][tid] = ii < Lq ? d.delta[(int64_t)bh * Lq + ii] : 0.f;
     }
   };
-  stage_rows256<false>(Ks, d.k, d.ldk, d.B, b, h, hd, j0, Lk, TQ);
-  stage_rows256<false>(Vs, d.v, d.ldv, d.B, b, h, hd, j0, Lk, TQ);
+  stage_rows256<false>(Ks, d.k, d.ldk, d.B, b, h, hd, j0, Lk, TQ, bf);
+  stage_rows256<false>(Vs, d.v, d.ldv, d.B, b, h, hd, j0, Lk, TQ, bf);
   if (T > 0) stage_q(0);
   stage_wait();
   fence_async_smem();
@@ -797,11 +818,11 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
       for (int c = 0; c < 16; ++c) { dv[c] = 0.f; dk[c] = 0.f; }
     }
     if (j < Lk) {
-      float* kp = d.dk + ((int64_t)j * d.B + b) * d.lddk + h * hd + half * 16;
-      float* vp = d.dv + ((int64_t)j * d.B + b) * d.lddv + h * hd + half * 16;
+      const int64_t ko = ((int64_t)j * d.B + b) * d.lddk + h * hd + half * 16;
+      const int64_t vo = ((int64_t)j * d.B + b) * d.lddv + h * hd + half * 16;
 #pragma unroll
       for (int c = 0; c < 16; ++c)
-        if (half * 16 + c < hd) { kp[c] = dk[c]; vp[c] = dv[c]; }
+        if (half * 16 + c < hd) { st1_any(d.dk, ko + c, dk[c], bf); st1_any(d.dv, vo + c, dv[c], bf); }
     }
   }
   tc_fence_before();
@@ -818,6 +839,7 @@ int attn_fwd_tc(const mtb_attn_desc* d, int n, cudaStream_t st) {
   Group<mtb_attn_desc> g;
   int ntc = 0, nrest = 0, tot = 0;
   for (int i = 0; i < n; ++i) {
+    MTB_CHECK(d[i].hd <= HP || !d[i].bf16, "attn_fwd: bf16 operands need head_dim <= %d (problem %d)", HP, i);
     if (d[i].hd > HP) { rest[nrest++] = d[i]; continue; }
     g.d[ntc] = d[i];
     g.start[ntc] = tot;
@@ -847,6 +869,7 @@ int attn_bwd_tc(const mtb_attn_bwd_desc* d, int n, cudaStream_t st) {
   Group<mtb_attn_bwd_desc> gq, gk;
   int ntc = 0, nrest = 0, totq = 0, totk = 0;
   for (int i = 0; i < n; ++i) {
+    MTB_CHECK(d[i].hd <= HP || !d[i].bf16, "attn_bwd: bf16 operands need head_dim <= %d (problem %d)", HP, i);
     if (d[i].hd > HP) { rest[nrest++] = d[i]; continue; }
     gq.d[ntc] = d[i]; gk.d[ntc] = d[i];
     gq.start[ntc] = totq; gk.start[ntc] = totk;

@@ -117,6 +117,40 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---------------------------------------------------------------- bf16 <-> fp32 (bf16 data path: activations between kernels)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {      // round-to-nearest-even, lo in bits [0,16)
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ float bf16_round(float x) { return bf16_lo(pack_bf16x2(x, 0.f)); }
+// 4 consecutive elements at ELEMENT offset `off` of a tensor that is fp32 or bf16 (8- / 16-byte aligned accesses)
+__device__ __forceinline__ float4 ld4_any(const void* base, int64_t off, bool bf16) {
+  if (bf16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + off);
+    return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+}
+__device__ __forceinline__ void st4_any(void* base, int64_t off, float4 v, bool bf16) {
+  if (bf16) {
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(base) + off) = u;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off) = v;
+  }
+}
+__device__ __forceinline__ float ld1_any(const void* base, int64_t off, bool bf16) {
+  return bf16 ? __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(base)[off] << 16) : reinterpret_cast<const float*>(base)[off];
+}
+__device__ __forceinline__ void st1_any(void* base, int64_t off, float v, bool bf16) {
+  if (bf16) reinterpret_cast<uint16_t*>(base)[off] = (uint16_t)(pack_bf16x2(v, 0.f) & 0xffffu);
+  else reinterpret_cast<float*>(base)[off] = v;
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // Every hot kernel starts with pdl_sync(): it waits until the preceding kernel of the stream has completed and
 // flushed its writes, then lets the NEXT kernel's CTAs be scheduled while this one is still running (they park in

@@ -137,21 +137,21 @@ __global__ void __launch_bounds__(EW_THREADS) addn_kernel(const __grid_constant_
       if (v >= nvec) break;
       const int64_t t = v / ev;
       const int c = (int)(v - t * ev) << 2;
-      float4 acc = d.accumulate ? *reinterpret_cast<const float4*>(d.dst + t * d.ld_dst + c) : make_float4(0, 0, 0, 0);
+      float4 acc = d.accumulate ? ld4_any(d.dst, t * d.ld_dst + c, d.dst_bf16 != 0) : make_float4(0, 0, 0, 0);
       for (int i = 0; i < d.n_src; ++i) {
-        const float4 a = *reinterpret_cast<const float4*>(d.src[i] + t * d.ld_src[i] + c);
+        const float4 a = ld4_any(d.src[i], t * d.ld_src[i] + c, d.src_bf16[i] != 0);
         acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
       }
-      *reinterpret_cast<float4*>(d.dst + t * d.ld_dst + c) = acc;
+      st4_any(d.dst, t * d.ld_dst + c, acc, d.dst_bf16 != 0);
     }
   } else {
     const int64_t base = (int64_t)local * (EW_THREADS * EW_VEC_PER_THREAD * 4);
     for (int64_t e = base + threadIdx.x; e < base + EW_THREADS * EW_VEC_PER_THREAD * 4 && e < total; e += EW_THREADS) {
       const int64_t t = e / E;
       const int c = (int)(e - t * E);
-      float acc = d.accumulate ? d.dst[t * d.ld_dst + c] : 0.f;
-      for (int i = 0; i < d.n_src; ++i) acc += d.src[i][t * d.ld_src[i] + c];
-      d.dst[t * d.ld_dst + c] = acc;
+      float acc = d.accumulate ? ld1_any(d.dst, t * d.ld_dst + c, d.dst_bf16 != 0) : 0.f;
+      for (int i = 0; i < d.n_src; ++i) acc += ld1_any(d.src[i], t * d.ld_src[i] + c, d.src_bf16[i] != 0);
+      st1_any(d.dst, t * d.ld_dst + c, acc, d.dst_bf16 != 0);
     }
   }
 }

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(LN_THREADS) resln_fwd_kernel(const __grid_cons
       const int c = v << 2;
       float4 r = d.res ? ld4(d.res + (int64_t)t * d.ld_res + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       if (d.a) {
-        const float4 a = ld4(d.a + (int64_t)t * d.ld_a + c);
+        const float4 a = ld4_any(d.a, (int64_t)t * d.ld_a + c, d.a_bf16 != 0);
         const float4 k = keep4(dc, ((uint64_t)t * E + c) >> 2);
         r.x += a.x * k.x; r.y += a.y * k.y; r.z += a.z * k.z; r.w += a.w * k.w;
         if (d.x_new) st4(d.x_new + (int64_t)t * d.ld_x + c, r);
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(LN_THREADS) resln_fwd_kernel(const __grid_cons
       float4 y;
       y.x = (x[i].x - mean) * rstd * gm.x + bt.x; y.y = (x[i].y - mean) * rstd * gm.y + bt.y;
       y.z = (x[i].z - mean) * rstd * gm.z + bt.z; y.w = (x[i].w - mean) * rstd * gm.w + bt.w;
-      st4(d.y + (int64_t)t * d.ld_y + c, y);
+      st4_any(d.y, (int64_t)t * d.ld_y + c, y, d.y_bf16 != 0);
     }
   }
 }
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(LN_THREADS) resln_bwd_kernel(const __grid_cons
       wdy[i] = make_float4(0, 0, 0, 0); xh[i] = make_float4(0, 0, 0, 0);
       if (v < nv && has_ln) {
         const int c = v << 2;
-        const float4 dy = ld4(d.dy + (int64_t)t * d.ld_dy + c);
+        const float4 dy = ld4_any(d.dy, (int64_t)t * d.ld_dy + c, d.dy_bf16 != 0);
         const float4 x = ld4(d.x_new + (int64_t)t * d.ld_x + c);
         const float4 gm = gather4(d.gamma, d.idx, c);
         xh[i] = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
@@ -186,8 +186,11 @@ __global__ void __launch_bounds__(LN_THREADS) resln_bwd_kernel(const __grid_cons
         if (d.d_res) st4(d.d_res + (int64_t)t * d.ld_dres + c, gx);
         if (d.d_a) {
           const float4 k = keep4(dc, ((uint64_t)t * E + c) >> 2);
-          const float4 da = make_float4(gx.x * k.x, gx.y * k.y, gx.z * k.z, gx.w * k.w);
-          st4(d.d_a + (int64_t)t * d.ld_da + c, da);
+          float4 da = make_float4(gx.x * k.x, gx.y * k.y, gx.z * k.z, gx.w * k.w);
+          if (d.da_bf16) {     // the bias gradient sums exactly what the GEMMs will read
+            da = make_float4(bf16_round(da.x), bf16_round(da.y), bf16_round(da.z), bf16_round(da.w));
+          }
+          st4_any(d.d_a, (int64_t)t * d.ld_da + c, da, d.da_bf16 != 0);
           if (AFFINE_GRAD && bgrad) { dba[i].x += da.x; dba[i].y += da.y; dba[i].z += da.z; dba[i].w += da.w; }
         }
       }
@@ -307,9 +310,12 @@ int mtb_resln_fwd(const mtb_resln_desc* d, int n, void* stream) {
     g.start[i] = tot;
     tot += (x.T + LN_WARPS - 1) / LN_WARPS;
     maxE = x.E > maxE ? x.E : maxE;
-    vec = vec && (x.E % 4 == 0) && (!x.res || (aligned16(x.res) && x.ld_res % 4 == 0)) &&
+    const bool v1 = (x.E % 4 == 0) && (!x.res || (aligned16(x.res) && x.ld_res % 4 == 0)) &&
           (!x.a || (aligned16(x.a) && x.ld_a % 4 == 0)) && (!x.x_new || (aligned16(x.x_new) && x.ld_x % 4 == 0)) &&
           (!x.y || (aligned16(x.y) && x.ld_y % 4 == 0)) && (!x.gamma || x.idx || (aligned16(x.gamma) && aligned16(x.beta)));
+    MTB_CHECK(v1 || !(x.a_bf16 || x.y_bf16), "resln_fwd: problem %d has bf16 operands but is not 4-element aligned", i);
+    MTB_CHECK(x.E <= 1024 || !(x.a_bf16 || x.y_bf16), "resln_fwd: bf16 operands need E <= 1024 (problem %d)", i);
+    vec = vec && v1;
   }
   g.start[n] = tot;
   if (tot == 0) return 0;
@@ -335,9 +341,11 @@ int mtb_resln_bwd(const mtb_resln_bwd_desc* d, int n, void* stream) {
     maxE = x.E > maxE ? x.E : maxE;
     maxT = x.T > maxT ? x.T : maxT;
     affine = affine || (x.dgamma != nullptr) || (x.dbias != nullptr);
-    vec = vec && (x.E % 4 == 0) && (!x.dy || (aligned16(x.dy) && x.ld_dy % 4 == 0 && aligned16(x.x_new) && x.ld_x % 4 == 0)) &&
+    const bool v1 = (x.E % 4 == 0) && (!x.dy || (aligned16(x.dy) && x.ld_dy % 4 == 0 && aligned16(x.x_new) && x.ld_x % 4 == 0)) &&
           (!x.d_xnew || (aligned16(x.d_xnew) && x.ld_dx % 4 == 0)) && (!x.d_res || (aligned16(x.d_res) && x.ld_dres % 4 == 0)) &&
           (!x.d_a || (aligned16(x.d_a) && x.ld_da % 4 == 0)) && (!x.dy || x.idx || aligned16(x.gamma));
+    MTB_CHECK((v1 && x.E <= 1024) || !(x.dy_bf16 || x.da_bf16), "resln_bwd: problem %d has bf16 operands but is not vectorisable", i);
+    vec = vec && v1;
   }
   cudaStream_t st = (cudaStream_t)stream;
   int tot = 0;

@@ -15,6 +15,7 @@
 // Partial tiles (M % 128, N % BJ, K % 32 such as K = 200) rely on TMA zero fill.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 #include <time.h>
 
@@ -54,6 +55,8 @@ struct alignas(64) TcProblem {
   int splits;          // split of the reduction range (epi == 2)
   int epi;             // 0 store, 1 +=, 2 atomicAdd
   int act; float p; mtb_rng rng;
+  int ab16;            // operands are bf16: 64 reduction elements per 128-byte row, UMMA_K = 16, tcgen05.mma.kind::f16
+  int c16;             // output is bf16 (fp32 accumulator converted in the epilogue, 64-column TMA boxes; BJ % 64 == 0)
 };
 
 // The problem list travels in the kernel parameter block.  Parameter blocks above 4 KB take a slower launch path
@@ -106,6 +109,13 @@ __device__ __forceinline__ void tcgen05_mma_tf32(uint32_t d_tmem, uint64_t adesc
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -129,15 +139,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 //             sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only available smem
 //             layout"): atom = 32 MN elements (128 B) x 4 reduction rows; MN atoms LBO = 4096 B apart
 //             (one 32 x 32 TMA box each), 4-row reduction groups SBO = 512 B apart
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, bool mn_major) {
+//   MN-major, 16-bit operands: plain SWIZZLE_128B (2): atom = 64 MN elements (128 B) x 8 reduction rows; MN atoms LBO =
+//             8192 B apart (one 64-wide x 64-row TMA box each), 8-row reduction groups SBO = 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, bool mn_major, bool ab16 = false) {
   uint64_t d = 0;
   d |= (uint64_t)((addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((mn_major ? 4096u : 16u) >> 4) << 16;
-  d |= (uint64_t)((mn_major ? 512u : 1024u) >> 4) << 32;
+  d |= (uint64_t)((mn_major ? (ab16 ? 8192u : 4096u) : 16u) >> 4) << 16;
+  d |= (uint64_t)((mn_major ? (ab16 ? 1024u : 512u) : 1024u) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(mn_major ? 1 : 2) << 61;
+  d |= (uint64_t)((mn_major && !ab16) ? 1 : 2) << 61;
   return d;
 }
+
 
 #ifdef MTB_TC_TRACE
 __device__ unsigned long long g_tc_trace[64];
@@ -169,7 +182,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
   const int ti = tile / tj_n, tj = tile - ti * tj_n;
   const int is = ti / tpi, il0 = (ti - is * tpi) * TC_BI;        // block / offset inside block along I
   const int js = tj / tpj, jl0 = (tj - js * tpj) * P.BJ;
-  const int kbps = (P.r_len + TC_BR - 1) / TC_BR;                // reduction slabs per block
+  const bool ab16 = P.ab16 != 0;
+  const int BR = ab16 ? 64 : TC_BR;                              // reduction elements per stage (one 128-byte row)
+  const int MNW = ab16 ? 64 : 32;                                // MN-major operands: elements per 128-byte box row
+  const uint32_t MNBOX = ab16 ? 8192u : 4096u;                   // bytes of one MN-major box (MNW wide x BR rows)
+  const int kbps = (P.r_len + BR - 1) / BR;                      // reduction slabs per block
   const int nkb_total = kbps * P.r_nseg;
   const int per = (nkb_total + P.splits - 1) / P.splits;
   const int kb0 = split * per;
@@ -178,8 +195,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int b_boxes = P.b_mn ? (P.BJ + 31) / 32 : 1;
-  const uint32_t b_bytes = P.b_mn ? (uint32_t)b_boxes * 4096u : (uint32_t)P.BJ * 128u;
+  const int b_boxes = P.b_mn ? (P.BJ + MNW - 1) / MNW : 1;
+  const uint32_t b_bytes = P.b_mn ? (uint32_t)b_boxes * MNBOX : (uint32_t)P.BJ * 128u;
   const int TC_STAGES = P.stages;
   const uint32_t TC_STAGE_BYTES = (uint32_t)TC_A_BYTES + (((uint32_t)P.BJ * 128u + 1023u) & ~1023u);
 
@@ -215,19 +232,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
           const uint32_t sa = smem_base + (uint32_t)s * TC_STAGE_BYTES;
           const uint32_t sb = sa + TC_A_BYTES;
           const int rs = (kb0 + kb) / kbps;
-          const int rl0 = ((kb0 + kb) - rs * kbps) * TC_BR;
+          const int rl0 = ((kb0 + kb) - rs * kbps) * BR;
           // 4-D coordinates {col_in_block, col_block, row_in_block, row_block}; K-major operands have the
           // reduction on the (contiguous) column axis, MN-major operands on the row axis
           if (P.a_mn) {
-#pragma unroll
-            for (int b = 0; b < TC_BI / 32; ++b)
-              tma_load_4d(sa + b * 4096, &P.mapA, fb, il0 + b * 32, P.a_iseg[is], rl0, P.a_rseg[rs]);
+            for (int b = 0; b < TC_BI / MNW; ++b)
+              tma_load_4d(sa + b * MNBOX, &P.mapA, fb, il0 + b * MNW, P.a_iseg[is], rl0, P.a_rseg[rs]);
           } else {
             tma_load_4d(sa, &P.mapA, fb, rl0, P.a_rseg[rs], il0, P.a_iseg[is]);
           }
           if (P.b_mn) {
             for (int b = 0; b < b_boxes; ++b)
-              tma_load_4d(sb + b * 4096, &P.mapB, fb, jl0 + b * 32, P.b_jseg[js], rl0, P.b_rseg[rs]);
+              tma_load_4d(sb + b * MNBOX, &P.mapB, fb, jl0 + b * MNW, P.b_jseg[js], rl0, P.b_rseg[rs]);
           } else {
             tma_load_4d(sb, &P.mapB, fb, rl0, P.b_rseg[rs], jl0, P.b_jseg[js]);
           }
@@ -237,11 +253,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
       if (lane == 0) {
         // ===== MMA issuer =====
         // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, majors, N >> 3, M >> 4
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.a_mn ? 1 : 0) << 15) |
+        //   operand format (bits [7,10) and [10,13)): 1 = bf16, 2 = tf32
+        const uint32_t fmt = ab16 ? 1u : 2u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.a_mn ? 1 : 0) << 15) |
                                ((uint32_t)(P.b_mn ? 1 : 0) << 16) | ((uint32_t)(P.BJ >> 3) << 17) |
                                ((uint32_t)(TC_BI >> 4) << 24);
-        const uint32_t a_step = P.a_mn ? 1024u : 32u;    // bytes per UMMA_K (8 tf32) step
-        const uint32_t b_step = P.b_mn ? 1024u : 32u;
+        // bytes per UMMA_K step (8 tf32 / 16 bf16 = 32 B of a K-major row; 8 / 16 reduction rows of 128 B when MN-major)
+        const uint32_t mn_step = ab16 ? 2048u : 1024u;
+        const uint32_t a_step = P.a_mn ? mn_step : 32u;
+        const uint32_t b_step = P.b_mn ? mn_step : 32u;
         for (int kb = 0; kb < nkb; ++kb) {
           const int s = kb % TC_STAGES;
           const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
@@ -252,9 +272,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
           const uint32_t sb = sa + TC_A_BYTES;
 #pragma unroll
           for (int k = 0; k < TC_BR / 8; ++k) {
-            const uint64_t ad = make_desc(sa + k * a_step, P.a_mn);
-            const uint64_t bd = make_desc(sb + k * b_step, P.b_mn);
-            tcgen05_mma_tf32(tmem_d, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint64_t ad = make_desc(sa + k * a_step, P.a_mn, ab16);
+            const uint64_t bd = make_desc(sb + k * b_step, P.b_mn, ab16);
+            if (ab16) tcgen05_mma_f16(tmem_d, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            else tcgen05_mma_tf32(tmem_d, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           tcgen05_commit(smem_u32(&empty_bar[s]));        // frees the ring slot when these MMAs retire
         }
@@ -290,12 +311,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
       if (threadIdx.x == 64) TRACE(2);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       int nbuf = 0;
-      for (int c0 = 0; c0 < BJ; c0 += 32) {
-        if (jl0 + c0 >= j_len || !rows_any) break;        // warp-uniform
-        uint32_t v[32];
-        if (threadIdx.x == 64 && nbuf < 3) TRACE(40 + nbuf * 6);
+      // one 32-column group of my accumulator row: TMEM -> registers, + bias, ReLU + dropout
+      auto load32 = [&](int c0, uint32_t (&v)[32]) {
         tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        if (threadIdx.x == 64 && nbuf < 3) TRACE(41 + nbuf * 6);
         const int jb = jl0 + c0;
         if (brow) {
 #pragma unroll
@@ -327,9 +345,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             for (int e = 0; e < 4; ++e) v[c + e] = __float_as_uint(o[e]);
           }
         }
-        if (threadIdx.x == 64 && nbuf < 3) TRACE(42 + nbuf * 6);
-        const uint32_t st = stage0 + (uint32_t)(nbuf % nstage) * 4096u;
-        if (nbuf >= nstage) {                             // the store issued `nstage` chunks ago must have finished reading this tile
+      };
+      // the store issued `nstage` chunks ago must have finished reading its staging tile before it is overwritten
+      auto wait_stage = [&]() {
+        if (nbuf >= nstage) {
           if (lane == 0) {
             switch (nstage) {                             // wait_group takes an immediate: allow nstage - 1 stores in flight
               case 2: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
@@ -343,14 +362,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
           }
           __syncwarp();
         }
-#pragma unroll
-        for (int c = 0; c < 8; ++c)                       // 16-byte chunk c of row r lives at chunk (c ^ (r & 7)): SWIZZLE_128B
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + my_row + (((uint32_t)c ^ sw) << 4)),
-                       "r"(v[4 * c]), "r"(v[4 * c + 1]), "r"(v[4 * c + 2]), "r"(v[4 * c + 3]) : "memory");
-        if (threadIdx.x == 64 && nbuf < 3) TRACE(43 + nbuf * 6);
+      };
+      auto tma_out = [&](uint32_t st, int jb) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (threadIdx.x == 64 && nbuf < 3) TRACE(44 + nbuf * 6);
         if (lane == 0) {
           if (epi == 0)
             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -360,8 +375,49 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                          ::"l"(&P.mapC), "r"(st), "r"(jb), "r"(cj), "r"(il_w), "r"(ci) : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        if (threadIdx.x == 64 && nbuf < 3) TRACE(45 + nbuf * 6);
-        ++nbuf;
+      };
+      if (P.c16) {
+        // bf16 output: two 32-column groups are converted (round-to-nearest-even) and packed into ONE 128-byte staging
+        // row = a 64-column x 32-row TMA box of the bf16 output map
+        for (int c0 = 0; c0 < BJ; c0 += 64) {
+          if (jl0 + c0 >= j_len || !rows_any) break;      // warp-uniform
+          const uint32_t st = stage0 + (uint32_t)(nbuf % nstage) * 4096u;
+          wait_stage();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v[32];
+            load32(c0 + hh * 32, v);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {                 // 16-byte chunk (4 hh + c) of row r lives at chunk ((4 hh + c) ^ (r & 7))
+              const uint32_t w0 = pack_bf16x2(__uint_as_float(v[8 * c]), __uint_as_float(v[8 * c + 1]));
+              const uint32_t w1 = pack_bf16x2(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3]));
+              const uint32_t w2 = pack_bf16x2(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5]));
+              const uint32_t w3 = pack_bf16x2(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7]));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + my_row + ((((uint32_t)(4 * hh + c)) ^ sw) << 4)),
+                           "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+            }
+          }
+          tma_out(st, jl0 + c0);
+          ++nbuf;
+        }
+      } else {
+        for (int c0 = 0; c0 < BJ; c0 += 32) {
+          if (jl0 + c0 >= j_len || !rows_any) break;      // warp-uniform
+          uint32_t v[32];
+          if (threadIdx.x == 64 && nbuf < 3) TRACE(40 + nbuf * 6);
+          load32(c0, v);
+          if (threadIdx.x == 64 && nbuf < 3) TRACE(42 + nbuf * 6);
+          const uint32_t st = stage0 + (uint32_t)(nbuf % nstage) * 4096u;
+          wait_stage();
+#pragma unroll
+          for (int c = 0; c < 8; ++c)                     // 16-byte chunk c of row r lives at chunk (c ^ (r & 7)): SWIZZLE_128B
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + my_row + (((uint32_t)c ^ sw) << 4)),
+                         "r"(v[4 * c]), "r"(v[4 * c + 1]), "r"(v[4 * c + 2]), "r"(v[4 * c + 3]) : "memory");
+          if (threadIdx.x == 64 && nbuf < 3) TRACE(43 + nbuf * 6);
+          tma_out(st, jl0 + c0);
+          if (threadIdx.x == 64 && nbuf < 3) TRACE(45 + nbuf * 6);
+          ++nbuf;
+        }
       }
       if (threadIdx.x == 64) TRACE(5);
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -387,12 +443,20 @@ extern "C" int mtb_debug_tc_trace(unsigned long long* out) {
 // scratch = dY * [Y > 0] * inv_keep  (ReLU + dropout backward applied once, feeds dgrad and wgrad) and, fused,
 // db[phys(n)] += sum_m scratch[m, n]: one thread per column, 64 rows per block, coalesced along n.
 struct ActgradArgs {
-  const float* dY; int64_t ldy; const float* Y; int64_t ldyy; float* out; float* db;
+  const void* dY; int64_t ldy; const void* Y; int64_t ldyy; void* out; float* db;
   int M, N, seg_len; float inv_keep; uint8_t seg[TC_MAXSEG];
 };
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 constexpr int ACT_ROWS = 32;           // rows per block: 4 row-lanes x 8 rows, all 8 loads of a lane in flight
+template <typename T>
 __global__ void __launch_bounds__(512) actgrad_kernel(const ActgradArgs a) {
   pdl_sync();
+  const T* dYp = reinterpret_cast<const T*>(a.dY);
+  const T* Yp = reinterpret_cast<const T*>(a.Y);
+  T* outp = reinterpret_cast<T*>(a.out);
   __shared__ float part[4][128];
   const int n = blockIdx.x * 128 + threadIdx.x;
   const int m0 = blockIdx.y * ACT_ROWS + threadIdx.y * 8;
@@ -403,14 +467,15 @@ __global__ void __launch_bounds__(512) actgrad_kernel(const ActgradArgs a) {
     for (int u = 0; u < 8; ++u) {
       const int m = m0 + u;
       const bool ok = m < a.M;
-      dy[u] = ok ? a.dY[(int64_t)m * a.ldy + n] : 0.f;
-      y[u] = ok ? a.Y[(int64_t)m * a.ldyy + n] : 0.f;
+      dy[u] = ok ? ldf(dYp + (int64_t)m * a.ldy + n) : 0.f;
+      y[u] = ok ? ldf(Yp + (int64_t)m * a.ldyy + n) : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int m = m0 + u;
-      const float v = y[u] > 0.f ? dy[u] * a.inv_keep : 0.f;
-      if (m < a.M) a.out[(int64_t)m * a.N + n] = v;
+      float v = y[u] > 0.f ? dy[u] * a.inv_keep : 0.f;
+      if (sizeof(T) == 2) v = __bfloat162float(__float2bfloat16_rn(v));      // the bias gradient sums what the GEMMs will read
+      if (m < a.M) stf(outp + (int64_t)m * a.N + n, v);
       s += v;
     }
   }
@@ -425,7 +490,7 @@ __global__ void __launch_bounds__(512) actgrad_kernel(const ActgradArgs a) {
 // db[phys(n)] += sum_m dY[m, n]; one thread per column, 64 rows per block, 8 independent loads in flight
 constexpr int COLSUM_ROWS = 64;
 struct ColsumArgs {
-  const float* dY; int64_t ldy; float* db; int M, N, seg_len; uint8_t seg[TC_MAXSEG];
+  const void* dY; int64_t ldy; float* db; int M, N, seg_len; int bf16; uint8_t seg[TC_MAXSEG];
 };
 struct ColsumGroup {
   ColsumArgs a[MTB_MAX_GROUP];
@@ -439,14 +504,23 @@ __global__ void __launch_bounds__(128) colsum_kernel(const __grid_constant__ Col
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int m0 = blockIdx.y * COLSUM_ROWS, m1 = min(a.M, m0 + COLSUM_ROWS);
   if (n >= a.N || m0 >= a.M) return;
-  const float* p = a.dY + n;
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   int m = m0;
-  for (; m + 8 <= m1; m += 8) {
+  if (a.bf16) {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(a.dY) + n;
+    for (; m + 8 <= m1; m += 8) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) s[u] += p[(int64_t)(m + u) * a.ldy];
+      for (int u = 0; u < 8; ++u) s[u] += __bfloat162float(p[(int64_t)(m + u) * a.ldy]);
+    }
+    for (; m < m1; ++m) s[0] += __bfloat162float(p[(int64_t)m * a.ldy]);
+  } else {
+    const float* p = reinterpret_cast<const float*>(a.dY) + n;
+    for (; m + 8 <= m1; m += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s[u] += p[(int64_t)(m + u) * a.ldy];
+    }
+    for (; m < m1; ++m) s[0] += p[(int64_t)m * a.ldy];
   }
-  for (; m < m1; ++m) s[0] += p[(int64_t)m * a.ldy];
   const float t = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
   const int sgi = n / a.seg_len;
   atomicAdd(a.db + (int64_t)a.seg[sgi] * a.seg_len + (n - sgi * a.seg_len), t);
@@ -473,17 +547,19 @@ static EncodeTiledFn get_encode() {
 
 // Row-major fp32 matrix with leading dimension ld seen as 4-D {col_in_block, col_block, row_in_block,
 // row_block}: column blocks of clen (ncb of them), row blocks of rlen (nrb of them); box = bx cols x by rows.
-static bool encode_map(CUtensorMap* m, const float* ptr, int64_t ld, int64_t clen, int64_t ncb, int64_t rlen, int64_t nrb,
-                       int bx, int by, bool mn_major) {
+// esz = bytes per element: 4 (fp32, consumed as tf32) or 2 (bf16).  32-bit MN-major operand tiles need the 32-byte-atom
+// variant of the 128-byte swizzle, everything else the plain one.
+static bool encode_map(CUtensorMap* m, const void* ptr, int64_t ld, int64_t clen, int64_t ncb, int64_t rlen, int64_t nrb,
+                       int bx, int by, bool mn_major, int esz) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
-  if (ncb > 1 && (clen % 4) != 0) return false;
+  if (ncb > 1 && ((clen * esz) % 16) != 0) return false;
   cuuint64_t dims[4] = {(cuuint64_t)clen, (cuuint64_t)ncb, (cuuint64_t)rlen, (cuuint64_t)nrb};
-  cuuint64_t strides[3] = {(cuuint64_t)(ncb > 1 ? clen * 4 : ld * 4), (cuuint64_t)ld * 4, (cuuint64_t)rlen * ld * 4};
+  cuuint64_t strides[3] = {(cuuint64_t)(ncb > 1 ? clen * esz : ld * esz), (cuuint64_t)ld * esz, (cuuint64_t)rlen * ld * esz};
   cuuint32_t box[4] = {(cuuint32_t)bx, 1, (cuuint32_t)by, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = enc(m, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ptr, dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, (mn_major && esz == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -493,38 +569,38 @@ static bool encode_map(CUtensorMap* m, const float* ptr, int64_t ld, int64_t cle
 // every GEMM launch -- on the critical path, because the GPU finishes these small kernels faster than the host issues
 // them.  Direct-mapped cache of encoded maps (single host thread per device context, like the rest of the library).
 struct MapKey {
-  const void* ptr; int64_t ld, clen, ncb, rlen, nrb; int32_t bx, by, mn, pad;
+  const void* ptr; int64_t ld, clen, ncb, rlen, nrb; int32_t bx, by, mn, esz;
   bool operator==(const MapKey& o) const {
     return ptr == o.ptr && ld == o.ld && clen == o.clen && ncb == o.ncb && rlen == o.rlen && nrb == o.nrb && bx == o.bx && by == o.by &&
-           mn == o.mn;
+           mn == o.mn && esz == o.esz;
   }
 };
 struct MapEntry { MapKey key; CUtensorMap map; bool valid; };
 constexpr int MAP_CACHE = 1 << 14;
 static MapEntry* g_map_cache = nullptr;
 
-static bool make_map(CUtensorMap* m, const float* ptr, int64_t ld, int64_t clen, int64_t ncb, int64_t rlen, int64_t nrb,
-                     int bx, int by, bool mn_major) {
+static bool make_map(CUtensorMap* m, const void* ptr, int64_t ld, int64_t clen, int64_t ncb, int64_t rlen, int64_t nrb,
+                     int bx, int by, bool mn_major, int esz = 4) {
   if (!g_map_cache) g_map_cache = (MapEntry*)calloc(MAP_CACHE, sizeof(MapEntry));
-  MapKey k{ptr, ld, clen, ncb, rlen, nrb, bx, by, mn_major ? 1 : 0, 0};
+  MapKey k{ptr, ld, clen, ncb, rlen, nrb, bx, by, mn_major ? 1 : 0, esz};
   uint64_t h = (uint64_t)(uintptr_t)ptr * 0x9E3779B97F4A7C15ull;
   h ^= ((uint64_t)ld * 0xC2B2AE3D27D4EB4Full) ^ ((uint64_t)clen << 17) ^ ((uint64_t)rlen << 29) ^ ((uint64_t)ncb << 7) ^ ((uint64_t)nrb << 11) ^
-       ((uint64_t)bx << 41) ^ ((uint64_t)by << 47) ^ ((uint64_t)k.mn << 53);
+       ((uint64_t)bx << 41) ^ ((uint64_t)by << 47) ^ ((uint64_t)k.mn << 53) ^ ((uint64_t)esz << 57);
   h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
   MapEntry* e = g_map_cache ? &g_map_cache[h & (MAP_CACHE - 1)] : nullptr;
   if (e && e->valid && e->key == k) { *m = e->map; return true; }
-  if (!encode_map(m, ptr, ld, clen, ncb, rlen, nrb, bx, by, mn_major)) return false;
+  if (!encode_map(m, ptr, ld, clen, ncb, rlen, nrb, bx, by, mn_major, esz)) return false;
   if (e) { e->key = k; e->map = *m; e->valid = true; }
   return true;
 }
 
-static bool tma_ok(const float* p, int64_t ld) { return p != nullptr && ((((uintptr_t)p) & 15) == 0) && (ld % 4 == 0) && ld > 0; }
+static bool tma_ok(const void* p, int64_t ld, int esz = 4) { return p != nullptr && ((((uintptr_t)p) & 15) == 0) && ((ld * esz) % 16 == 0) && ld > 0; }
 
 // Tile width along J: a multiple of 32 (the epilogue moves 32-column TMA boxes), chosen to minimise
 // tiles x (width + 128) -- the "+ 128" is the A tile every extra column tile has to load again.
-static int pick_bj(int J) {
+static int pick_bj(int J, int gran = 32) {
   int best = 64, best_cost = 1 << 30;
-  for (int c = 256; c >= 32; c -= 32) {
+  for (int c = 256; c >= gran; c -= gran) {
     const int tiles = (J + c - 1) / c;
     const int cost = tiles * (c + 128);
     if (cost < best_cost) { best_cost = cost; best = c; }
@@ -533,11 +609,11 @@ static int pick_bj(int J) {
 }
 // Launches that cannot fill the GPU with full-width tiles (<= one CTA per SM) are pure latency: halve the tile
 // width so twice as many CTAs each run a shorter main loop (3-stage ring at <= 128 columns) and epilogue.
-static int pick_bj_narrow(int J) {
-  const int bj = pick_bj(J);
+static int pick_bj_narrow(int J, int gran = 32) {
+  const int bj = pick_bj(J, gran);
   if (J < 128) return bj;
   const int tiles = (J + bj - 1) / bj;
-  int nb = ((J + 2 * tiles - 1) / (2 * tiles) + 31) / 32 * 32;
+  int nb = ((J + 2 * tiles - 1) / (2 * tiles) + gran - 1) / gran * gran;
   return nb < 64 ? 64 : nb;
 }
 static int tiles_of(int I, int i_n, int J, int j_n, int bj) { return ((I + TC_BI - 1) / TC_BI) * i_n * ((J + bj - 1) / bj) * j_n; }
@@ -554,7 +630,7 @@ static int zero_matrix(float* p, int64_t ld, int rows, int cols, cudaStream_t st
   else { MTB_CUDA(cudaMemset2DAsync(p, (size_t)ld * sizeof(float), 0, (size_t)cols * sizeof(float), (size_t)rows, st)); }
   return 0;
 }
-static int round_bj_mn(int bj) { return ((bj + 31) / 32) * 32; }   // MN-major B tiles are loaded in 32-wide boxes
+static int round_bj_mn(int bj, int mnw = 32) { return ((bj + mnw - 1) / mnw) * mnw; }   // MN-major B tiles are loaded in 32- (tf32) / 64- (bf16) wide boxes
 
 // axis description derived from the public descriptor
 struct Axis {
@@ -562,12 +638,12 @@ struct Axis {
   uint8_t phys[TC_MAXSEG];          // physical block index of compact block s
   int nphys;                        // physical blocks addressable (max + 1)
 };
-static bool make_axis(Axis& a, int total, const int32_t* idx, const mtb_segs& sg) {
+static bool make_axis(Axis& a, int total, const int32_t* idx, const mtb_segs& sg, int esz = 4) {
   if (idx == nullptr) {
     a.len = total; a.n = 1; a.phys[0] = 0; a.nphys = 1;
     return true;
   }
-  if (sg.n <= 0 || sg.n > TC_MAXSEG || sg.len <= 0 || sg.len * sg.n != total || (sg.len % 4) != 0) return false;
+  if (sg.n <= 0 || sg.n > TC_MAXSEG || sg.len <= 0 || sg.len * sg.n != total || ((sg.len * esz) % 16) != 0) return false;
   a.len = sg.len; a.n = sg.n; a.nphys = 0;
   for (int s = 0; s < sg.n; ++s) {
     if (sg.seg[s] < 0 || sg.seg[s] > 255) return false;
@@ -593,7 +669,8 @@ static int launch_tc_cap(const TcProblem* probs, int n, cudaStream_t st) {
   for (int i = 0; i < n; ++i) {
     TcProblem& q = g.d[i];
     q = probs[i];
-    const size_t stage = (size_t)TC_A_BYTES + (((size_t)(q.b_mn ? ((q.BJ + 31) / 32) * 32 : q.BJ) * 128 + 1023) & ~(size_t)1023);
+    const int mnw = q.ab16 ? 64 : 32;
+    const size_t stage = (size_t)TC_A_BYTES + (((size_t)(q.b_mn ? ((q.BJ + mnw - 1) / mnw) * mnw : q.BJ) * 128 + 1023) & ~(size_t)1023);
     int stages = (int)(TC_SMEM_BUDGET / stage);
     stages = stages > TC_MAX_STAGES ? TC_MAX_STAGES : (stages < 2 ? 2 : stages);
     q.stages = stages;
@@ -607,8 +684,8 @@ static int launch_tc_cap(const TcProblem* probs, int n, cudaStream_t st) {
   if (dbg) {
     fprintf(stderr, "[tc] grid %d:", tot);
     for (int i = 0; i < n; ++i)
-      fprintf(stderr, " {I %d J %d R %d BJ %d st %d sp %d mn %d%d epi %d}", g.d[i].I, g.d[i].J, g.d[i].R, g.d[i].BJ, g.d[i].stages, g.d[i].splits,
-              g.d[i].a_mn, g.d[i].b_mn, g.d[i].epi);
+      fprintf(stderr, " {I %d J %d R %d BJ %d st %d sp %d mn %d%d epi %d ab16 %d c16 %d}", g.d[i].I, g.d[i].J, g.d[i].R, g.d[i].BJ, g.d[i].stages,
+              g.d[i].splits, g.d[i].a_mn, g.d[i].b_mn, g.d[i].epi, g.d[i].ab16, g.d[i].c16);
     fprintf(stderr, "\n");
   }
   MTB_CUDA(launch_k(gemm_tc_kernel<CAP>, dim3(tot), dim3(TC_THREADS), smem, st, g));
@@ -625,9 +702,6 @@ static int launch_tc(const TcProblem* probs, int n, cudaStream_t st) {
 }
 
 int linear_fwd_tc(const mtb_linear_desc* d, int n, cudaStream_t st) {
-  static const bool dbgt = getenv("MTB_TC_TIMING") != nullptr;
-  timespec ts0{}, ts1{}, ts2{};
-  if (dbgt) clock_gettime(CLOCK_MONOTONIC, &ts0);
   TcProblem tc[MTB_MAX_GROUP];
   mtb_linear_desc rest[MTB_MAX_GROUP];
   Axis ans[MTB_MAX_GROUP], aks[MTB_MAX_GROUP];
@@ -635,50 +709,56 @@ int linear_fwd_tc(const mtb_linear_desc* d, int n, cudaStream_t st) {
   int ntc = 0, nrest = 0, full_tiles = 0;
   for (int i = 0; i < n; ++i) {
     const mtb_linear_desc& x = d[i];
-    oks[i] = x.N >= 16 && x.K >= 8 && x.M >= 1 && tma_ok(x.X, x.ldx) && tma_ok(x.W, x.ldw) && tma_ok(x.Y, x.ldy) &&
-             make_axis(ans[i], x.N, x.row_idx, x.row_segs) && make_axis(aks[i], x.K, x.col_idx, x.col_segs);
-    if (oks[i]) full_tiles += tiles_of(x.M, 1, ans[i].len, ans[i].n, pick_bj(ans[i].len));
+    const int ei = x.in_bf16 ? 2 : 4, eo = x.out_bf16 ? 2 : 4;
+    oks[i] = x.N >= 16 && x.K >= 8 && x.M >= 1 && tma_ok(x.X, x.ldx, ei) && tma_ok(x.W, x.ldw, ei) && tma_ok(x.Y, x.ldy, eo) &&
+             make_axis(ans[i], x.N, x.row_idx, x.row_segs, eo < ei ? eo : ei) && make_axis(aks[i], x.K, x.col_idx, x.col_segs, ei);
+    MTB_CHECK(oks[i] || !(x.in_bf16 || x.out_bf16),
+              "linear_fwd: problem %d has bf16 operands the TMA engine cannot address (M %d N %d K %d ldx %lld ldw %lld ldy %lld); there is no "
+              "bf16 fallback", i, x.M, x.N, x.K, (long long)x.ldx, (long long)x.ldw, (long long)x.ldy);
+    if (oks[i]) full_tiles += tiles_of(x.M, 1, ans[i].len, ans[i].n, pick_bj(ans[i].len, x.out_bf16 ? 64 : 32));
   }
   const bool narrow = full_tiles <= sm_count();
   for (int i = 0; i < n; ++i) {
     const mtb_linear_desc& x = d[i];
     const Axis& an = ans[i];
     const Axis& ak = aks[i];
+    const int ei = x.in_bf16 ? 2 : 4, eo = x.out_bf16 ? 2 : 4;
+    const int br = x.in_bf16 ? 64 : TC_BR;
+    const int gran = x.out_bf16 ? 64 : 32;
     bool ok = oks[i];
     TcProblem& q = tc[ntc];
     if (ok) {
       q = TcProblem{};
-      q.BJ = narrow ? pick_bj_narrow(an.len) : pick_bj(an.len);
-      ok = make_map(&q.mapA, x.X, x.ldx, ak.len, ak.n, x.M, 1, TC_BR, TC_BI, false) &&
-           make_map(&q.mapB, x.W, x.ldw, ak.len, ak.nphys, an.len, an.nphys, TC_BR, q.BJ, false) &&
-           make_map(&q.mapC, x.Y, x.ldy, an.len, an.n, x.M, 1, 32, 32, false);
+      q.BJ = narrow ? pick_bj_narrow(an.len, gran) : pick_bj(an.len, gran);
+      ok = make_map(&q.mapA, x.X, x.ldx, ak.len, ak.n, x.M, 1, br, TC_BI, false, ei) &&
+           make_map(&q.mapB, x.W, x.ldw, ak.len, ak.nphys, an.len, an.nphys, br, q.BJ, false, ei) &&
+           make_map(&q.mapC, x.Y, x.ldy, an.len, an.n, x.M, 1, x.out_bf16 ? 64 : 32, 32, false, eo);
+      MTB_CHECK(ok || !(x.in_bf16 || x.out_bf16), "linear_fwd: tensor-map encoding failed for bf16 problem %d", i);
     }
     if (!ok) { rest[nrest++] = x; continue; }
-    q.C = x.Y; q.ldc = x.ldy; q.bias = x.bias;
+    q.C = (float*)x.Y; q.ldc = x.ldy; q.bias = x.bias;
     q.I = x.M; q.J = x.N; q.R = x.K;
     q.i_len = x.M; q.i_nseg = 1; q.j_len = an.len; q.j_nseg = an.n; q.r_len = ak.len; q.r_nseg = ak.n;
     ident(q.a_iseg, 1); ident(q.a_rseg, ak.n); copy_phys(q.b_jseg, an); copy_phys(q.b_rseg, ak);
     ident(q.c_iseg, 1); ident(q.c_jseg, an.n); copy_phys(q.bias_seg, an);
     q.a_mn = 0; q.b_mn = 0; q.splits = 1; q.epi = 0;
     q.act = x.act; q.p = x.p; q.rng = x.rng;
-    if (x.act == 0) {     // few tiles, long reduction (the head's [B, 3000] inputs): split K, partial sums meet in L2
-      const int nkb = ((ak.len + TC_BR - 1) / TC_BR) * ak.n;
+    q.ab16 = x.in_bf16 ? 1 : 0; q.c16 = x.out_bf16 ? 1 : 0;
+    if (x.act == 0 && !x.out_bf16) {     // few tiles, long reduction (the head's [B, 3000] inputs): split K, partial sums meet in L2 (fp32 outputs only)
+      const int nkb = ((ak.len + br - 1) / br) * ak.n;
       const int sp = pick_splitk(tiles_of(x.M, 1, an.len, an.n, q.BJ), nkb);
       if (sp > 1) {
         q.splits = sp; q.epi = 2;
-        if (zero_matrix(x.Y, x.ldy, x.M, x.N, st)) return -2;
+        if (zero_matrix((float*)x.Y, x.ldy, x.M, x.N, st)) return -2;
       }
+    } else if (x.out_bf16 && tiles_of(x.M, 1, an.len, an.n, q.BJ) * 8 <= sm_count()) {
+      q.BJ = 64;                         // bf16 outputs cannot be split over K: spread a long skinny problem over more column tiles instead
+      ok = make_map(&q.mapB, x.W, x.ldw, ak.len, ak.nphys, an.len, an.nphys, br, q.BJ, false, ei);
+      MTB_CHECK(ok, "linear_fwd: tensor-map encoding failed for bf16 problem %d", i);
     }
     ++ntc;
   }
-  if (dbgt) clock_gettime(CLOCK_MONOTONIC, &ts1);
   int rc = launch_tc(tc, ntc, st);
-  if (dbgt) {
-    clock_gettime(CLOCK_MONOTONIC, &ts2);
-    const double a = (ts1.tv_sec - ts0.tv_sec) * 1e6 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-3;
-    const double b = (ts2.tv_sec - ts1.tv_sec) * 1e6 + (ts2.tv_nsec - ts1.tv_nsec) * 1e-3;
-    if (a + b > 30.0) fprintf(stderr, "[tc-timing] fwd n=%d ntc=%d nrest=%d build %.1f us launch %.1f us (N0 %d K0 %d M0 %d)\n", n, ntc, nrest, a, b, d[0].N, d[0].K, d[0].M);
-  }
   if (rc) return rc;
   if (nrest) return linear_fwd_simt(rest, nrest, st);
   return 0;
@@ -694,33 +774,73 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
   for (int i = 0; i < n; ++i) {
     const mtb_linear_bwd_desc& x = d[i];
     Axis an, ak;
-    bool ok = x.N >= 16 && x.K >= 16 && x.M >= 1 && tma_ok(x.dY, x.ldy) && tma_ok(x.W, x.ldw) &&
-              (!x.dX || tma_ok(x.dX, x.lddx)) && (!x.dW || tma_ok(x.X, x.ldx)) && (x.act == 0 || x.scratch != nullptr) &&
-              make_axis(an, x.N, x.row_idx, x.row_segs) && make_axis(ak, x.K, x.col_idx, x.col_segs);
-    if (!ok) { rest[nrest++] = x; continue; }
+    const int ei = x.in_bf16 ? 2 : 4, ex = x.dx_bf16 ? 2 : 4;
+    const int br = x.in_bf16 ? 64 : TC_BR, mnw = x.in_bf16 ? 64 : 32;
+    bool ok = x.N >= 16 && x.K >= 16 && x.M >= 1 && tma_ok(x.dY, x.ldy, ei) && tma_ok(x.W, x.ldw, ei) &&
+              (!x.dX || tma_ok(x.dX, x.lddx, ex)) && (!x.dW || tma_ok(x.X, x.ldx, ei)) && (x.act == 0 || x.scratch != nullptr) &&
+              make_axis(an, x.N, x.row_idx, x.row_segs, ei) && make_axis(ak, x.K, x.col_idx, x.col_segs, ei < ex ? ei : ex);
+    MTB_CHECK(ok || !(x.in_bf16 || x.dx_bf16), "linear_bwd: problem %d has bf16 operands the TMA engine cannot address (M %d N %d K %d); there is "
+              "no bf16 fallback", i, x.M, x.N, x.K);
+    if (!ok) {
+      // fp32-engine fallback (operands TMA cannot address, e.g. a gather without block structure).  Callers that split
+      // dgrad and wgrad into separate calls rely on `scratch` holding dY' = dY * [Y > 0] / (1 - p) afterwards (the
+      // deferred weight-gradient call reads it as its dY): materialise it here exactly like the tensor-core path does,
+      // and hand the fp32 engine a plain (act = 0) problem over it.
+      mtb_linear_bwd_desc y = x;
+      if (x.act == 1 && x.scratch != nullptr) {
+        Axis arow;
+        MTB_CHECK(make_axis(arow, x.N, x.row_idx, x.row_segs, 4), "linear_bwd: problem %d needs ReLU backward over a row gather without "
+                  "block structure, which neither engine supports", i);
+        ActgradArgs aa{};
+        aa.dY = x.dY; aa.ldy = x.ldy; aa.Y = x.Yact; aa.ldyy = x.ldyact; aa.out = x.scratch; aa.db = x.db;
+        aa.M = x.M; aa.N = x.N; aa.seg_len = arow.len; aa.inv_keep = x.p > 0.f ? 1.f / (1.f - x.p) : 1.f;
+        for (int s2 = 0; s2 < TC_MAXSEG; ++s2) aa.seg[s2] = s2 < arow.n ? arow.phys[s2] : 0;
+        dim3 grid((x.N + 127) / 128, (x.M + ACT_ROWS - 1) / ACT_ROWS);
+        MTB_CUDA(launch_k(actgrad_kernel<float>, grid, dim3(128, 4), 0, st, aa));
+        mtb::note_launch();
+        MTB_CUDA(cudaGetLastError());
+        y.dY = x.scratch; y.ldy = x.N; y.act = 0; y.Yact = nullptr; y.ldyact = 0; y.db = nullptr; y.p = 0.f;
+      }
+      if (y.db != nullptr && y.dW == nullptr) {
+        // the fp32 engine only forms a bias gradient inside its weight-gradient GEMM: column-sum it here instead
+        Axis arow;
+        MTB_CHECK(make_axis(arow, x.N, x.row_idx, x.row_segs, 4), "linear_bwd: problem %d needs a bias gradient over a row gather without "
+                  "block structure and no weight gradient, which neither engine supports", i);
+        ColsumArgs& ca = cs.a[cs.n++];
+        ca = ColsumArgs{};
+        ca.dY = y.dY; ca.ldy = y.ldy; ca.db = y.db; ca.M = x.M; ca.N = x.N; ca.seg_len = arow.len; ca.bf16 = 0;
+        for (int s = 0; s < TC_MAXSEG; ++s) ca.seg[s] = s < arow.n ? arow.phys[s] : 0;
+        cs_gx = cs_gx > (x.N + 127) / 128 ? cs_gx : (x.N + 127) / 128;
+        cs_gy = cs_gy > (x.M + COLSUM_ROWS - 1) / COLSUM_ROWS ? cs_gy : (x.M + COLSUM_ROWS - 1) / COLSUM_ROWS;
+        y.db = nullptr;
+      }
+      rest[nrest++] = y;
+      continue;
+    }
     bool built = true;
     TcProblem qd{}, qw{};
-    const float* dYp = x.act == 1 ? x.scratch : x.dY;
+    const void* dYp = x.act == 1 ? (const void*)x.scratch : (const void*)x.dY;
     const int64_t ldyp = x.act == 1 ? x.N : x.ldy;
     if (x.dX) {           // dX[M,K] = dY'[M,N] . W'[N,K] : A K-major (reduction n contiguous), B MN-major (k_out contiguous)
-      qd.BJ = round_bj_mn(pick_bj(ak.len));
+      qd.BJ = round_bj_mn(pick_bj(ak.len, x.dx_bf16 ? 64 : 32), mnw);
       if (qd.BJ > 256) qd.BJ = 256;
-      built = built && make_map(&qd.mapA, dYp, ldyp, an.len, an.n, x.M, 1, TC_BR, TC_BI, false) &&
-              make_map(&qd.mapB, x.W, x.ldw, ak.len, ak.nphys, an.len, an.nphys, 32, TC_BR, true) &&
-              make_map(&qd.mapC, x.dX, x.lddx, ak.len, ak.n, x.M, 1, 32, 32, false);
-      qd.C = x.dX; qd.ldc = x.lddx; qd.bias = nullptr;
+      built = built && make_map(&qd.mapA, dYp, ldyp, an.len, an.n, x.M, 1, br, TC_BI, false, ei) &&
+              make_map(&qd.mapB, x.W, x.ldw, ak.len, ak.nphys, an.len, an.nphys, mnw, br, true, ei) &&
+              make_map(&qd.mapC, x.dX, x.lddx, ak.len, ak.n, x.M, 1, x.dx_bf16 ? 64 : 32, 32, false, ex);
+      qd.C = (float*)x.dX; qd.ldc = x.lddx; qd.bias = nullptr;
       qd.I = x.M; qd.J = x.K; qd.R = x.N;
       qd.i_len = x.M; qd.i_nseg = 1; qd.j_len = ak.len; qd.j_nseg = ak.n; qd.r_len = an.len; qd.r_nseg = an.n;
       ident(qd.a_iseg, 1); ident(qd.a_rseg, an.n); copy_phys(qd.b_jseg, ak); copy_phys(qd.b_rseg, an);
       ident(qd.c_iseg, 1); ident(qd.c_jseg, ak.n); ident(qd.bias_seg, 1);
       qd.a_mn = 0; qd.b_mn = 1; qd.splits = 1; qd.epi = x.accumulate_dx ? 1 : 0;
+      qd.ab16 = x.in_bf16 ? 1 : 0; qd.c16 = x.dx_bf16 ? 1 : 0;
     }
-    if (x.dW) {           // dW'[N,K] += dY'^T[N,M] . X[M,K] : both MN-major, reduction over tokens split across CTAs
-      qw.BJ = round_bj_mn(pick_bj(ak.len));
+    if (x.dW) {           // dW'[N,K] += dY'^T[N,M] . X[M,K] : both MN-major, reduction over tokens split across CTAs; fp32 output
+      qw.BJ = round_bj_mn(pick_bj(ak.len), mnw);
       if (qw.BJ > 256) qw.BJ = 256;
-      built = built && make_map(&qw.mapA, dYp, ldyp, an.len, an.n, x.M, 1, 32, TC_BR, true) &&
-              make_map(&qw.mapB, x.X, x.ldx, ak.len, ak.n, x.M, 1, 32, TC_BR, true) &&
-              make_map(&qw.mapC, x.dW, x.ldw, ak.len, ak.nphys, an.len, an.nphys, 32, 32, false);
+      built = built && make_map(&qw.mapA, dYp, ldyp, an.len, an.n, x.M, 1, mnw, br, true, ei) &&
+              make_map(&qw.mapB, x.X, x.ldx, ak.len, ak.n, x.M, 1, mnw, br, true, ei) &&
+              make_map(&qw.mapC, x.dW, x.ldw, ak.len, ak.nphys, an.len, an.nphys, 32, 32, false, 4);
       qw.C = x.dW; qw.ldc = x.ldw; qw.bias = nullptr;
       qw.I = x.N; qw.J = x.K; qw.R = x.M;
       qw.i_len = an.len; qw.i_nseg = an.n; qw.j_len = ak.len; qw.j_nseg = ak.n; qw.r_len = x.M; qw.r_nseg = 1;
@@ -728,7 +848,9 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
       copy_phys(qw.c_iseg, an); copy_phys(qw.c_jseg, ak); ident(qw.bias_seg, 1);
       qw.a_mn = 1; qw.b_mn = 1; qw.epi = 2;
       qw.splits = 1;        // decided for the whole launch below
+      qw.ab16 = x.in_bf16 ? 1 : 0; qw.c16 = 0;
     }
+    MTB_CHECK(built || !(x.in_bf16 || x.dx_bf16), "linear_bwd: tensor-map encoding failed for bf16 problem %d", i);
     if (!built) { rest[nrest++] = x; continue; }
     if (x.act == 1) {       // dY' = dY * [Y > 0] / (1 - p), materialised once for dgrad + wgrad; bias grad fused
       ActgradArgs aa{};
@@ -736,7 +858,8 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
       aa.M = x.M; aa.N = x.N; aa.seg_len = an.len; aa.inv_keep = x.p > 0.f ? 1.f / (1.f - x.p) : 1.f;
       for (int s2 = 0; s2 < TC_MAXSEG; ++s2) aa.seg[s2] = s2 < an.n ? an.phys[s2] : 0;
       dim3 grid((x.N + 127) / 128, (x.M + ACT_ROWS - 1) / ACT_ROWS);
-      MTB_CUDA(launch_k(actgrad_kernel, grid, dim3(128, 4), 0, st, aa));
+      if (x.in_bf16) { MTB_CUDA(launch_k(actgrad_kernel<__nv_bfloat16>, grid, dim3(128, 4), 0, st, aa)); }
+      else { MTB_CUDA(launch_k(actgrad_kernel<float>, grid, dim3(128, 4), 0, st, aa)); }
       mtb::note_launch();
       MTB_CUDA(cudaGetLastError());
     }
@@ -745,7 +868,7 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
     if (x.db && x.act != 1) {
       ColsumArgs& ca = cs.a[cs.n++];
       ca = ColsumArgs{};
-      ca.dY = dYp; ca.ldy = ldyp; ca.db = x.db; ca.M = x.M; ca.N = x.N; ca.seg_len = an.len;
+      ca.dY = dYp; ca.ldy = ldyp; ca.db = x.db; ca.M = x.M; ca.N = x.N; ca.seg_len = an.len; ca.bf16 = x.in_bf16 ? 1 : 0;
       for (int s = 0; s < TC_MAXSEG; ++s) ca.seg[s] = s < an.n ? an.phys[s] : 0;
       cs_gx = cs_gx > (x.N + 127) / 128 ? cs_gx : (x.N + 127) / 128;
       cs_gy = cs_gy > (x.M + COLSUM_ROWS - 1) / COLSUM_ROWS ? cs_gy : (x.M + COLSUM_ROWS - 1) / COLSUM_ROWS;
@@ -756,19 +879,25 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
     mtb::note_launch();
     MTB_CUDA(cudaGetLastError());
   }
-  // ---- launch-wide tiling policy (B operands are MN-major here: 32-wide TMA boxes, so BJ is free to change) ----
+  // ---- launch-wide tiling policy (B operands are MN-major here: 32- / 64-wide TMA boxes, so BJ is free to change) ----
+  auto gran_of = [](const TcProblem& q) { return (q.ab16 || q.c16) ? 64 : 32; };
+  auto br_of = [](const TcProblem& q) { return q.ab16 ? 64 : TC_BR; };
   int dg_ctas = 0;
   for (int i = 0; i < ndg; ++i) dg_ctas += tiles_of(dg[i].i_len, dg[i].i_nseg, dg[i].j_len, dg[i].j_nseg, dg[i].BJ);
   if (dg_ctas <= sm_count()) {
     dg_ctas = 0;
     for (int i = 0; i < ndg; ++i) {
-      dg[i].BJ = pick_bj_narrow(dg[i].j_len);
+      dg[i].BJ = pick_bj_narrow(dg[i].j_len, gran_of(dg[i]));
       dg_ctas += tiles_of(dg[i].i_len, dg[i].i_nseg, dg[i].j_len, dg[i].j_nseg, dg[i].BJ);
     }
   }
-  for (int i = 0; i < ndg; ++i) {        // few tiles, long reduction (head): split it; partial sums meet in L2
+  for (int i = 0; i < ndg; ++i) {        // few tiles, long reduction (head): split it; partial sums meet in L2 (fp32 outputs only)
     TcProblem& q = dg[i];
-    const int nkb = ((q.r_len + TC_BR - 1) / TC_BR) * q.r_nseg;
+    if (q.c16) {
+      if (tiles_of(q.i_len, q.i_nseg, q.j_len, q.j_nseg, q.BJ) * 8 <= sm_count()) q.BJ = 64;
+      continue;
+    }
+    const int nkb = ((q.r_len + br_of(q) - 1) / br_of(q)) * q.r_nseg;
     const int sp = pick_splitk(tiles_of(q.i_len, q.i_nseg, q.j_len, q.j_nseg, q.BJ), nkb);
     if (sp > 1) {
       q.splits = sp;
@@ -780,17 +909,18 @@ int linear_bwd_tc(const mtb_linear_bwd_desc* d, int n, cudaStream_t st) {
     }
   }
   {
-    // weight gradients reduce over the token axis: give every CTA >= 8 reduction slabs and aim the whole launch
-    // at about one wave (2 CTAs / SM) -- more splits only multiply the reduce-add traffic on the same tiles
+    // weight gradients reduce over the token axis: give every CTA >= 8 reduction slabs (>= 4 of the twice as deep bf16
+    // slabs) and aim the whole launch at about one wave (2 CTAs / SM) -- more splits only multiply the reduce-add traffic
     long long work = 0;
     for (int i = 0; i < nwg; ++i)
-      work += (long long)tiles_of(wg[i].i_len, wg[i].i_nseg, wg[i].j_len, wg[i].j_nseg, wg[i].BJ) * ((wg[i].r_len + TC_BR - 1) / TC_BR);
+      work += (long long)tiles_of(wg[i].i_len, wg[i].i_nseg, wg[i].j_len, wg[i].j_nseg, wg[i].BJ) * ((wg[i].r_len + br_of(wg[i]) - 1) / br_of(wg[i]));
     int budget = 2 * sm_count() - (dg_ctas < sm_count() ? dg_ctas : sm_count());
     int kpc = (int)((work + budget - 1) / budget);
-    if (kpc < 8) kpc = 8;
     for (int i = 0; i < nwg; ++i) {
-      const int nkb = (wg[i].r_len + TC_BR - 1) / TC_BR;
-      int sp = (nkb + kpc - 1) / kpc;
+      const int kmin = wg[i].ab16 ? 4 : 8;
+      const int k = kpc < kmin ? kmin : kpc;
+      const int nkb = (wg[i].r_len + br_of(wg[i]) - 1) / br_of(wg[i]);
+      int sp = (nkb + k - 1) / k;
       wg[i].splits = sp < 1 ? 1 : sp;
     }
   }
@@ -816,7 +946,8 @@ int preload_linear_tc() {
   { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, gemm_tc_kernel<6>) != cudaSuccess) ++bad; }
   { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, gemm_tc_kernel<12>) != cudaSuccess) ++bad; }
   { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, gemm_tc_kernel<MTB_MAX_GROUP>) != cudaSuccess) ++bad; }
-  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, actgrad_kernel) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, actgrad_kernel<float>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, actgrad_kernel<__nv_bfloat16>) != cudaSuccess) ++bad; }
   { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, colsum_kernel) != cudaSuccess) ++bad; }
   return bad;
 }

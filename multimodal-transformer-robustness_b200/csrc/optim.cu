@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(AD_THREADS) adam_update_kernel(const mtb_adam_
   float* __restrict__ g = d.grad + off;
   float* __restrict__ m = d.exp_avg + off;
   float* __restrict__ v = d.exp_avg_sq + off;
+  uint16_t* __restrict__ sh = d.shadow ? d.shadow + off : nullptr;      // bf16 shadow of the parameter (bf16 data path)
   auto upd = [&](float& pp, float& gg, float& mm, float& vv) {
     gg *= coef;
     float ge = gg;
@@ -109,11 +110,13 @@ __global__ void __launch_bounds__(AD_THREADS) adam_update_kernel(const mtb_adam_
     float4 P = p4[i], G = g4[i], M = m4[i], V = v4[i];
     upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
     p4[i] = P; g4[i] = G; m4[i] = M; v4[i] = V;
+    if (sh) { uint2 u; u.x = pack_bf16x2(P.x, P.y); u.y = pack_bf16x2(P.z, P.w); *reinterpret_cast<uint2*>(sh + 4 * i) = u; }
   }
   for (int i = (n4 << 2) + threadIdx.x; i < n; i += AD_THREADS) {
     float P = p[i], G = g[i], M = m[i], V = v[i];
     upd(P, G, M, V);
     p[i] = P; g[i] = G; m[i] = M; v[i] = V;
+    if (sh) sh[i] = (uint16_t)(pack_bf16x2(P, 0.f) & 0xffffu);
   }
 }
 

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MTB_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libmultb200.so")   # MTB_LIB: instrumented debug builds
 
 MAX_GROUP = 24
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 
 class MtbError(RuntimeError):
@@ -38,7 +38,8 @@ class EmbedDesc(C.Structure):
 
 class AddNDesc(C.Structure):
     _fields_ = [("src", C.c_void_p * 3), ("ld_src", C.c_int64 * 3), ("n_src", C.c_int),
-                ("dst", C.c_void_p), ("ld_dst", C.c_int64), ("T", C.c_int), ("E", C.c_int), ("accumulate", C.c_int)]
+                ("dst", C.c_void_p), ("ld_dst", C.c_int64), ("T", C.c_int), ("E", C.c_int), ("accumulate", C.c_int),
+                ("src_bf16", C.c_int * 3), ("dst_bf16", C.c_int)]
 
 
 class ResLnDesc(C.Structure):
@@ -46,7 +47,7 @@ class ResLnDesc(C.Structure):
                 ("x_new", C.c_void_p), ("ld_x", C.c_int64), ("y", C.c_void_p), ("ld_y", C.c_int64),
                 ("gamma", C.c_void_p), ("beta", C.c_void_p), ("idx", C.c_void_p),
                 ("mean", C.c_void_p), ("rstd", C.c_void_p), ("T", C.c_int), ("E", C.c_int),
-                ("eps", C.c_float), ("p", C.c_float), ("rng", Rng)]
+                ("eps", C.c_float), ("p", C.c_float), ("rng", Rng), ("a_bf16", C.c_int), ("y_bf16", C.c_int)]
 
 
 class ResLnBwdDesc(C.Structure):
@@ -55,14 +56,15 @@ class ResLnBwdDesc(C.Structure):
                 ("gamma", C.c_void_p), ("idx", C.c_void_p),
                 ("d_res", C.c_void_p), ("ld_dres", C.c_int64), ("d_a", C.c_void_p), ("ld_da", C.c_int64),
                 ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("T", C.c_int), ("E", C.c_int),
-                ("p", C.c_float), ("rng", Rng), ("dbias", C.c_void_p)]
+                ("p", C.c_float), ("rng", Rng), ("dbias", C.c_void_p), ("dy_bf16", C.c_int), ("da_bf16", C.c_int)]
 
 
 class LinearDesc(C.Structure):
     _fields_ = [("X", C.c_void_p), ("ldx", C.c_int64), ("W", C.c_void_p), ("ldw", C.c_int64),
                 ("bias", C.c_void_p), ("row_idx", C.c_void_p), ("col_idx", C.c_void_p),
                 ("Y", C.c_void_p), ("ldy", C.c_int64), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
-                ("act", C.c_int), ("p", C.c_float), ("rng", Rng), ("row_segs", Segs), ("col_segs", Segs)]
+                ("act", C.c_int), ("p", C.c_float), ("rng", Rng), ("row_segs", Segs), ("col_segs", Segs),
+                ("in_bf16", C.c_int), ("out_bf16", C.c_int)]
 
 
 class LinearBwdDesc(C.Structure):
@@ -71,14 +73,16 @@ class LinearBwdDesc(C.Structure):
                 ("row_idx", C.c_void_p), ("col_idx", C.c_void_p),
                 ("dX", C.c_void_p), ("lddx", C.c_int64), ("accumulate_dx", C.c_int),
                 ("dW", C.c_void_p), ("db", C.c_void_p), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
-                ("act", C.c_int), ("p", C.c_float), ("scratch", C.c_void_p), ("row_segs", Segs), ("col_segs", Segs)]
+                ("act", C.c_int), ("p", C.c_float), ("scratch", C.c_void_p), ("row_segs", Segs), ("col_segs", Segs),
+                ("in_bf16", C.c_int), ("dx_bf16", C.c_int)]
 
 
 class AttnDesc(C.Structure):
     _fields_ = [("q", C.c_void_p), ("ldq", C.c_int64), ("k", C.c_void_p), ("ldk", C.c_int64),
                 ("v", C.c_void_p), ("ldv", C.c_int64), ("o", C.c_void_p), ("ldo", C.c_int64),
                 ("lse", C.c_void_p), ("Lq", C.c_int), ("Lk", C.c_int), ("B", C.c_int), ("H", C.c_int),
-                ("hd", C.c_int), ("scale", C.c_float), ("p", C.c_float), ("rng", Rng), ("keep_bits", C.c_void_p)]
+                ("hd", C.c_int), ("scale", C.c_float), ("p", C.c_float), ("rng", Rng), ("keep_bits", C.c_void_p),
+                ("bf16", C.c_int)]
 
 
 class AttnBwdDesc(C.Structure):
@@ -87,7 +91,8 @@ class AttnBwdDesc(C.Structure):
                 ("d_o", C.c_void_p), ("lddo", C.c_int64), ("lse", C.c_void_p), ("delta", C.c_void_p),
                 ("dq", C.c_void_p), ("lddq", C.c_int64), ("dk", C.c_void_p), ("lddk", C.c_int64),
                 ("dv", C.c_void_p), ("lddv", C.c_int64), ("Lq", C.c_int), ("Lk", C.c_int), ("B", C.c_int),
-                ("H", C.c_int), ("hd", C.c_int), ("scale", C.c_float), ("p", C.c_float), ("rng", Rng), ("keep_bits", C.c_void_p)]
+                ("H", C.c_int), ("hd", C.c_int), ("scale", C.c_float), ("p", C.c_float), ("rng", Rng), ("keep_bits", C.c_void_p),
+                ("bf16", C.c_int)]
 
 
 class AdamDesc(C.Structure):
@@ -95,7 +100,7 @@ class AdamDesc(C.Structure):
                 ("active", C.c_void_p), ("steps", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p),
                 ("exp_avg_sq", C.c_void_p), ("partial", C.c_void_p), ("scalars", C.c_void_p),
                 ("n_chunks", C.c_int), ("n_params", C.c_int), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
-                ("eps", C.c_float), ("weight_decay", C.c_float), ("max_norm", C.c_float)]
+                ("eps", C.c_float), ("weight_decay", C.c_float), ("max_norm", C.c_float), ("shadow", C.c_void_p)]
 
 
 class OpDesc(C.Structure):

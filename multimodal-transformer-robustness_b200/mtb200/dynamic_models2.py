@@ -74,7 +74,7 @@ class Conv1x1FrontEnd(nn.Module):
         B, L, D = x.shape
         x2, W = x.reshape(B * L, D), self.weight.view(self.d, self.d_in)
         K = self.d_in
-        if K % 4 != 0 and x.is_cuda and _lib.lib.mtb_get_gemm_mode() == 1:
+        if K % 4 != 0 and x.is_cuda and _lib.lib.mtb_get_gemm_mode() >= 1:
             # TMA needs 16-byte row pitches: feature counts such as 74 / 35 (MOSEI audio / video) are zero-padded to a
             # multiple of 4 so the projection and its weight gradient run on the tcgen05 engine instead of the fp32
             # fallback (the padded columns multiply zeros; autograd slices the weight gradient back)

@@ -37,17 +37,22 @@ F4 = 4  # bytes per float
 
 
 class Mat:
-    """[rows, cols] fp32 matrix at a raw device address with leading dimension ld (floats)."""
-    __slots__ = ("ptr", "rows", "cols", "ld")
+    """[rows, cols] matrix at a raw device address with leading dimension ld (ELEMENTS); es = bytes per element:
+    4 = fp32, 2 = bfloat16 (the bf16 data path keeps GEMM / attention operands in bf16, everything else in fp32)."""
+    __slots__ = ("ptr", "rows", "cols", "ld", "es")
 
-    def __init__(self, ptr: int, rows: int, cols: int, ld: Optional[int] = None):
-        self.ptr, self.rows, self.cols, self.ld = ptr, rows, cols, (cols if ld is None else ld)
+    def __init__(self, ptr: int, rows: int, cols: int, ld: Optional[int] = None, es: int = 4):
+        self.ptr, self.rows, self.cols, self.ld, self.es = ptr, rows, cols, (cols if ld is None else ld), es
 
     def cols_slice(self, c0: int, n: int) -> "Mat":
-        return Mat(self.ptr + F4 * c0, self.rows, n, self.ld)
+        return Mat(self.ptr + self.es * c0, self.rows, n, self.ld, self.es)
 
     def rows_slice(self, r0: int, n: int) -> "Mat":
-        return Mat(self.ptr + F4 * r0 * self.ld, n, self.cols, self.ld)
+        return Mat(self.ptr + self.es * r0 * self.ld, n, self.cols, self.ld, self.es)
+
+    @property
+    def h(self) -> int:
+        return 1 if self.es == 2 else 0
 
 
 class Arena:
@@ -70,14 +75,14 @@ class Arena:
         self.peak = max(self.peak, self.off)
         return p
 
-    def mat(self, rows: int, cols: int) -> Mat:
-        return Mat(self.alloc(rows * cols), rows, cols)
+    def mat(self, rows: int, cols: int, es: int = 4) -> Mat:
+        return Mat(self.alloc((rows * cols * es + 3) // 4), rows, cols, None, es)
 
     def view(self, m: Mat) -> torch.Tensor:
         """torch view of a contiguous Mat living in this arena"""
         assert m.ld == m.cols
         o = m.ptr - self.base
-        return self.buf[o:o + m.rows * m.cols * F4].view(torch.float32).view(m.rows, m.cols)
+        return self.buf[o:o + m.rows * m.cols * m.es].view(torch.float32 if m.es == 4 else torch.bfloat16).view(m.rows, m.cols)
 
 
 class CountingArena(Arena):
@@ -130,7 +135,7 @@ def _rank(what: str) -> Tuple[int, int]:
 
 class EncPlan:
     """memoised launches of one encoder invocation: [(rank, Op with unfinalised descriptor list)]"""
-    __slots__ = ("spec", "fwd", "bwd", "active_params", "sites")
+    __slots__ = ("spec", "fwd", "bwd", "active_params", "sites", "used_weights", "acts")
 
 
 STEP_SPAN = 1 << 34            # Philox offset advance per training step (larger than any encoder's span)
@@ -242,9 +247,15 @@ class PlanBuilder:
         self.fwd: List = []
         self.bwd: List = []          # built in execution order by the backward builders
         self.sites: Dict[str, Tuple[int, int, float]] = {}
+        self.acts: Dict[str, tuple] = {}     # ReLU sites: tag -> (Mat of the post-activation tensor, first row) -- test support
         self.rng_off = 0
         self.active_params: List[torch.nn.Parameter] = []
         self._active_ids = set()
+        self.used_weights: List[torch.nn.Parameter] = []      # bf16 data path: weights read through their bf16 shadow
+        self._used_ids = set()
+        # element size of GEMM / attention operands between kernels: bf16 data path (gemm mode 2) or fp32
+        self.bf = lib.mtb_get_gemm_mode() == 2
+        self.H = 2 if self.bf else 4
 
     # -- helpers
     def rng(self, tag: str, n_elems: int, p: float, last_rows: bool = False) -> Rng:
@@ -268,6 +279,39 @@ class PlanBuilder:
             self.active_params.append(param)
         return self.eng.grad_ptr(param)
 
+    def wptr(self, W: torch.nn.Parameter, es: int, row0: int = 0) -> int:
+        """address of row `row0` of a weight as a GEMM operand of element size `es`: the fp32 parameter itself, or its
+        bf16 shadow (same shape and leading dimension in elements)"""
+        if es == 2:
+            if id(W) not in self._used_ids:
+                self._used_ids.add(id(W))
+                self.used_weights.append(W)
+            return self.eng.shadow_ptr(W) + 2 * row0 * W.stride(0)
+        return W.data_ptr() + F4 * row0 * W.stride(0)
+
+    def lin(self, X: Mat, W, b, Y: Mat, N: int, K: int, *, row0: int = 0, row_idx=None, col_idx=None, act: int = 0, p: float = 0.0,
+            rng: Rng = None, rsegs: Segs = None, csegs: Segs = None) -> LinearDesc:
+        """Y[M, N] = act(X[M, K] . W[row0 : row0 + N]^T + b); operand types follow the Mats"""
+        return LinearDesc(X.ptr, X.ld, self.wptr(W, X.es, row0), W.stride(0), (b.data_ptr() + F4 * row0) if b is not None else None,
+                          row_idx, col_idx, Y.ptr, Y.ld, X.rows, N, K, act, p, rng if rng is not None else _NO_RNG,
+                          rsegs if rsegs is not None else _NO_SEGS, csegs if csegs is not None else _NO_SEGS, X.h, Y.h)
+
+    def lin_bwd(self, dY: Mat, W, N: int, K: int, *, row0: int = 0, Yact: Optional[Mat] = None, X: Optional[Mat] = None,
+                dX: Optional[Mat] = None, acc: int = 0, gW: bool = False, gb: bool = False, b=None, row_idx=None, col_idx=None,
+                act: int = 0, p: float = 0.0, scratch: Optional[int] = None, rsegs: Segs = None, csegs: Segs = None) -> LinearBwdDesc:
+        """dX (+)= dY' . W[row0 : row0 + N];  dW[row0 : row0 + N] += dY'^T . X;  db[row0 : row0 + N] += colsum(dY')"""
+        gWp = self.grad_ptr(W) if gW else None
+        gbp = self.grad_ptr(b) if (gb and b is not None) else None
+        if gWp is not None:
+            gWp += F4 * row0 * W.stride(0)
+        if gbp is not None:
+            gbp += F4 * row0
+        return LinearBwdDesc(dY.ptr, dY.ld, Yact.ptr if Yact is not None else None, Yact.ld if Yact is not None else 0,
+                             X.ptr if X is not None else None, X.ld if X is not None else 0, self.wptr(W, dY.es, row0), W.stride(0),
+                             row_idx, col_idx, dX.ptr if dX is not None else None, dX.ld if dX is not None else 0, acc, gWp, gbp,
+                             dY.rows, N, K, act, p, scratch, rsegs if rsegs is not None else _NO_SEGS,
+                             csegs if csegs is not None else _NO_SEGS, dY.h, dX.h if dX is not None else 0)
+
     def emit(self, lst, fn, dtype, descs, what):
         descs = [d for d in descs if d is not None]
         if descs:
@@ -278,6 +322,7 @@ class PlanBuilder:
         A = self.arena
         tr = self.training
         ng = self.need_grad
+        Hs = self.H
         # 1. embed (q, k, v streams) -------------------------------------------------------
         descs = []
         for e in group:
@@ -306,15 +351,15 @@ class PlanBuilder:
             idx = e.mask.idx.data_ptr() if e.mask is not None else None
             if e.n_layers == 0:
                 ln = e.enc.layer_norm.ln
-                dst = e.out
+                dst = e.out                         # encoder outputs stay fp32 (they feed embed / concat / head)
             else:
                 ln = e.enc._ll[0]._lns[0].ln
-                dst = A.mat(Tq, e.E)
+                dst = A.mat(Tq, e.E, Hs)
             st = (A.alloc(Tq), A.alloc(Tq)) if ng else (None, None)
             e.saved["ln_first"] = (ln, dst, st)
             e.saved["xn"] = dst
             descs.append(ResLnDesc(e.saved["x0"].ptr, e.E, None, 0, None, 0, dst.ptr, dst.ld, ln.weight.data_ptr(),
-                                   ln.bias.data_ptr(), idx, st[0], st[1], Tq, e.E, ln.eps, 0.0, _NO_RNG))
+                                   ln.bias.data_ptr(), idx, st[0], st[1], Tq, e.E, ln.eps, 0.0, _NO_RNG, 0, dst.h))
         self.emit(self.fwd, lib.mtb_resln_fwd, ResLnDesc, descs, "ln_first")
 
         max_layers = max((e.n_layers for e in group), default=0)
@@ -331,11 +376,11 @@ class PlanBuilder:
                 S = e.saved["layers"][i]
                 ln = e.enc._ll[i]._lns[0].ln
                 for nm in ("k", "v"):
-                    dst = A.mat(Tk, e.E)
+                    dst = A.mat(Tk, e.E, Hs)
                     st = (A.alloc(Tk), A.alloc(Tk)) if ng else (None, None)
                     S[nm + "n"] = (dst, st)
                     descs.append(ResLnDesc(e.saved["x" + nm].ptr, e.E, None, 0, None, 0, dst.ptr, e.E, ln.weight.data_ptr(),
-                                           ln.bias.data_ptr(), None, st[0], st[1], Tk, e.E, ln.eps, 0.0, _NO_RNG))
+                                           ln.bias.data_ptr(), None, st[0], st[1], Tk, e.E, ln.eps, 0.0, _NO_RNG, 0, dst.h))
         self.emit(self.fwd, lib.mtb_resln_fwd, ResLnDesc, descs, "ln0_kv_all")
         for i in range(max_layers):
             act = [e for e in group if e.n_layers > i]
@@ -351,31 +396,25 @@ class PlanBuilder:
                 W, b = sa.in_proj_weight, sa.in_proj_bias
                 S["xn_in"] = e.saved["xn"]
                 r0, Tr = _qrows(e, i)
+                cidx = e.mask.idx.data_ptr() if e.mask is not None else None
                 if not e.cross and Tr != Tq:
                     # pruned final layer: q from the last step only, k / v (packed) from every step
-                    cidx = e.mask.idx.data_ptr() if e.mask is not None else None
                     xn = e.saved["xn"]
                     xq = xn.rows_slice(r0, Tr)
-                    q, kv = A.mat(Tr, D), A.mat(Tq, 2 * D)
+                    q, kv = A.mat(Tr, D, Hs), A.mat(Tq, 2 * D, Hs)
                     S["q_last"], S["kv"] = q, kv
-                    descs.append(LinearDesc(xq.ptr, xq.ld, W.data_ptr(), W.stride(0), b.data_ptr(), None, cidx,
-                                            q.ptr, q.ld, Tr, D, e.E, 0, 0.0, _NO_RNG, _NO_SEGS, _segs(e.mask)))
-                    descs.append(LinearDesc(xn.ptr, xn.ld, W.data_ptr() + F4 * D * W.stride(0), W.stride(0), b.data_ptr() + F4 * D, None, cidx,
-                                            kv.ptr, kv.ld, Tq, 2 * D, e.E, 0, 0.0, _NO_RNG, _NO_SEGS, _segs(e.mask)))
+                    descs.append(self.lin(xq, W, b, q, D, e.E, col_idx=cidx, csegs=_segs(e.mask)))
+                    descs.append(self.lin(xn, W, b, kv, 2 * D, e.E, row0=D, col_idx=cidx, csegs=_segs(e.mask)))
                 elif not e.cross:
-                    qkv = A.mat(Tq, 3 * D)
+                    qkv = A.mat(Tq, 3 * D, Hs)
                     S["qkv"] = qkv
-                    cidx = e.mask.idx.data_ptr() if e.mask is not None else None
-                    descs.append(LinearDesc(e.saved["xn"].ptr, e.saved["xn"].ld, W.data_ptr(), W.stride(0), b.data_ptr(), None, cidx,
-                                            qkv.ptr, qkv.ld, Tq, 3 * D, e.E, 0, 0.0, _NO_RNG, _NO_SEGS, _segs(e.mask)))
+                    descs.append(self.lin(e.saved["xn"], W, b, qkv, 3 * D, e.E, col_idx=cidx, csegs=_segs(e.mask)))
                 else:
-                    q, k, v = A.mat(Tq, D), A.mat(Tk, D), A.mat(Tk, D)
+                    q, k, v = A.mat(Tq, D, Hs), A.mat(Tk, D, Hs), A.mat(Tk, D, Hs)
                     S["q"], S["k"], S["v"] = q, k, v
                     srcs = (e.saved["xn"], S["kn"][0], S["vn"][0])
-                    for part, (src, dst, T) in enumerate(zip(srcs, (q, k, v), (Tq, Tk, Tk))):
-                        descs.append(LinearDesc(src.ptr, src.ld, W.data_ptr() + F4 * part * D * W.stride(0), W.stride(0),
-                                                b.data_ptr() + F4 * part * D, None, None, dst.ptr, dst.ld, T, D, e.E, 0, 0.0,
-                                                _NO_RNG, _NO_SEGS, _NO_SEGS))
+                    for part, (src, dst) in enumerate(zip(srcs, (q, k, v))):
+                        descs.append(self.lin(src, W, b, dst, D, e.E, row0=part * D))
             self.emit(self.fwd, lib.mtb_linear_fwd, LinearDesc, descs, f"in_proj[{i}]")
             # c. attention core ----------------------------------------------------------------
             descs = []
@@ -388,7 +427,7 @@ class PlanBuilder:
                 r0, Tr = _qrows(e, i)
                 pruned = Tr != Tq
                 Lq_a = 1 if pruned else e.Lq          # pruned: one query step against all Lk keys (no key is masked for the last step)
-                o = A.mat(Tr, D)
+                o = A.mat(Tr, D, Hs)
                 lse = A.alloc(e.B * H * Lq_a)
                 S["o"], S["lse"] = o, lse
                 pa = self.p(e.tag, sa.attn_dropout)
@@ -404,10 +443,10 @@ class PlanBuilder:
                     qm, km, vm = S["q"], S["k"], S["v"]
                 S["qkv_mats"] = (qm, km, vm)
                 # keep bits of the attention dropout, stored by the forward kernel for the two backward kernels
-                bits = A.alloc(e.B * H * Lq_a * ((e.Lk + 31) // 32)) if (ng and pa > 0.0 and lib.mtb_get_gemm_mode() == 1) else None
+                bits = A.alloc(e.B * H * Lq_a * ((e.Lk + 31) // 32)) if (ng and pa > 0.0 and lib.mtb_get_gemm_mode() >= 1) else None
                 S["keep_bits"] = bits
                 descs.append(AttnDesc(qm.ptr, qm.ld, km.ptr, km.ld, vm.ptr, vm.ld, o.ptr, o.ld, lse, Lq_a, e.Lk, e.B, H, hd,
-                                      hd ** -0.5, pa, r, bits))
+                                      hd ** -0.5, pa, r, bits, o.h))
             self.emit(self.fwd, lib.mtb_attn_fwd, AttnDesc, descs, f"attn[{i}]")
             # d. out-projection ----------------------------------------------------------------
             descs = []
@@ -416,12 +455,10 @@ class PlanBuilder:
                 sa = e.enc._ll[i].self_attn
                 D = sa.num_heads * sa.head_dim
                 r0, Tq = _qrows(e, i)
-                a = A.mat(Tq, e.E)
+                a = A.mat(Tq, e.E, Hs)
                 S["a"] = a
-                Wo, bo = sa.out_proj.weight, sa.out_proj.bias
                 ridx = e.mask.idx.data_ptr() if e.mask is not None else None
-                descs.append(LinearDesc(S["o"].ptr, S["o"].ld, Wo.data_ptr(), Wo.stride(0), bo.data_ptr(), ridx, None, a.ptr, a.ld,
-                                        Tq, e.E, D, 0, 0.0, _NO_RNG, _segs(e.mask), _NO_SEGS))
+                descs.append(self.lin(S["o"], sa.out_proj.weight, sa.out_proj.bias, a, e.E, D, row_idx=ridx, rsegs=_segs(e.mask)))
             self.emit(self.fwd, lib.mtb_linear_fwd, LinearDesc, descs, f"out_proj[{i}]")
             # e. dropout + residual + LN1 ------------------------------------------------------
             descs = []
@@ -432,14 +469,15 @@ class PlanBuilder:
                 r0, Tq = _qrows(e, i)
                 x_prev = e.saved["x0"] if i == 0 else e.saved["layers"][i - 1]["x2"]
                 x_prev = x_prev.rows_slice(r0, Tq)
-                x1, xn1 = A.mat(Tq, e.E), A.mat(Tq, e.E)
+                x1, xn1 = A.mat(Tq, e.E), A.mat(Tq, e.E, Hs)
                 st = (A.alloc(Tq), A.alloc(Tq)) if ng else (None, None)
                 pr = self.p(e.tag, layer.res_dropout)
                 r = self.rng(f"{e.tag}layers.{i}.res0", Tq * e.E, pr, last_rows=r0 > 0)
                 S["x1"], S["xn1"], S["st1"], S["rng_res0"] = x1, xn1, st, (r, pr)
                 idx = e.mask.idx.data_ptr() if e.mask is not None else None
                 descs.append(ResLnDesc(x_prev.ptr, x_prev.ld, S["a"].ptr, S["a"].ld, x1.ptr, x1.ld, xn1.ptr, xn1.ld,
-                                       ln.weight.data_ptr(), ln.bias.data_ptr(), idx, st[0], st[1], Tq, e.E, ln.eps, pr, r))
+                                       ln.weight.data_ptr(), ln.bias.data_ptr(), idx, st[0], st[1], Tq, e.E, ln.eps, pr, r,
+                                       S["a"].h, xn1.h))
             self.emit(self.fwd, lib.mtb_resln_fwd, ResLnDesc, descs, f"res_ln1[{i}]")
             # f. fc1 (+ReLU, dropout)  g. fc2 ----------------------------------------------------
             d1, d2 = [], []
@@ -448,17 +486,16 @@ class PlanBuilder:
                 layer = e.enc._ll[i]
                 Fa = min(layer.active_hidden_out_fc1, layer.fc1.dim_out)
                 r0, Tq = _qrows(e, i)
-                h, y = A.mat(Tq, Fa), A.mat(Tq, e.E)
+                h, y = A.mat(Tq, Fa, Hs), A.mat(Tq, e.E, Hs)
                 S["h"], S["y"], S["F"] = h, y, Fa
                 pl = self.p(e.tag, layer.relu_dropout)
                 r = self.rng(f"{e.tag}layers.{i}.relu", Tq * Fa, pl, last_rows=r0 > 0)
                 S["p_relu"] = pl
-                W1, b1, W2, b2 = layer.fc1.l.weight, layer.fc1.l.bias, layer.fc2.l.weight, layer.fc2.l.bias
+                self.acts[f"{e.tag}layers.{i}.relu"] = (h, r0)
                 midx = e.mask.idx.data_ptr() if e.mask is not None else None
-                d1.append(LinearDesc(S["xn1"].ptr, S["xn1"].ld, W1.data_ptr(), W1.stride(0), b1.data_ptr(), None, midx, h.ptr, h.ld,
-                                     Tq, Fa, e.E, 1, pl, r, _NO_SEGS, _segs(e.mask)))
-                d2.append(LinearDesc(h.ptr, h.ld, W2.data_ptr(), W2.stride(0), b2.data_ptr(), midx, None, y.ptr, y.ld,
-                                     Tq, e.E, Fa, 0, 0.0, _NO_RNG, _segs(e.mask), _NO_SEGS))
+                d1.append(self.lin(S["xn1"], layer.fc1.l.weight, layer.fc1.l.bias, h, Fa, e.E, col_idx=midx, act=1, p=pl, rng=r,
+                                   csegs=_segs(e.mask)))
+                d2.append(self.lin(h, layer.fc2.l.weight, layer.fc2.l.bias, y, e.E, Fa, row_idx=midx, rsegs=_segs(e.mask)))
             self.emit(self.fwd, lib.mtb_linear_fwd, LinearDesc, d1, f"fc1[{i}]")
             self.emit(self.fwd, lib.mtb_linear_fwd, LinearDesc, d2, f"fc2[{i}]")
             # h. dropout + residual + next LN0 / final LN ---------------------------------------
@@ -470,14 +507,15 @@ class PlanBuilder:
                 last = (i + 1 == e.n_layers)
                 ln = e.enc.layer_norm.ln if last else e.enc._ll[i + 1]._lns[0].ln
                 x2 = A.mat(Tq, e.E)
-                dst = e.out.rows_slice(r0, Tq) if last else A.mat(Tq, e.E)       # pruned: only the last step of e.out is defined
+                dst = e.out.rows_slice(r0, Tq) if last else A.mat(Tq, e.E, Hs)   # pruned: only the last step of e.out is defined
                 st = (A.alloc(Tq), A.alloc(Tq)) if ng else (None, None)
                 pr = self.p(e.tag, layer.res_dropout)
                 r = self.rng(f"{e.tag}layers.{i}.res1", Tq * e.E, pr, last_rows=r0 > 0)
                 S["x2"], S["xn_next"], S["st2"], S["rng_res1"], S["ln_next"] = x2, dst, st, (r, pr), ln
                 idx = e.mask.idx.data_ptr() if e.mask is not None else None
                 descs.append(ResLnDesc(S["x1"].ptr, S["x1"].ld, S["y"].ptr, S["y"].ld, x2.ptr, x2.ld, dst.ptr, dst.ld,
-                                       ln.weight.data_ptr(), ln.bias.data_ptr(), idx, st[0], st[1], Tq, e.E, ln.eps, pr, r))
+                                       ln.weight.data_ptr(), ln.bias.data_ptr(), idx, st[0], st[1], Tq, e.E, ln.eps, pr, r,
+                                       S["y"].h, dst.h))
                 e.saved["xn"] = dst
             self.emit(self.fwd, lib.mtb_resln_fwd, ResLnDesc, descs, f"res_ln2[{i}]")
 
@@ -495,7 +533,8 @@ class PlanBuilder:
                 rr = Rng(rng.seed, rng.offset + (r0 * e.E) // 4, rng.dev)
             return ResLnBwdDesc(a.ptr, a.ld, gx_part.ptr if gx_part is not None else None, gx_part.ld if gx_part is not None else 0,
                                 b2.ptr, b2.ld, st[0] + F4 * r0, st[1] + F4 * r0, gamma_ptr, idx_ptr, c.ptr, c.ld,
-                                da.ptr if da is not None else None, da.ld if da is not None else 0, dgamma, dbeta, rows, e.E, p, rr, dbias)
+                                da.ptr if da is not None else None, da.ld if da is not None else 0, dgamma, dbeta, rows, e.E, p, rr, dbias,
+                                a.h, da.h if da is not None else 0)
         if gx is None or gx_r0 == 0:
             return [one(0, T, gx)]
         assert (gx_r0 * e.E) % 4 == 0
@@ -507,6 +546,7 @@ class PlanBuilder:
         encoder; allocates and fills e.d_q_in (and d_k_in / d_v_in) as contiguous [T, E] mats."""
         A = self.arena
         none_rng = _NO_RNG
+        Hs = self.H
         max_layers = max((e.n_layers for e in group), default=0)
         # running gradients per encoder: g_xn (wrt the LN output feeding the next block), g_x (residual path)
         for e in group:
@@ -518,7 +558,7 @@ class PlanBuilder:
         # Tensor-core engine: the weight-gradient GEMMs of a layer do not feed the backward chain, so they are
         # split off the four linear backward calls and issued as ONE grouped launch per stage-layer
         # (4-6 problems per branch, split over tokens) -- fewer launches, fuller SMs.
-        defer = lib.mtb_get_gemm_mode() == 1
+        defer = lib.mtb_get_gemm_mode() >= 1
         for i in reversed(range(max_layers)):
             act = [e for e in group if e.n_layers > i]
             wg_descs = []
@@ -529,7 +569,7 @@ class PlanBuilder:
                 r0, Tq = _qrows(e, i)
                 ln = S["ln_next"]
                 masked = e.mask is not None
-                g_x1r, g_y = A.mat(Tq, e.E), A.mat(Tq, e.E)
+                g_x1r, g_y = A.mat(Tq, e.E), A.mat(Tq, e.E, Hs)
                 S["g_x1r"], S["g_y"] = g_x1r, g_y
                 gx = e.saved["g_x"]
                 gxn = e.saved["g_xn"].rows_slice(r0, Tq)          # pruned final layer: only the last step carries gradient
@@ -545,30 +585,24 @@ class PlanBuilder:
                 S = e.saved["layers"][i]
                 layer = e.enc._ll[i]
                 Tq, Fa = _qrows(e, i)[1], S["F"]
-                W1, b1, W2, b2 = layer.fc1.l.weight, layer.fc1.l.bias, layer.fc2.l.weight, layer.fc2.l.bias
+                W1, b1, W2 = layer.fc1.l.weight, layer.fc1.l.bias, layer.fc2.l.weight
                 midx = e.mask.idx.data_ptr() if e.mask is not None else None
-                g_h, g_xn1 = A.mat(Tq, Fa), A.mat(Tq, e.E)
-                scratch = A.alloc(Tq * Fa)
+                sg = _segs(e.mask)
+                g_h, g_xn1 = A.mat(Tq, Fa, Hs), A.mat(Tq, e.E, Hs)
+                scratch = A.mat(Tq, Fa, Hs)
                 S["g_xn1"] = g_xn1
                 if defer:
-                    d2.append(LinearBwdDesc(S["g_y"].ptr, S["g_y"].ld, None, 0, None, 0, W2.data_ptr(), W2.stride(0), midx, None,
-                                            g_h.ptr, g_h.ld, 0, None, None, Tq, e.E, Fa, 0, 0.0, None, _segs(e.mask), _NO_SEGS))
-                    wg_descs.append(LinearBwdDesc(S["g_y"].ptr, S["g_y"].ld, None, 0, S["h"].ptr, S["h"].ld, W2.data_ptr(), W2.stride(0), midx, None,
-                                                  None, 0, 0, self.grad_ptr(W2), None, Tq, e.E, Fa, 0, 0.0, None, _segs(e.mask), _NO_SEGS))
+                    d2.append(self.lin_bwd(S["g_y"], W2, e.E, Fa, dX=g_h, row_idx=midx, rsegs=sg))
+                    wg_descs.append(self.lin_bwd(S["g_y"], W2, e.E, Fa, X=S["h"], gW=True, row_idx=midx, rsegs=sg))
                     # fc1: the dgrad call materialises dY' = dY*[h>0]/(1-p) into `scratch` (bias grad fused there);
                     # the deferred wgrad reads it back as a plain dY
-                    d1.append(LinearBwdDesc(g_h.ptr, g_h.ld, S["h"].ptr, S["h"].ld, None, 0, W1.data_ptr(), W1.stride(0), None, midx,
-                                            g_xn1.ptr, g_xn1.ld, 0, None, self.grad_ptr(b1), Tq, Fa, e.E, 1, S["p_relu"], scratch,
-                                            _NO_SEGS, _segs(e.mask)))
-                    wg_descs.append(LinearBwdDesc(scratch, Fa, None, 0, S["xn1"].ptr, S["xn1"].ld, W1.data_ptr(), W1.stride(0), None, midx,
-                                                  None, 0, 0, self.grad_ptr(W1), None, Tq, Fa, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
+                    d1.append(self.lin_bwd(g_h, W1, Fa, e.E, Yact=S["h"], dX=g_xn1, gb=True, b=b1, col_idx=midx, act=1, p=S["p_relu"],
+                                           scratch=scratch.ptr, csegs=sg))
+                    wg_descs.append(self.lin_bwd(scratch, W1, Fa, e.E, X=S["xn1"], gW=True, col_idx=midx, csegs=sg))
                 else:
-                    d2.append(LinearBwdDesc(S["g_y"].ptr, S["g_y"].ld, None, 0, S["h"].ptr, S["h"].ld, W2.data_ptr(), W2.stride(0), midx, None,
-                                            g_h.ptr, g_h.ld, 0, self.grad_ptr(W2), None, Tq, e.E, Fa, 0, 0.0, None,
-                                            _segs(e.mask), _NO_SEGS))
-                    d1.append(LinearBwdDesc(g_h.ptr, g_h.ld, S["h"].ptr, S["h"].ld, S["xn1"].ptr, S["xn1"].ld, W1.data_ptr(), W1.stride(0), None, midx,
-                                            g_xn1.ptr, g_xn1.ld, 0, self.grad_ptr(W1), self.grad_ptr(b1), Tq, Fa, e.E, 1, S["p_relu"], scratch,
-                                            _NO_SEGS, _segs(e.mask)))
+                    d2.append(self.lin_bwd(S["g_y"], W2, e.E, Fa, X=S["h"], dX=g_h, gW=True, row_idx=midx, rsegs=sg))
+                    d1.append(self.lin_bwd(g_h, W1, Fa, e.E, Yact=S["h"], X=S["xn1"], dX=g_xn1, gW=True, gb=True, b=b1, col_idx=midx,
+                                           act=1, p=S["p_relu"], scratch=scratch.ptr, csegs=sg))
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, d2, f"fc2_bwd[{i}]")
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, d1, f"fc1_bwd[{i}]")
             # e'. res_ln1 backward -> g_x (residual into the layer input), g_a
@@ -579,7 +613,7 @@ class PlanBuilder:
                 ln = layer._lns[1].ln
                 r0, Tq = _qrows(e, i)
                 masked = e.mask is not None
-                g_xr, g_a = A.mat(Tq, e.E), A.mat(Tq, e.E)
+                g_xr, g_a = A.mat(Tq, e.E), A.mat(Tq, e.E, Hs)
                 S["g_a"] = g_a
                 e.saved["g_x"] = g_xr
                 e.saved["g_x_r0"] = r0                           # rows [r0, T) only when this layer was pruned
@@ -588,7 +622,8 @@ class PlanBuilder:
                                           S["st1"][0], S["st1"][1], ln.weight.data_ptr(), e.mask.idx.data_ptr() if masked else None,
                                           g_xr.ptr, g_xr.ld, g_a.ptr, g_a.ld,
                                           None if masked else self.grad_ptr(ln.weight), None if masked else self.grad_ptr(ln.bias),
-                                          Tq, e.E, pr, r, self.grad_ptr(layer.self_attn.out_proj.bias)))   # out-proj bias grad, fused
+                                          Tq, e.E, pr, r, self.grad_ptr(layer.self_attn.out_proj.bias),      # out-proj bias grad, fused
+                                          S["g_xn1"].h, g_a.h))
             self.emit(self.bwd, lib.mtb_resln_bwd, ResLnBwdDesc, descs, f"res_ln1_bwd[{i}]")
             # d'. out-projection backward
             descs = []
@@ -597,19 +632,16 @@ class PlanBuilder:
                 sa = e.enc._ll[i].self_attn
                 D = sa.num_heads * sa.head_dim
                 Tq = _qrows(e, i)[1]
-                Wo, bo = sa.out_proj.weight, sa.out_proj.bias
+                Wo = sa.out_proj.weight
                 ridx = e.mask.idx.data_ptr() if e.mask is not None else None
-                g_o = A.mat(Tq, D)
+                sg = _segs(e.mask)
+                g_o = A.mat(Tq, D, Hs)
                 S["g_o"] = g_o
                 if defer:
-                    descs.append(LinearBwdDesc(S["g_a"].ptr, S["g_a"].ld, None, 0, None, 0, Wo.data_ptr(), Wo.stride(0), ridx, None,
-                                               g_o.ptr, g_o.ld, 0, None, None, Tq, e.E, D, 0, 0.0, None, _segs(e.mask), _NO_SEGS))
-                    wg_descs.append(LinearBwdDesc(S["g_a"].ptr, S["g_a"].ld, None, 0, S["o"].ptr, S["o"].ld, Wo.data_ptr(), Wo.stride(0), ridx, None,
-                                                  None, 0, 0, self.grad_ptr(Wo), None, Tq, e.E, D, 0, 0.0, None, _segs(e.mask), _NO_SEGS))
+                    descs.append(self.lin_bwd(S["g_a"], Wo, e.E, D, dX=g_o, row_idx=ridx, rsegs=sg))
+                    wg_descs.append(self.lin_bwd(S["g_a"], Wo, e.E, D, X=S["o"], gW=True, row_idx=ridx, rsegs=sg))
                 else:
-                    descs.append(LinearBwdDesc(S["g_a"].ptr, S["g_a"].ld, None, 0, S["o"].ptr, S["o"].ld, Wo.data_ptr(), Wo.stride(0), ridx, None,
-                                               g_o.ptr, g_o.ld, 0, self.grad_ptr(Wo), None, Tq, e.E, D, 0, 0.0, None,
-                                               _segs(e.mask), _NO_SEGS))
+                    descs.append(self.lin_bwd(S["g_a"], Wo, e.E, D, X=S["o"], dX=g_o, gW=True, row_idx=ridx, rsegs=sg))
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, descs, f"out_proj_bwd[{i}]")
             # c'. attention backward
             descs = []
@@ -624,21 +656,21 @@ class PlanBuilder:
                 pruned = Tr != Tq
                 Lq_a = 1 if pruned else e.Lq
                 if pruned:
-                    dq, dkv = A.mat(Tr, D), A.mat(Tq, 2 * D)
+                    dq, dkv = A.mat(Tr, D, Hs), A.mat(Tq, 2 * D, Hs)
                     S["dq_last"], S["dkv"] = dq, dkv
                     dk, dv = dkv.cols_slice(0, D), dkv.cols_slice(D, D)
                 elif not e.cross:
-                    dqkv = A.mat(Tq, 3 * D)
+                    dqkv = A.mat(Tq, 3 * D, Hs)
                     S["dqkv"] = dqkv
                     dq, dk, dv = dqkv.cols_slice(0, D), dqkv.cols_slice(D, D), dqkv.cols_slice(2 * D, D)
                 else:
-                    dq, dk, dv = A.mat(Tq, D), A.mat(Tk, D), A.mat(Tk, D)
+                    dq, dk, dv = A.mat(Tq, D, Hs), A.mat(Tk, D, Hs), A.mat(Tk, D, Hs)
                     S["dq"], S["dk"], S["dv"] = dq, dk, dv
                 delta = A.alloc(e.B * H * Lq_a)
                 r, pa = S["rng_attn"]
                 descs.append(AttnBwdDesc(qm.ptr, qm.ld, km.ptr, km.ld, vm.ptr, vm.ld, S["o"].ptr, S["o"].ld, S["g_o"].ptr, S["g_o"].ld,
                                          S["lse"], delta, dq.ptr, dq.ld, dk.ptr, dk.ld, dv.ptr, dv.ld, Lq_a, e.Lk, e.B, H, hd,
-                                         hd ** -0.5, pa, r, S.get("keep_bits")))
+                                         hd ** -0.5, pa, r, S.get("keep_bits"), qm.h))
             self.emit(self.bwd, lib.mtb_attn_bwd, AttnBwdDesc, descs, f"attn_bwd[{i}]")
             # b'. in-projection backward
             descs, descs_q = [], []
@@ -648,60 +680,41 @@ class PlanBuilder:
                 D = sa.num_heads * sa.head_dim
                 Tq, Tk = e.Lq * e.B, e.Lk * e.B
                 W, b = sa.in_proj_weight, sa.in_proj_bias
-                gW, gb = self.grad_ptr(W), self.grad_ptr(b)
                 xn_in = S["xn_in"]
-                g_xn = A.mat(Tq, e.E)
+                g_xn = A.mat(Tq, e.E, Hs)
                 e.saved["g_xn"] = g_xn
                 r0, Tr = _qrows(e, i)
+                cidx = e.mask.idx.data_ptr() if e.mask is not None else None
+                sg = _segs(e.mask)
                 if not e.cross and Tr != Tq:
                     # pruned final layer: d(xn) = dkv . W[D:3D]  (every step)  +  dq . W[0:D]  (last step, second launch)
-                    cidx = e.mask.idx.data_ptr() if e.mask is not None else None
                     dq, dkv = S["dq_last"], S["dkv"]
                     xq = xn_in.rows_slice(r0, Tr)
                     g_q = g_xn.rows_slice(r0, Tr)
-                    Wkv = W.data_ptr() + F4 * D * W.stride(0)
-                    gWkv = (gW + F4 * D * W.stride(0)) if gW else None
-                    gbkv = (gb + F4 * D) if gb else None
                     if defer:
-                        descs.append(LinearBwdDesc(dkv.ptr, dkv.ld, None, 0, None, 0, Wkv, W.stride(0), None, cidx,
-                                                   g_xn.ptr, g_xn.ld, 0, None, None, Tq, 2 * D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
-                        descs_q.append(LinearBwdDesc(dq.ptr, dq.ld, None, 0, None, 0, W.data_ptr(), W.stride(0), None, cidx,
-                                                     g_q.ptr, g_q.ld, 1, None, None, Tr, D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
-                        wg_descs.append(LinearBwdDesc(dkv.ptr, dkv.ld, None, 0, xn_in.ptr, xn_in.ld, Wkv, W.stride(0), None, cidx,
-                                                      None, 0, 0, gWkv, gbkv, Tq, 2 * D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
-                        wg_descs.append(LinearBwdDesc(dq.ptr, dq.ld, None, 0, xq.ptr, xq.ld, W.data_ptr(), W.stride(0), None, cidx,
-                                                      None, 0, 0, gW, gb, Tr, D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
+                        descs.append(self.lin_bwd(dkv, W, 2 * D, e.E, row0=D, dX=g_xn, col_idx=cidx, csegs=sg))
+                        descs_q.append(self.lin_bwd(dq, W, D, e.E, dX=g_q, acc=1, col_idx=cidx, csegs=sg))
+                        wg_descs.append(self.lin_bwd(dkv, W, 2 * D, e.E, row0=D, X=xn_in, gW=True, gb=True, b=b, col_idx=cidx, csegs=sg))
+                        wg_descs.append(self.lin_bwd(dq, W, D, e.E, X=xq, gW=True, gb=True, b=b, col_idx=cidx, csegs=sg))
                     else:
-                        descs.append(LinearBwdDesc(dkv.ptr, dkv.ld, None, 0, xn_in.ptr, xn_in.ld, Wkv, W.stride(0), None, cidx,
-                                                   g_xn.ptr, g_xn.ld, 0, gWkv, gbkv, Tq, 2 * D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
-                        descs_q.append(LinearBwdDesc(dq.ptr, dq.ld, None, 0, xq.ptr, xq.ld, W.data_ptr(), W.stride(0), None, cidx,
-                                                     g_q.ptr, g_q.ld, 1, gW, gb, Tr, D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
+                        descs.append(self.lin_bwd(dkv, W, 2 * D, e.E, row0=D, X=xn_in, dX=g_xn, gW=True, gb=True, b=b, col_idx=cidx, csegs=sg))
+                        descs_q.append(self.lin_bwd(dq, W, D, e.E, X=xq, dX=g_q, acc=1, gW=True, gb=True, b=b, col_idx=cidx, csegs=sg))
                 elif not e.cross:
-                    cidx = e.mask.idx.data_ptr() if e.mask is not None else None
                     if defer:
-                        descs.append(LinearBwdDesc(S["dqkv"].ptr, S["dqkv"].ld, None, 0, None, 0, W.data_ptr(), W.stride(0), None, cidx,
-                                                   g_xn.ptr, g_xn.ld, 0, None, None, Tq, 3 * D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
-                        wg_descs.append(LinearBwdDesc(S["dqkv"].ptr, S["dqkv"].ld, None, 0, xn_in.ptr, xn_in.ld, W.data_ptr(), W.stride(0), None, cidx,
-                                                      None, 0, 0, gW, gb, Tq, 3 * D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
+                        descs.append(self.lin_bwd(S["dqkv"], W, 3 * D, e.E, dX=g_xn, col_idx=cidx, csegs=sg))
+                        wg_descs.append(self.lin_bwd(S["dqkv"], W, 3 * D, e.E, X=xn_in, gW=True, gb=True, b=b, col_idx=cidx, csegs=sg))
                     else:
-                        descs.append(LinearBwdDesc(S["dqkv"].ptr, S["dqkv"].ld, None, 0, xn_in.ptr, xn_in.ld, W.data_ptr(), W.stride(0), None, cidx,
-                                                   g_xn.ptr, g_xn.ld, 0, gW, gb, Tq, 3 * D, e.E, 0, 0.0, None, _NO_SEGS, _segs(e.mask)))
+                        descs.append(self.lin_bwd(S["dqkv"], W, 3 * D, e.E, X=xn_in, dX=g_xn, gW=True, gb=True, b=b, col_idx=cidx, csegs=sg))
                 else:
-                    g_kn, g_vn = A.mat(Tk, e.E), A.mat(Tk, e.E)
+                    g_kn, g_vn = A.mat(Tk, e.E, Hs), A.mat(Tk, e.E, Hs)
                     S["g_kn"], S["g_vn"] = g_kn, g_vn
                     srcs = (xn_in, S["kn"][0], S["vn"][0])
-                    for part, (dy, src, dst, T) in enumerate(zip((S["dq"], S["dk"], S["dv"]), srcs, (g_xn, g_kn, g_vn), (Tq, Tk, Tk))):
-                        gWp = (gW + F4 * part * D * W.stride(0)) if gW else None
-                        gbp = (gb + F4 * part * D) if gb else None
-                        Wp = W.data_ptr() + F4 * part * D * W.stride(0)
+                    for part, (dy, src, dst) in enumerate(zip((S["dq"], S["dk"], S["dv"]), srcs, (g_xn, g_kn, g_vn))):
                         if defer:
-                            descs.append(LinearBwdDesc(dy.ptr, dy.ld, None, 0, None, 0, Wp, W.stride(0), None, None, dst.ptr, dst.ld, 0,
-                                                       None, None, T, D, e.E, 0, 0.0, None, _NO_SEGS, _NO_SEGS))
-                            wg_descs.append(LinearBwdDesc(dy.ptr, dy.ld, None, 0, src.ptr, src.ld, Wp, W.stride(0), None, None, None, 0, 0,
-                                                          gWp, gbp, T, D, e.E, 0, 0.0, None, _NO_SEGS, _NO_SEGS))
+                            descs.append(self.lin_bwd(dy, W, D, e.E, row0=part * D, dX=dst))
+                            wg_descs.append(self.lin_bwd(dy, W, D, e.E, row0=part * D, X=src, gW=True, gb=True, b=b))
                         else:
-                            descs.append(LinearBwdDesc(dy.ptr, dy.ld, None, 0, src.ptr, src.ld, Wp, W.stride(0),
-                                                       None, None, dst.ptr, dst.ld, 0, gWp, gbp, T, D, e.E, 0, 0.0, None, _NO_SEGS, _NO_SEGS))
+                            descs.append(self.lin_bwd(dy, W, D, e.E, row0=part * D, X=src, dX=dst, gW=True, gb=True, b=b))
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, descs, f"in_proj_bwd[{i}]")
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, descs_q, f"in_proj_bwd_q[{i}]")
             self.emit(self.bwd, lib.mtb_linear_bwd, LinearBwdDesc, wg_descs, f"wgrad[{i}]")
@@ -723,7 +736,7 @@ class PlanBuilder:
                     gy = S["g_" + nm + "n"]
                     descs.append(ResLnBwdDesc(gy.ptr, gy.ld, None if first else acc.ptr, 0 if first else acc.ld, e.saved["x" + nm].ptr, e.E,
                                               st[0], st[1], ln.weight.data_ptr(), None, acc.ptr, acc.ld, None, 0,
-                                              self.grad_ptr(ln.weight), self.grad_ptr(ln.bias), Tk, e.E, 0.0, none_rng, None))
+                                              self.grad_ptr(ln.weight), self.grad_ptr(ln.bias), Tk, e.E, 0.0, none_rng, None, gy.h, 0))
             self.emit(self.bwd, lib.mtb_resln_bwd, ResLnBwdDesc, descs, f"ln0_kv_bwd[{i}]")
         # first LayerNorm backward -> g_x0
         descs = []
@@ -772,8 +785,9 @@ class PlanBuilder:
                 for k, s in enumerate(chunk):
                     d.src[k] = s.ptr
                     d.ld_src[k] = s.ld
+                    d.src_bf16[k] = s.h
                 d.n_src = len(chunk)
-                d.dst, d.ld_dst, d.T, d.E = dst.ptr, dst.ld, dst.rows, dst.cols
+                d.dst, d.ld_dst, d.T, d.E, d.dst_bf16 = dst.ptr, dst.ld, dst.rows, dst.cols, dst.h
                 d.accumulate = 1 if (acc or not first) else 0
                 first = False
                 descs.append(d)
@@ -902,6 +916,8 @@ class Engine:
         self.grad_arena = torch.zeros(total, dtype=torch.float32, device=self.device)
         self.grad_views = {id(p): self.grad_arena[self._grad_off[id(p)]:self._grad_off[id(p)] + p.numel()].view(p.shape)
                            for p in self.params}
+        self.shadow: Optional[torch.Tensor] = None
+        self._shadow_ver: Dict[int, int] = {}
         self.rng_state = torch.zeros(2, dtype=torch.int64, device=self.device)     # {seed_add, offset_add}
         self.rng_state_ptr = self.rng_state.data_ptr()
         self.anchor = torch.zeros(1, device=self.device, requires_grad=True)
@@ -917,6 +933,29 @@ class Engine:
 
     def grad_ptr(self, p) -> int:
         return self.grad_arena.data_ptr() + F4 * self._grad_off[id(p)]
+
+    # -- bf16 data path: bf16 shadow of every weight, laid out like the gradient arena.  The fp32 parameters stay the master
+    #    copy (optimizer, checkpoints); the fused Adam kernel rewrites the shadow of what it updates, any other in-place
+    #    update is noticed through the tensor version counter and re-cast before the next forward.
+    def shadow_ptr(self, p) -> int:
+        if self.shadow is None:
+            self.shadow = torch.empty(self.grad_arena.numel(), dtype=torch.bfloat16, device=self.device)
+            self._shadow_ver = {}
+        return self.shadow.data_ptr() + 2 * self._grad_off[id(p)]
+
+    def shadow_view(self, p) -> torch.Tensor:
+        o = self._grad_off[id(p)]
+        return self.shadow[o:o + p.numel()].view(p.shape)
+
+    def refresh_shadow(self, params):
+        """re-cast the shadows of weights whose fp32 master changed since the last cast (cheap version check)"""
+        ver = self._shadow_ver
+        stale = [p for p in params if ver.get(id(p)) != p._version]
+        if stale:
+            with torch.no_grad():
+                torch._foreach_copy_([self.shadow_view(p) for p in stale], [p.detach() for p in stale])
+            for p in stale:
+                ver[id(p)] = p._version
 
     def active_ranges(self, max_gap: int = 1 << 18) -> List[Tuple[int, int]]:
         """Element ranges [lo, hi) of the gradient arena covered by the parameters that ran in the
@@ -995,7 +1034,7 @@ class Engine:
             for l in layers:
                 l.__dict__["active_hidden_out_fc1"] = l.fc1.dim_out
             peak = 0
-            for mode in (0, 1):                  # the two GEMM engines allocate different scratch
+            for mode in (0, 1, 2):               # the GEMM engines allocate different scratch / element sizes
                 lib.mtb_set_gemm_mode(mode)
                 ca = CountingArena()
                 pb = PlanBuilder(self, ca, True, True)
@@ -1080,7 +1119,7 @@ class Engine:
         for buf in (self.arena.buf, self.enc_buf):
             o = mt.ptr - buf.data_ptr()
             if 0 <= o < buf.numel():
-                return buf[o:o + mt.rows * mt.cols * F4].view(torch.float32).view(mt.rows, mt.cols)
+                return buf[o:o + mt.rows * mt.cols * mt.es].view(torch.float32 if mt.es == 4 else torch.bfloat16).view(mt.rows, mt.cols)
         raise ValueError("Mat outside the engine's buffers")
 
     def _enc_plan(self, kind, name, tag, enc, Lq, Lk, B, E, n_layers, mask, q_src, kv_src, want_bwd, training, need_grad) -> EncPlan:
@@ -1108,6 +1147,7 @@ class Engine:
         ep.fwd = [(_rank(op.what), op) for op in pb.fwd]
         ep.bwd = [(_rank(op.what), op) for op in pb.bwd]
         ep.active_params, ep.sites = pb.active_params, pb.sites
+        ep.used_weights, ep.acts = pb.used_weights, pb.acts
         e.saved = None                       # only the Mats on the spec are needed from here on
         if len(self._enc_cache) > 4096:
             self._enc_cache.clear()
@@ -1320,24 +1360,25 @@ class Engine:
         pb.addn(pb.fwd, items, "head_gather")
         hmask = make_mask(out_index, self.device)
         Cd = m.combined_dim
-        z1, z2, z3 = A.mat(B, Cd), A.mat(B, C_total), A.mat(B, C_total)
+        Hs = pb.H
+        # bf16 data path: proj1 / proj2 run on bf16 operands (their 2 x 36 MB of weights are the head's whole cost at small
+        # batch); the N = 1 output layer and the residual sum stay fp32
+        out16 = A.mat(B, C_total, Hs) if pb.bf else out
+        if pb.bf:
+            pb.addn(pb.fwd, [(out16, [out], False)], "head_cast")
+        z1, z2, z3 = A.mat(B, Cd, Hs), A.mat(B, C_total, Hs), A.mat(B, C_total)
         pred = A.mat(B, m.output_dim)
         po = pb.p("", m.out_dropout)
         r = pb.rng("head.out", B * Cd, po)
+        pb.acts["head.out"] = (z1, 0)
         W1, b1 = m.proj1.l.weight, m.proj1.l.bias
         W2, b2 = m.proj2.l.weight, m.proj2.l.bias
         W3, b3 = m.out_layer.l.weight, m.out_layer.l.bias
         hp, hs = hmask.idx.data_ptr(), _segs(hmask)
-        pb.emit(pb.fwd, lib.mtb_linear_fwd, LinearDesc,
-                [LinearDesc(out.ptr, out.ld, W1.data_ptr(), W1.stride(0), b1.data_ptr(), None, hp, z1.ptr, z1.ld, B, Cd, C_total, 1, po, r,
-                            _NO_SEGS, hs)], "proj1")
-        pb.emit(pb.fwd, lib.mtb_linear_fwd, LinearDesc,
-                [LinearDesc(z1.ptr, z1.ld, W2.data_ptr(), W2.stride(0), b2.data_ptr(), hp, None, z2.ptr, z2.ld, B, C_total, Cd, 0, 0.0,
-                            _NO_RNG, hs, _NO_SEGS)], "proj2")
+        pb.emit(pb.fwd, lib.mtb_linear_fwd, LinearDesc, [pb.lin(out16, W1, b1, z1, Cd, C_total, col_idx=hp, act=1, p=po, rng=r, csegs=hs)], "proj1")
+        pb.emit(pb.fwd, lib.mtb_linear_fwd, LinearDesc, [pb.lin(z1, W2, b2, z2, C_total, Cd, row_idx=hp, rsegs=hs)], "proj2")
         pb.addn(pb.fwd, [(z3, [out, z2], False)], "head_residual")
-        pb.emit(pb.fwd, lib.mtb_linear_fwd, LinearDesc,
-                [LinearDesc(z3.ptr, z3.ld, W3.data_ptr(), W3.stride(0), b3.data_ptr(), None, hp, pred.ptr, pred.ld, B, m.output_dim, C_total,
-                            0, 0.0, _NO_RNG, _NO_SEGS, hs)], "out_layer")
+        pb.emit(pb.fwd, lib.mtb_linear_fwd, LinearDesc, [pb.lin(z3, W3, b3, pred, m.output_dim, C_total, col_idx=hp, csegs=hs)], "out_layer")
 
         plan.inputs = [(i, stage_in[ch]) for i, ch in enumerate(names) if ch in need]
         plan._pred_mat = pred
@@ -1347,17 +1388,19 @@ class Engine:
         if need_grad:
             d_pred = A.mat(B, m.output_dim)
             plan._d_pred_mat = d_pred
-            g_z3, g_z1, g_outb, g_out = A.mat(B, C_total), A.mat(B, Cd), A.mat(B, C_total), A.mat(B, C_total)
-            scratch = A.alloc(B * Cd)
+            g_z3, g_z1, g_outb, g_out = A.mat(B, C_total), A.mat(B, Cd, Hs), A.mat(B, C_total, Hs), A.mat(B, C_total)
+            scratch = A.mat(B, Cd, Hs)
             pb.emit(pb.bwd, lib.mtb_linear_bwd, LinearBwdDesc,
-                    [LinearBwdDesc(d_pred.ptr, d_pred.ld, None, 0, z3.ptr, z3.ld, W3.data_ptr(), W3.stride(0), None, hp, g_z3.ptr, g_z3.ld, 0,
-                                   pb.grad_ptr(W3), pb.grad_ptr(b3), B, m.output_dim, C_total, 0, 0.0, None, _NO_SEGS, hs)], "out_layer_bwd")
+                    [pb.lin_bwd(d_pred, W3, m.output_dim, C_total, X=z3, dX=g_z3, gW=True, gb=True, b=b3, col_idx=hp, csegs=hs)], "out_layer_bwd")
+            g_z3h = g_z3
+            if pb.bf:
+                g_z3h = A.mat(B, C_total, Hs)
+                pb.addn(pb.bwd, [(g_z3h, [g_z3], False)], "head_cast_bwd")
             pb.emit(pb.bwd, lib.mtb_linear_bwd, LinearBwdDesc,
-                    [LinearBwdDesc(g_z3.ptr, g_z3.ld, None, 0, z1.ptr, z1.ld, W2.data_ptr(), W2.stride(0), hp, None, g_z1.ptr, g_z1.ld, 0,
-                                   pb.grad_ptr(W2), pb.grad_ptr(b2), B, C_total, Cd, 0, 0.0, None, hs, _NO_SEGS)], "proj2_bwd")
+                    [pb.lin_bwd(g_z3h, W2, C_total, Cd, X=z1, dX=g_z1, gW=True, gb=True, b=b2, row_idx=hp, rsegs=hs)], "proj2_bwd")
             pb.emit(pb.bwd, lib.mtb_linear_bwd, LinearBwdDesc,
-                    [LinearBwdDesc(g_z1.ptr, g_z1.ld, z1.ptr, z1.ld, out.ptr, out.ld, W1.data_ptr(), W1.stride(0), None, hp, g_outb.ptr, g_outb.ld,
-                                   0, pb.grad_ptr(W1), pb.grad_ptr(b1), B, Cd, C_total, 1, po, scratch, _NO_SEGS, hs)], "proj1_bwd")
+                    [pb.lin_bwd(g_z1, W1, Cd, C_total, Yact=z1, X=out16, dX=g_outb, gW=True, gb=True, b=b1, col_idx=hp, act=1, p=po,
+                                scratch=scratch.ptr, csegs=hs)], "proj1_bwd")
             pb.addn(pb.bwd, [(g_out, [g_z3, g_outb], False)], "head_residual_bwd")
             # scatter into zero-filled d(mems output): only the last time step received gradient
             items = []
@@ -1404,10 +1447,17 @@ class Engine:
                 op.finalize()
         plan.fwd, plan.bwd = pb.fwd, pb.bwd
         sites = dict(pb.sites)
+        acts = dict(pb.acts)
+        uw, seen_w = list(pb.used_weights), {id(w_) for w_ in pb.used_weights}
         aps, seen_p = [], set()
         for g in groups:
             for ep in g:
                 sites.update(ep.sites)
+                acts.update(ep.acts)
+                for w_ in ep.used_weights:
+                    if id(w_) not in seen_w:
+                        seen_w.add(id(w_))
+                        uw.append(w_)
                 for p_ in ep.active_params:
                     if id(p_) not in seen_p:
                         seen_p.add(id(p_))
@@ -1417,6 +1467,7 @@ class Engine:
                 seen_p.add(id(p_))
                 aps.append(p_)
         plan.sites, plan.rng_span = sites, (STEP_SPAN if training else 0)
+        plan.acts, plan.used_weights = acts, uw
         plan.active_params = aps
         # The launch descriptors hold RAW device addresses of index arrays: the plan owns the Mask objects (head gather
         # + every encoder's active_mask through its EncPlan), so evicting the mask / encoder-plan caches can never
@@ -1493,6 +1544,8 @@ class Engine:
         plan = self.plan_for(meta, training, need_grad)
         plan.hits += 1
         self.generation += 1
+        if plan.used_weights:
+            self.refresh_shadow(plan.used_weights)
         for i, mt in plan.inputs:
             ch = m.modality_list[i]
             L, B = meta[i]

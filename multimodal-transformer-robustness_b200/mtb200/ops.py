@@ -122,13 +122,18 @@ def preload():
         _preloaded = True
 
 
-GEMM_MODES = ("fp32", "tf32")
+GEMM_MODES = ("fp32", "tf32", "bf16")
+_MODE_ID = {"fp32": 0, "tf32": 1, "bf16": 2}
+_MODE_NAME = {0: "fp32", 1: "tf32", 2: "bf16"}
 
 
 def set_gemm_mode(mode: str) -> str:
-    """'fp32' = CUDA-core parity engine, 'tf32' = tcgen05 tensor-core engine."""
-    prev = lib.mtb_set_gemm_mode({"fp32": 0, "tf32": 1}[mode])
-    return "tf32" if prev else "fp32"
+    """'fp32' = CUDA-core parity engine (1e-5), 'tf32' = tcgen05 tensor-core engine on fp32 storage, 'bf16' = the bf16
+    data path of the plan executor: bf16 activations between kernels and bf16 weight shadows, tcgen05.mma.kind::f16 GEMMs,
+    fp32 master weights / residual stream / LayerNorm statistics / softmax.  The per-op (drop-in module) path keeps fp32
+    tensors at its boundary and behaves like 'tf32' under 'bf16'."""
+    prev = lib.mtb_set_gemm_mode(_MODE_ID[mode])
+    return _MODE_NAME.get(prev, "fp32")
 
 
 def set_attn_mode(mode: str) -> str:
@@ -139,29 +144,43 @@ def set_attn_mode(mode: str) -> str:
 
 
 def get_gemm_mode() -> str:
-    return "tf32" if lib.mtb_get_gemm_mode() else "fp32"
+    return _MODE_NAME.get(lib.mtb_get_gemm_mode(), "fp32")
 
 
 # -- bench.py's isolated-kernel roofline probe: the GEMM of the given engine on its native operand types
 def gemm_elem_size(mode: str) -> int:
-    return 4
+    return 2 if mode == "bf16" else 4
 
 
 def bench_operand(x: Tensor, mode: str) -> Tensor:
-    return x
+    return x.to(torch.bfloat16) if mode == "bf16" else x
 
 
 def bench_linear(x: Tensor, W: Tensor, b: Optional[Tensor], mode: str):
-    """closure launching Y = X W^T + b once on the current stream with engine ``mode``"""
+    """closure launching Y = X W^T + b once on the current stream with engine ``mode`` (bf16: bf16 X / W / Y, fp32 bias)"""
     N, K = W.shape
+    if mode != "bf16":
+        def fn():
+            prev = set_gemm_mode(mode)
+            try:
+                return linear(x, W, b, N=N, K=K)
+            finally:
+                set_gemm_mode(prev)
+        return fn
+    W16 = W.to(torch.bfloat16).contiguous()
+    y = torch.empty((x.shape[0], N), device=x.device, dtype=torch.bfloat16)
+    d = LinearDesc(x.data_ptr(), x.stride(0), W16.data_ptr(), W16.stride(0), _p(b), None, None, y.data_ptr(), y.stride(0),
+                   x.shape[0], N, K, 0, 0.0, _rng_struct(0, 0), _NO_SEGS, _NO_SEGS, 1, 1)
 
-    def fn():
-        prev = set_gemm_mode(mode)
+    def fn16():
+        prev = set_gemm_mode("bf16")
         try:
-            return linear(x, W, b, N=N, K=K)
+            call_group(lib.mtb_linear_fwd, LinearDesc, [d], _stream(), "mtb_linear_fwd")
+            fn16.keep = (W16, y)
+            return y
         finally:
             set_gemm_mode(prev)
-    return fn
+    return fn16
 
 
 # ----------------------------------------------------------------------------- embed
@@ -288,7 +307,7 @@ def _lin_fwd_desc(x, W, b, row_idx, col_idx, row0, N, K, y, act, p, seed, off, r
 def _lin_bwd_desc(dy, yact, x, W, row_idx, col_idx, row0, N, K, dX, acc, dW, db, act, p, rsegs=_NO_SEGS, csegs=_NO_SEGS):
     ldw = W.stride(0)
     scratch = None
-    if act == 1 and lib.mtb_get_gemm_mode() == 1:
+    if act == 1 and lib.mtb_get_gemm_mode() >= 1:
         scratch = torch.empty((dy.shape[0], N), device=dy.device, dtype=torch.float32)
         _keepalive.append(scratch)
     return LinearBwdDesc(dy.data_ptr(), dy.stride(0), _p(yact), yact.stride(0) if yact is not None else 0,

@@ -127,6 +127,9 @@ class FlatAdam(torch.optim.Optimizer):
         d.active = flags.data_ptr()
         d.lr, (d.beta1, d.beta2) = float(g["lr"]), g["betas"]
         d.eps, d.weight_decay, d.max_norm = float(g["eps"]), float(g["weight_decay"]), float(max_norm)
+        # bf16 data path: the update kernel also rewrites the bf16 shadow of every element it touches (the raw-pointer
+        # update does not bump tensor version counters, so the engine's staleness check would not see it)
+        d.shadow = eng.shadow.data_ptr() if eng.shadow is not None else None
         _lib.check(lib.mtb_adam_step(C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mtb_adam_step")
         return self.scalars[0]
 

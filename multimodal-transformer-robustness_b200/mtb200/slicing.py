@@ -54,21 +54,30 @@ class Mask:
 
 
 def _block_structure(ix: Sequence[int]):
-    """(block_len, [block ids]) if ix is a concatenation of aligned blocks of equal length."""
+    """(block_len, [block ids]) if ix is a concatenation of aligned blocks of equal length.  The block length is the
+    gcd of every maximal run's start and length, so ADJACENT blocks (e.g. slots 1 and 2 of a `mems` stack: one run of
+    2 d indices starting at d) are still recognised as d-wide blocks."""
+    import math
     n = len(ix)
     if n == 0:
         return 0, None
-    run = 1
-    while run < n and ix[run] == ix[run - 1] + 1:
-        run += 1
-    if run < 4 or n % run != 0 or n // run > 16:
+    L, s = 0, 0
+    while s < n:                                   # maximal runs of consecutive indices
+        e = s + 1
+        while e < n and ix[e] == ix[e - 1] + 1:
+            e += 1
+        L = math.gcd(L, math.gcd(ix[s], e - s))
+        s = e
+    if L < 4 or n % L != 0:
+        return 0, None
+    if n // L > 16:
         return 0, None
     segs = []
-    for s in range(0, n, run):
-        if ix[s] % run != 0 or any(ix[s + t] != ix[s] + t for t in range(run)):
+    for s in range(0, n, L):
+        if ix[s] % L != 0 or ix[s + L - 1] != ix[s] + L - 1:
             return 0, None
-        segs.append(ix[s] // run)
-    return run, segs
+        segs.append(ix[s] // L)
+    return L, segs
 
 
 _mask_cache: dict = {}

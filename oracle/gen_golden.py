@@ -308,8 +308,14 @@ def grad_fingerprint(g, n=257):
 
 
 def weight_checksums(m):
-    return {k: (float(v.double().sum()), float(v.double().abs().sum())) for k, v in m.state_dict().items()
-            if v.dtype.is_floating_point and "_float_tensor" not in k}
+    """two EXACT integer checksums of the fp32 bit patterns (independent of summation order / thread count)"""
+    out = {}
+    for k, v in m.state_dict().items():
+        if v.dtype == torch.float32 and "_float_tensor" not in k:
+            bits = v.detach().contiguous().view(torch.int32).reshape(-1).to(torch.int64)
+            w = (torch.arange(bits.numel(), dtype=torch.int64) % 251) + 1
+            out[k] = (int(bits.sum()), int((bits * w).sum()))
+    return out
 
 
 def gen_real_dims():

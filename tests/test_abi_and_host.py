@@ -150,3 +150,18 @@ def test_plan_stage_merge_order():
                      "wgrad", "ln0_kv_bwd")] + ["ln_first_bwd", "embed_bwd"]
     assert sorted(bwd, key=_rank) == bwd
     assert all(_rank(a) != _rank(b) for a in fwd for b in fwd if a != b)
+
+
+def test_block_structure_of_gather_masks():
+    """active_mask gathers are unions of d-wide blocks (src/dynamic_models2.py:243-251).  ADJACENT blocks form one longer
+    run of indices and must still be recognised as d-wide blocks: an unrecognised mask silently sent every GEMM of that
+    `mems` stack to the fp32 fallback (round-1 bug: its deferred fc1 weight gradient was then never formed)."""
+    from mtb200.slicing import _block_structure as bs
+    assert bs(list(range(200, 600))) == (200, [1, 2])
+    assert bs(list(range(0, 200)) + list(range(400, 600))) == (200, [0, 2])
+    assert bs(list(range(200, 400)) + list(range(600, 1000))) == (200, [1, 3, 4])
+    assert bs(list(range(0, 1000))) == (1000, [0])
+    assert bs(list(range(8, 16)) + list(range(24, 40))) == (8, [1, 3, 4])
+    assert bs([0, 2, 4, 6]) == (0, None)                          # strided: general gather (fp32 engine)
+    assert bs([]) == (0, None)
+    assert bs(list(range(3, 11))) == (0, None)                    # unaligned start: gcd(3, 8) = 1

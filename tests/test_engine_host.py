@@ -111,3 +111,45 @@ def test_dropout_sites_of_a_plan_never_share_philox_offsets(setup):
         spans = sorted((site[0], site[0] + (site[1] + 3) // 4 + 1) for site in plan.sites.values())
         for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
             assert a1 <= b0
+
+
+def test_bf16_plans_mark_operand_types_consistently(setup):
+    """bf16 data path (gemm mode 2): every GEMM / attention problem of a plan reads and writes bf16 where the builder
+    says so, weights come from the bf16 shadow arena, the residual stream / statistics / encoder outputs stay fp32."""
+    from mtb200 import _lib
+    from mtb200.engine import Batch, Op
+    from mtb200.train import sample_next_config
+    m, hyp, eng, meta = setup
+    prev = _lib.lib.mtb_set_gemm_mode(2)
+    try:
+        torch.manual_seed(11)
+        for _ in range(6):
+            sample_next_config(m, hyp)
+            plan = eng.plan_for(meta, True, True)
+            assert plan.used_weights, "bf16 plans must read weights through the shadow arena"
+            lo, hi = eng.shadow.data_ptr(), eng.shadow.data_ptr() + 2 * eng.shadow.numel()
+            n_lin = n_attn = 0
+
+            def walk(ops):
+                for op in ops:
+                    if type(op) is Batch:
+                        yield from walk(op.ops)
+                    elif type(op) is Op:
+                        for arr, n in op.arr:
+                            for i in range(n):
+                                yield op.fn.mtb_name, arr[i]
+            for name, d in walk(plan.fwd + plan.bwd):
+                if name == "mtb_linear_fwd" and d.N > 1:
+                    n_lin += 1
+                    assert d.in_bf16 == 1 and d.out_bf16 == 1 and lo <= d.W < hi, (name, d.M, d.N, d.K)
+                elif name == "mtb_linear_fwd":
+                    assert d.in_bf16 == 0 and d.out_bf16 == 0                      # N = 1 output layer: fp32 CUDA-core kernel
+                elif name == "mtb_linear_bwd" and d.N > 1:
+                    assert d.in_bf16 == 1 and lo <= d.W < hi
+                    assert d.dX is None or d.dx_bf16 == 1
+                elif name in ("mtb_attn_fwd", "mtb_attn_bwd"):
+                    n_attn += 1
+                    assert d.bf16 == 1
+            assert n_lin > 0 and (n_attn > 0 or all(e.active_layer_num == 0 for e in m.trans_mems0.values()))
+    finally:
+        _lib.lib.mtb_set_gemm_mode(prev)
