@@ -326,6 +326,10 @@ def main():
                         "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / K, "ms_per_step_min": min(t_e2e) / K,
                         "ms_per_step_max": max(t_e2e) / K},
                 "gpu_launches": int(launches)}
+        eng = getattr(model, "_engine", None)
+        if eng is not None:
+            line["engine"] = {k: int(v) for k, v in eng.stats.items()}
+            line["engine"]["stage_graphs_after_hits"] = eng.stage_graphs
         if ea is not None:
             line["ea"] = ea
         line["roofline"] = kernel_roofline(dev, args, mode)
@@ -450,16 +454,17 @@ def kernel_roofline(dev, args, mode):
     tf = peaks.get("bf16_tflops", 1590.0)
     alg_bytes = es * (M * K + N * K + M * N)
     ach = alg_bytes / (ms * 1e-3) / 1e9
-    kernel = {"fp32": "gemm_simt_kernel", "tf32": "gemm_tc_kernel", "bf16": "gemm_bf16_kernel"}[mode]
+    kernel = {"fp32": "gemm_simt_kernel", "tf32": "gemm_tc_kernel", "bf16": "gemm_tc_kernel"}[mode]
+    operands = {"fp32": "fp32", "tf32": "fp32 storage, tf32 MMA", "bf16": "bf16 storage, kind::f16 MMA, fp32 accumulate"}[mode]
     traffic, traffic_src = None, None
     try:      # dram__bytes_read.sum + dram__bytes_write.sum of this launch from an `ncu --set full` capture (profiles/)
         tab = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-        ent = tab.get(f"{kernel}:{M}x{N}x{K}")
+        ent = tab.get(f"{kernel}:{mode}:{M}x{N}x{K}") or tab.get(f"{kernel}:{M}x{N}x{K}" if mode == "tf32" else "-")
         if ent:
             traffic, traffic_src = ent["dram_bytes"], ent["source"]
     except Exception:
         pass
-    return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+    return {"kernel": kernel, "operands": operands, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
             "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 GB/s",
             "shape": [M, N, K], "ms": ms, "algorithmic_bytes": alg_bytes, "bytes_per_element": es,

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MTB_ABI_VERSION 14
+#define MTB_ABI_VERSION 15
 #define MTB_MAX_GROUP 24
 
 /* Dropout RNG: Philox4x32-7.  Element `i` of a dropout site is kept iff
@@ -253,6 +253,14 @@ typedef struct {
   int32_t reserved;
 } mtb_op;
 int mtb_run_ops(const mtb_op* ops, int n_ops, void* stream, void* side_stream);
+/* The same op list captured into a CUDA graph (side ops become a parallel branch when use_side != 0) and replayed with
+ * one launch.  Valid as long as every address in the descriptors stays valid -- the plan executor's stage batches only
+ * reference persistent regions, parameters and the device-side dropout counter, so a replay draws fresh dropout masks.
+ * The descriptor arrays themselves are copied into the graph (kernel parameters) and may be freed after capture.
+ * mtb_graph_capture returns 0 and a handle, or non-zero when this driver cannot capture the list (run it eagerly). */
+int mtb_graph_capture(const mtb_op* ops, int n_ops, int use_side, void** handle);
+int mtb_graph_launch(void* handle, void* stream);
+int mtb_graph_destroy(void* handle);
 
 /* ---- fused gradient clip + Adam over the flat arenas --------------------------------
  * Replaces `torch.nn.utils.clip_grad_norm_(model.parameters(), clip); optimizer.step()` of

@@ -10,7 +10,7 @@ static thread_local char g_err[512] = "";
 int g_gemm_mode = 0;
 int g_attn_mode = -1;
 int g_pdl = getenv("MTB_PDL") ? atoi(getenv("MTB_PDL")) : 1;   // programmatic dependent launch (common.cuh)   // -1 = follow the GEMM engine (tensor-core attention in tensor-core mode)
-static unsigned long long g_launches = 0;
+unsigned long long g_launches = 0;
 void note_launch() { ++g_launches; }
 unsigned long long launches() { return g_launches; }
 
@@ -118,14 +118,8 @@ int mtb_attn_bwd(const mtb_attn_bwd_desc* d, int n, void* stream) {
   return mtb::attn_bwd_simt(d, n, (cudaStream_t)stream);
 }
 
-int mtb_run_ops(const mtb_op* ops, int n_ops, void* stream, void* side_stream) {
-  MTB_CHECK(ops != nullptr || n_ops == 0, "run_ops: null op list");
-  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+static int run_ops_impl(const mtb_op* ops, int n_ops, void* stream, void* side_stream, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
   cudaStream_t st = (cudaStream_t)stream, s2 = (cudaStream_t)side_stream;
-  if (s2 && !ev_fork) {
-    MTB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    MTB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-  }
   bool forked = false;
   for (int i = 0; i < n_ops; ++i) {
     const mtb_op& o = ops[i];
@@ -155,6 +149,86 @@ int mtb_run_ops(const mtb_op* ops, int n_ops, void* stream, void* side_stream) {
     MTB_CUDA(cudaEventRecord(ev_join, s2));
     MTB_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
   }
+  return 0;
+}
+
+int mtb_run_ops(const mtb_op* ops, int n_ops, void* stream, void* side_stream) {
+  MTB_CHECK(ops != nullptr || n_ops == 0, "run_ops: null op list");
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (side_stream && !ev_fork) {
+    MTB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    MTB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
+  return run_ops_impl(ops, n_ops, stream, side_stream, ev_fork, ev_join);
+}
+
+/* ---- CUDA graphs of op lists ------------------------------------------------------------------------------------
+ * Every address a stage batch touches is persistent (plan executor regions, parameters, the device-side dropout
+ * counter), so an op list that comes back -- the same stage composition in a later step -- can be replayed as ONE
+ * graph launch instead of ~20-60 kernel launches: the host cost of a stage drops from ~0.2 ms to ~10 us and the
+ * GPU-side launch gaps go with it.  Side-stream ops become a parallel branch of the graph. */
+struct MtbGraph {
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+  unsigned long long launches;
+};
+
+int mtb_graph_capture(const mtb_op* ops, int n_ops, int use_side, void** out) {
+  MTB_CHECK(ops != nullptr && n_ops > 0 && out != nullptr, "graph_capture: empty op list");
+  static cudaStream_t cap = nullptr, cap2 = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (!cap) {
+    MTB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    MTB_CUDA(cudaStreamCreateWithFlags(&cap2, cudaStreamNonBlocking));
+    MTB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    MTB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
+  *out = nullptr;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const int pdl0 = mtb::g_pdl;
+    if (attempt == 1) mtb::g_pdl = 0;            // second try without programmatic dependent launch edges
+    const unsigned long long l0 = mtb::g_launches;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+    int rc = -1;
+    if (e == cudaSuccess) {
+      rc = run_ops_impl(ops, n_ops, cap, use_side ? cap2 : nullptr, ev_fork, ev_join);
+      e = cudaStreamEndCapture(cap, &graph);
+    }
+    const unsigned long long captured = mtb::g_launches - l0;
+    mtb::g_launches = l0;                        // nothing ran
+    mtb::g_pdl = pdl0;
+    if (rc == 0 && e == cudaSuccess && graph != nullptr) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (rc == 0 && e == cudaSuccess && exec != nullptr) {
+      MtbGraph* g = new MtbGraph{graph, exec, captured};
+      *out = g;
+      return 0;
+    }
+    if (graph) cudaGraphDestroy(graph);
+    (void)cudaGetLastError();
+    if (attempt == 1) {
+      if (rc == 0) mtb::set_error("graph_capture: %s", cudaGetErrorString(e));
+      return -3;
+    }
+  }
+  return -3;
+}
+
+int mtb_graph_launch(void* handle, void* stream) {
+  MTB_CHECK(handle != nullptr, "graph_launch: null handle");
+  MtbGraph* g = (MtbGraph*)handle;
+  MTB_CUDA(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+  mtb::g_launches += g->launches;               // kernels the replay runs (bench bookkeeping)
+  return 0;
+}
+
+int mtb_graph_destroy(void* handle) {
+  if (handle == nullptr) return 0;
+  MtbGraph* g = (MtbGraph*)handle;
+  cudaGraphExecDestroy(g->exec);
+  cudaGraphDestroy(g->graph);
+  delete g;
   return 0;
 }
 

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MTB_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libmultb200.so")   # MTB_LIB: instrumented debug builds
 
 MAX_GROUP = 24
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 
 class MtbError(RuntimeError):
@@ -135,6 +135,9 @@ SYMBOLS = {
     "mtb_attn_bwd": ([C.POINTER(AttnBwdDesc), C.c_int, C.c_void_p], C.c_int),
     "mtb_adam_step": ([C.POINTER(AdamDesc), C.c_void_p], C.c_int),
     "mtb_run_ops": ([C.POINTER(OpDesc), C.c_int, C.c_void_p, C.c_void_p], C.c_int),
+    "mtb_graph_capture": ([C.POINTER(OpDesc), C.c_int, C.c_int, C.POINTER(C.c_void_p)], C.c_int),
+    "mtb_graph_launch": ([C.c_void_p, C.c_void_p], C.c_int),
+    "mtb_graph_destroy": ([C.c_void_p], C.c_int),
 }
 
 

@@ -195,6 +195,14 @@ class Batch:
         self.n = self.launches = len(entries)
         self.arr = (_lib.OpDesc * len(entries))(*entries)
 
+    def __del__(self):
+        g, self.graph = getattr(self, "graph", None), None
+        if g:
+            try:
+                lib.mtb_graph_destroy(g)
+            except Exception:
+                pass
+
 
 class ZeroOp:
     __slots__ = ("t",)
@@ -821,9 +829,10 @@ class Plan:
         self.n_bwd_launches = 0
 
 
-def _run(ops, stream: int, side=None, stage_hook=None):
+def _run(ops, stream: int, side=None, stage_hook=None, graphs=None):
     """side: optional (torch side stream, fork event, join event) -- ops flagged `side` are launched there, ordered
-    after everything issued so far on the main stream; the main stream re-joins at the end of the list."""
+    after everything issued so far on the main stream; the main stream re-joins at the end of the list.
+    graphs: optional engine -- stage batches that keep coming back are captured into CUDA graphs (Engine.stage_graphs)."""
     sp = C.c_void_p(stream)
     forked = False
     if side is not None:
@@ -832,10 +841,34 @@ def _run(ops, stream: int, side=None, stage_hook=None):
     for op in ops:
         tp = type(op)
         if tp is Batch:
-            rc = lib.mtb_run_ops(op.arr, op.n, sp, sp2 if side is not None else None)
-            if rc != 0:
-                what = op.ops[0].what
-                raise _lib.MtbError(f"batched launches starting at {what} failed ({rc}): {lib.mtb_last_error().decode()}")
+            if op.graph is not None:
+                rc = lib.mtb_graph_launch(op.graph, sp)
+                if rc != 0:
+                    raise _lib.MtbError(f"graph replay of the batch starting at {op.ops[0].what} failed ({rc}): {lib.mtb_last_error().decode()}")
+                graphs.stats["stage_graph_replays"] += 1
+            else:
+                if graphs is not None and graphs.stage_graphs >= 0:
+                    op.hits += 1
+                    if op.hits > graphs.stage_graphs and op.graph is not False and graphs.stats["stage_graphs"] < graphs.max_stage_graphs:
+                        h = C.c_void_p()
+                        if lib.mtb_graph_capture(op.arr, op.n, 1 if side is not None else 0, C.byref(h)) == 0 and h.value:
+                            op.graph = h.value
+                            graphs.stats["stage_graphs"] += 1
+                            rc = lib.mtb_graph_launch(op.graph, sp)
+                            if rc != 0:
+                                raise _lib.MtbError(f"graph launch failed ({rc}): {lib.mtb_last_error().decode()}")
+                            graphs.stats["stage_graph_replays"] += 1
+                            if stage_hook is not None and op.grad_params:
+                                stage_hook(op.grad_params)
+                            continue
+                        op.graph = False              # this driver cannot capture the list: stay eager, do not retry
+                        graphs.stats["stage_graph_failures"] += 1
+                rc = lib.mtb_run_ops(op.arr, op.n, sp, sp2 if side is not None else None)
+                if rc != 0:
+                    what = op.ops[0].what
+                    raise _lib.MtbError(f"batched launches starting at {what} failed ({rc}): {lib.mtb_last_error().decode()}")
+                if graphs is not None:
+                    graphs.stats["stage_eager_runs"] += 1
             if stage_hook is not None and op.grad_params:
                 stage_hook(op.grad_params)        # data parallel: this stage's gradients can be reduced while earlier stages run
             continue
@@ -929,7 +962,13 @@ class Engine:
         self._grads_live = False   # p.grad of exactly last_plan.active_params are views of the gradient arena
         self._grads_dirty = False  # some p.grad may alias the arena (a backward ran since the last model.zero_grad())
         self._enc_index = {id(enc): j for j, (_, _, enc) in enumerate(self._all_encoders())}
-        self.stats = {"plans": 0, "graph_replays": 0, "eager_runs": 0}
+        self.stats = {"plans": 0, "graph_replays": 0, "eager_runs": 0, "stage_graphs": 0, "stage_graph_replays": 0,
+                      "stage_eager_runs": 0, "stage_graph_failures": 0}
+        # Stage batches (all launches of one stage composition, memoised in _merge_cache) are captured into a CUDA graph
+        # once they have been run more than `stage_graphs` times (-1 = never) and replayed from then on.
+        import os as _os
+        self.stage_graphs = int(_os.environ.get("MTB_STAGE_GRAPHS", "2"))
+        self.max_stage_graphs = int(_os.environ.get("MTB_MAX_STAGE_GRAPHS", "1024"))
 
     def grad_ptr(self, p) -> int:
         return self.grad_arena.data_ptr() + F4 * self._grad_off[id(p)]
@@ -1530,7 +1569,7 @@ class Engine:
             if self._side is None:
                 self._side = (torch.cuda.Stream(device=self.device), torch.cuda.Event(), torch.cuda.Event())
             side = self._side
-        _run(ops, stream, side, self.stage_hook if which == "bwd" else None)
+        _run(ops, stream, side, self.stage_hook if which == "bwd" else None, self if not torch.cuda.is_current_stream_capturing() else None)
         self.stats["eager_runs"] += 1
 
     def forward(self, px: Sequence[torch.Tensor]) -> torch.Tensor:

@@ -7,6 +7,8 @@ EVERY parameter gradient are compared, in the max-norm  max|a-b| / max|b|  per t
     fp32 engine           logits 1e-5 (north star), gradients 1e-4       vs the fp32 oracle
     tf32 engine           logits and gradients 2e-2 (north star's bound)  vs the fp32 oracle
     bf16 data path        logits and gradients 2e-2                       vs the AUTOCAST (bf16) oracle, SURVEY.md D8
+                          (a gradient may exceed 2e-2 only where the autocast oracle ITSELF is further than that from the
+                          fp32 oracle on the same tensor -- bf16's own noise floor; measured: 1 of 1302 tensors, 2.3e-2)
 
 Discrete choices are replayed, not re-derived: dropout masks (Philox streams) and ReLU gates.  A pre-activation that lies
 within rounding error of zero can fall on either side of the ReLU in two correct implementations, and one flipped gate
@@ -43,7 +45,7 @@ CASES = [
 ]
 TOL = {"fp32": (1e-5, 1e-4), "tf32": (2e-2, 2e-2), "bf16": (2e-2, 2e-2)}
 # replayed ReLU gates may disagree with the oracle's own only this often / only for pre-activations this small (x layer rms)
-GATE = {"fp32": (1e-5, 1e-4), "tf32": (5e-3, 2e-2), "bf16": (3e-2, 1e-1)}
+GATE = {"fp32": (1e-6, 1e-5), "tf32": (1e-3, 1e-2), "bf16": (3e-3, 8e-2)}      # measured: 2e-7 / 1e-6, 1.7e-4 / 4e-3, 7e-4 / 3.4e-2
 BASE0 = 7 << 34
 
 
@@ -119,6 +121,23 @@ def test_benched_path_matches_oracle_at_bench_shape(model, case):
         ref = ref.float()
         torch.nn.functional.l1_loss(ref, y_h).backward()
         rows = {"oracle_seconds": time.time() - t0, "oracle": "autocast bf16" if mode == "bf16" else "fp32"}
+        floor = {}
+        if mode == "bf16":
+            # bf16's own noise floor: the autocast oracle vs the fp32 oracle under the SAME masks and gates
+            w32 = _oracle_weights(m)
+            drop32 = O.Drop("inject", engine_mask_provider(ops, eng, plan, base), gate_fn=engine_gate_provider(ops, eng, plan, base))
+            ref32 = O.model_forward(w32, xs_h, modality_list=bench.NAMES, d=bench.D, H=bench.H, hd=bench.HD, layers_single=single,
+                                    layers_cross=bench.LAYERS["cross"], layers_self=bench.LAYERS["self"],
+                                    attn_dropout=bench.DROPS["attn"], relu_dropout=bench.DROPS["relu"], res_dropout=bench.DROPS["res"],
+                                    out_dropout=bench.DROPS["out"], embed_dropout=bench.DROPS["embed"], active_modality=am,
+                                    active_cross=cross, active_cross_output=outs, drop=drop32,
+                                    front_end=lambda i, x, w=w32: torch.einsum("bld,ed->lbe", x, w[f"proj.{i}.weight"][:, :, 0]), ffn=bench.D)
+            torch.nn.functional.l1_loss(ref32, y_h).backward()
+            floor = {k: max_rel(w[k].grad, v.grad) for k, v in w32.items() if v.grad is not None and w[k].grad is not None
+                     and float(v.grad.abs().max()) > 0}
+            rows["autocast_vs_fp32_oracle_pred"] = max_rel(ref, ref32)
+            rows["autocast_vs_fp32_oracle_grad_worst"] = max(floor.values())
+            del w32, drop32, ref32
         # ---- how much was replayed
         gfrac, gmag = GATE[mode]
         n_flip = sum(g[1] for g in drop.gate_stats)
@@ -152,8 +171,11 @@ def test_benched_path_matches_oracle_at_bench_shape(model, case):
             l2_worst = max(l2_worst, l2_rel(g, gr))
             if eg > worst[0]:
                 worst = (eg, k)
-            if not eg <= tol_g:
-                failures.append(f"{mode} grad {k}: max-norm rel err {eg:.3e} (L2 {l2_rel(g, gr):.3e}) > {tol_g:.0e}")
+            if not eg <= max(tol_g, floor.get(k, 0.0)):
+                failures.append(f"{mode} grad {k}: max-norm rel err {eg:.3e} (L2 {l2_rel(g, gr):.3e}) > {tol_g:.0e}"
+                                + (f" and > the autocast oracle's own distance to fp32 {floor[k]:.3e}" if k in floor else ""))
+            elif eg > tol_g:
+                rows.setdefault("above_tol_within_noise_floor", []).append((k, eg, floor[k]))
         rows.update(grad_worst_max=worst[0], grad_worst_name=worst[1], grad_worst_l2=l2_worst, grads_compared=n_cmp)
         report["modes"][mode] = rows
         del ref, w, drop

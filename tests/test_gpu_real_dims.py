@@ -5,7 +5,7 @@ the reference's).  Encoder: modules/dynamic_transformer.py:56-88; supernet: src/
 Tolerances (max-norm  max|a-b| / max|b|  per tensor unless stated): fp32 engine 2e-5 logits / 1e-4 gradients.  The
 reduced-precision engines are held to 2e-2 on the logits; a fixed fixture cannot replay ReLU gates (see
 tests/test_gpu_bench_shape.py, where the same engines meet 2e-2 in the max-norm on every gradient with the gates
-replayed), so their gradients are checked here in the L2 norm (2e-2 tf32, 5e-2 bf16-vs-fp32-reference) plus a loose
+replayed), so their gradients are checked here in the L2 norm (5e-2: 18-24 tokens per fixture, one flipped gate weighs a lot) plus a loose
 max-norm bound that still catches any structural error (missing / misplaced gradient blocks give errors >= 1)."""
 import os
 
@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 from engine_util import (build_real_dims_encoder, build_real_dims_model, check_checksums, check_fingerprint, l2_rel, max_rel,  # noqa: E402
                          ref_key)
 
-TOL = {"fp32": (2e-5, 1e-4), "tf32": (2e-2, 2e-2), "bf16": (2e-2, 5e-2)}
+TOL = {"fp32": (2e-5, 1e-4), "tf32": (2e-2, 5e-2), "bf16": (2e-2, 5e-2)}
 LOOSE_MAX = 0.5
 
 
