@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference's eager CUDA path (stock + clean loop)")
     ap.add_argument("--no-ea", action="store_true")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the configs[2] sub-benchmark (global batch 1024, strong scaling)")
     ap.add_argument("--ea-population", type=int, default=256)
     ap.add_argument("--ea-valid", type=int, default=2048)
     ap.add_argument("--ref-batch", type=int, default=None, help="reference arm: samples per step (default = the workload's)")
@@ -311,6 +312,9 @@ def main():
     clk = clocks.stop() if clocks else None
     ms, ms_e2e = statistics.median(t_val), statistics.median(t_e2e)
 
+    cfg3 = None
+    if args.workload == "cfg2" and not args.no_cfg3:
+        cfg3 = cfg3_throughput(args, model, opt, crit, sync, dev, world, rank)
     ea = None if args.no_ea else ea_throughput(args, model, dev, world, rank)
 
     if rank == 0:
@@ -332,6 +336,8 @@ def main():
             line["engine"]["stage_graphs_after_hits"] = eng.stage_graphs
         if ea is not None:
             line["ea"] = ea
+        if cfg3 is not None:
+            line["cfg3"] = cfg3
         line["roofline"] = kernel_roofline(dev, args, mode)
         if world == 1 and not args.no_cpu_baseline:
             r = _harness(["--device", "cpu", "--steps", "2", "--warmup", "1", "--batch", str(args.batch), "--workload", args.workload,
@@ -360,6 +366,60 @@ def main():
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- cfg3: global batch 1024 (strong scaling)
+def cfg3_throughput(args, model, opt, crit, sync, dev, world, rank, global_batch=1024, steps=10, repeats=3):
+    """BASELINE.json configs[2]: data-parallel training at GLOBAL batch 1024 (aligned L=50, `test_single` over [[0,1,2]] = all
+    six two-level branches), 1024 / N samples per GPU, gradients all-reduced over NCCL.  Device-resident inputs; same timing
+    rules as the main workload.  On one GPU the 1024-sample step needs a ~90 GB activation region: reported as skipped if
+    the engine's memory check refuses it."""
+    import torch
+    import torch.distributed as dist
+    from mtb200.train import sample_next_config, train_step
+    B = global_batch // world
+    seq = (50, 50, 50)
+    hyp = make_hyp(seq, "cfg3")
+    model.reset_engine()                      # new shapes: fresh persistent regions (the old buffer is released first)
+    opt._eng = None
+    torch.cuda.empty_cache()
+    gen = torch.Generator().manual_seed(3000 + rank)
+    data = [synth_batch(B, seq, gen) for _ in range(2)]
+    data = [([x.to(dev) for x in xs], y.to(dev)) for xs, y in data]
+    out = {"workload": "cfg3: aligned L=50, test_single over [[0,1,2]], global batch %d = %d x %d GPUs" % (global_batch, B, world),
+           "global_batch": global_batch, "batch_per_gpu": B, "n_gpus": world, "scaling": "strong", "steps": steps}
+    try:
+        torch.manual_seed(SEED)
+        sample_next_config(model, hyp)
+        for it in range(3):
+            train_step(model, opt, crit, *data[it % 2], hyp, grad_sync=sync)
+        ts = []
+        for _ in range(repeats):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for it in range(steps):
+                train_step(model, opt, crit, *data[it % 2], hyp, grad_sync=sync)
+            e1.record()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ts.append(float(t.item()))
+        ms = statistics.median(ts)
+        out.update(value=global_batch * steps / (ms / 1e3), unit="samples/s", ms_per_step=ms / steps,
+                   ms_per_step_min=min(ts) / steps, ms_per_step_max=max(ts) / steps)
+    except MemoryError as exc:
+        ok = torch.tensor([0.0], device=dev)
+        out.update(value=None, skipped=str(exc))
+    model.reset_engine()
+    opt._eng = None
+    torch.cuda.empty_cache()
+    return out
+
+
 # ----------------------------------------------------------------------------- EA fitness throughput (cfg4)
 def ea_throughput(args, model, dev, world, rank):
     """EA.py:75-81 (get_acc) + :149-169 (eval_model): every candidate = set_active_modalities + one eval-mode pass over the
@@ -370,7 +430,8 @@ def ea_throughput(args, model, dev, world, rank):
     from mtb200.ea import EvolutionSearch
     was_training, was_engine = model.training, model.use_engine
     model.eval()
-    model.use_engine = False          # EA fitness runs on the per-op path (inference at B=2048; branch memoisation)
+    model.use_engine = False          # the training engine's regions are sized for 16 samples; memoised EA passes use the
+                                      # forward-only evaluation engine (model.eval_engine()), unmemoised ones the per-op path
     gen = torch.Generator().manual_seed(1)
     seq = (50, 50, 50)
     xs, y = synth_batch(args.ea_valid, seq, gen)
@@ -413,7 +474,7 @@ def ea_throughput(args, model, dev, world, rank):
     v, sec, n, chk = out["memo"]
     return {"metric": "ea_subnets_evaluated_per_s", "value": v, "unit": "subnets/s", "population": n, "valid": args.ea_valid,
             "seq": list(seq), "memoize": True, "n_gpus": world, "seconds": sec, "score_checksum": chk,
-            "engine": getattr(model, "ea_path", "per-op"),
+            "engine": "plan executor (forward-only regions, memoised branch outputs)" if model.__dict__.get("_eval_engine") is not None else "per-op",
             "unmemoized": {"value": out["nomemo"][0], "population": out["nomemo"][2], "seconds": out["nomemo"][1],
                            "note": "every candidate recomputes all its branches, like EA.py's sequential eval_model"}}
 

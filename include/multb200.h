@@ -212,7 +212,9 @@ typedef struct {
    * computed (bit j%32 of word j/32 of row (b*H+h)*Lq + i); the backward kernels read them instead of re-drawing the
    * Philox stream twice.  NULL: not stored / re-drawn.  Tensor-core engine only (the fp32 engine ignores it). */
   uint32_t* keep_bits;
-  int bf16;   /* bf16 data path (tensor-core engine only): q, k, v, o are bfloat16; scores, softmax, lse stay fp32 */
+  int bf16;   /* bf16 data path (tensor-core engine only), bit mask: 1 = q, k, v are bfloat16; 2 = o is bfloat16.
+                 Scores, softmax and lse stay fp32.  (The plan executor keeps q / k / v in fp32 -- their 25-element head
+                 rows fall below cp.async's 4-byte granularity at 2 bytes per element -- and writes o in bf16.) */
 } mtb_attn_desc;
 int mtb_attn_fwd(const mtb_attn_desc* d, int n, void* stream);
 
@@ -230,7 +232,7 @@ typedef struct {
   int Lq, Lk, B, H, hd;
   float scale; float p; mtb_rng rng;
   const uint32_t* keep_bits;   /* optional: the words the forward kernel stored (see mtb_attn_desc) */
-  int bf16;   /* bf16 data path: q, k, v, o, d_o, dq, dk, dv are bfloat16; lse / delta stay fp32 */
+  int bf16;   /* bf16 data path, bit mask: 1 = q, k, v; 2 = o; 4 = d_o; 8 = dq, dk, dv are bfloat16.  lse / delta stay fp32 */
 } mtb_attn_bwd_desc;
 int mtb_attn_bwd(const mtb_attn_bwd_desc* d, int n, void* stream);
 

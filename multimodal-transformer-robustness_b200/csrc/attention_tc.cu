@@ -151,21 +151,39 @@ __device__ __forceinline__ void stage_rows256(uint8_t* tile, const float* base, 
     }
   } else {
     // bf16 activations (bf16 data path): rows are 2 * hd bytes at 2-byte aligned offsets, below cp.async's 4-byte
-    // granularity -- each element is loaded through a register, widened to fp32 (exact: a 16-bit shift; a bf16 value is
-    // also a valid tf32 operand) and stored into the same swizzled slot.  The loads of one call are independent and
-    // issued back to back (one L2 latency per tile).
-    const uint16_t* base16 = reinterpret_cast<const uint16_t*>(base);
-    const uint16_t* src = base16 + ((int64_t)(l0 + r0) * B + b) * ld + h * hd + c;
+    // granularity.  Each element's slot receives the 4-byte-aligned WORD that contains the element (asynchronously, like
+    // the fp32 path); fix_rows256() -- run by the same thread once its copies have landed -- keeps the right half and
+    // widens it to fp32 in place (exact: a 16-bit shift; a bf16 value is also a valid tf32 operand).  The neighbouring
+    // element read along is always inside the tensor: leading dimensions and element counts are even.
+    const uint16_t* src = reinterpret_cast<const uint16_t*>(base) + ((int64_t)(l0 + r0) * B + b) * ld + h * hd + c;
     const int64_t sstep = (int64_t)8 * B * ld;
-#pragma unroll 8
+#pragma unroll 4
     for (int r = r0; r < rows; r += 8) {
       const bool ok = ok_c && (l0 + r < L);
-      uint32_t v = 0;
-      if (ok) v = (uint32_t)__ldg(src) << 16;
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(v) : "memory");
+      const void* sp = ok ? reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3) : reinterpret_cast<const void*>(base);
+      const int nbytes = ok ? 4 : 0;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(sp), "r"(nbytes) : "memory");
       src += sstep;
       dst += 8 * 128;
     }
+  }
+}
+// second half of the bf16 staging: every thread converts the slots IT copied (cp.async.wait_group makes a thread's own
+// copies visible to it), so no barrier is needed between the wait and this pass.  Zero-filled slots stay zero.
+template <bool MNSW>
+__device__ __forceinline__ void fix_rows256(uint8_t* tile, const float* base, int64_t ld, int B, int b, int h, int hd, int l0, int rows) {
+  const int c = threadIdx.x & 31, r0 = threadIdx.x >> 5;
+  // parity of the element's 2-byte index in memory: rows advance by 8 * B * ld elements (even), so it is per-thread constant
+  const uint64_t e0 = (uint64_t)(reinterpret_cast<uintptr_t>(base) >> 1) + (uint64_t)(((int64_t)(l0 + r0) * B + b) * ld + h * hd + c);
+  const bool hi = (e0 & 1) != 0;
+  uint32_t dst = a_smem_u32(tile) + (MNSW ? swz128_32(r0, c * 4) : swz128(r0, c * 4));
+#pragma unroll 4
+  for (int r = r0; r < rows; r += 8) {
+    uint32_t w;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(dst) : "memory");
+    w = hi ? (w & 0xffff0000u) : (w << 16);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(w) : "memory");
+    dst += 8 * 128;
   }
 }
 __device__ __forceinline__ void a_tmem_ld16(uint32_t taddr, float (&v)[16]) {
@@ -277,7 +295,8 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
   const int off = abs(Lk - Lq);
   const int Lk4 = a_round4(Lk);
   const DropCtx dc = make_drop(d.rng, d.p);
-  const bool bf = d.bf16 != 0;                      // q / k / v / o are bfloat16 in HBM
+  const bool bf = (d.bf16 & 1) != 0;                // q / k / v are bfloat16 in HBM
+  const bool bf_o = (d.bf16 & 2) != 0;              // o is bfloat16
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, half = warp >> 2;
   const int row = quad * 32 + lane;                 // query row inside the tile = TMEM lane
@@ -303,6 +322,11 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
   stage_rows256<false>(KV, d.k, d.ldk, d.B, b, h, hd, 0, Lk, TK, bf);
   stage_rows256<true>(KV + TK * 128, d.v, d.ldv, d.B, b, h, hd, 0, Lk, TK, bf);
   stage_wait();
+  if (bf) {
+    fix_rows256<false>(Qs, d.q, d.ldq, d.B, b, h, hd, i0, TQ);
+    fix_rows256<false>(KV, d.k, d.ldk, d.B, b, h, hd, 0, TK);
+    fix_rows256<true>(KV + TK * 128, d.v, d.ldv, d.B, b, h, hd, 0, TK);
+  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -362,6 +386,10 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
     if (wrow != nullptr && 2 * t + half < KW) wrow[2 * t + half] = kbits;
     ATRACE(8 + t * 8 + 3);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (bf && t + 1 < T) {
+      fix_rows256<false>(nxt, d.k, d.ldk, d.B, b, h, hd, j0 + TK, TK);
+      fix_rows256<true>(nxt + TK * 128, d.v, d.ldv, d.B, b, h, hd, j0 + TK, TK);
+    }
     fence_async_smem();
     __syncthreads();                          // P written, S read by everyone, next K / V landed
     ATRACE(8 + t * 8 + 4);
@@ -412,7 +440,7 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
     const int64_t oo = ((int64_t)i * d.B + b) * d.ldo + h * hd;
 #pragma unroll
     for (int c = 0; c < HP; ++c)
-      if (c < hd) st1_any(d.o, oo + c, (o[c] * wa + e[4 + c] * wb) * inv, bf);
+      if (c < hd) st1_any(d.o, oo + c, (o[c] * wa + e[4 + c] * wb) * inv, bf_o);
     if (d.lse) d.lse[(int64_t)bh * Lq + i] = m * 0.6931471805599453f + logf(l);
   }
   tc_fence_before();
@@ -472,7 +500,8 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
   const int off = abs(Lk - Lq);
   const int Lk4 = a_round4(Lk);
   const DropCtx dc = make_drop(d.rng, d.p);
-  const bool bf = d.bf16 != 0;                      // q / k / v / o / d_o / dq are bfloat16 in HBM
+  const bool bf = (d.bf16 & 1) != 0;                // q / k / v are bfloat16 in HBM
+  const bool bf_o = (d.bf16 & 2) != 0, bf_do = (d.bf16 & 4) != 0, bf_dx = (d.bf16 & 8) != 0;   // o, d_o, dq likewise
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, half = warp >> 2;
   const int row = quad * 32 + lane;
@@ -495,7 +524,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   stage_rows256<false>(Qs, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TQ, bf);
-  stage_rows256<false>(dOs, d.d_o, d.lddo, d.B, b, h, hd, i0, Lq, TQ, bf);
+  stage_rows256<false>(dOs, d.d_o, d.lddo, d.B, b, h, hd, i0, Lq, TQ, bf_do);
   stage_rows256<false>(Ks, d.k, d.ldk, d.B, b, h, hd, 0, Lk, TK, bf);
   stage_rows256<false>(Vs, d.v, d.ldv, d.B, b, h, hd, 0, Lk, TK, bf);
   stage_rows256<true>(Kmn, d.k, d.ldk, d.B, b, h, hd, 0, Lk, TK, bf);
@@ -504,11 +533,18 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
   float delta = 0.f, lse2 = 0.f;
   if (i < Lq) {
     const int64_t oo = ((int64_t)i * d.B + b) * d.ldo + h * hd, og = ((int64_t)i * d.B + b) * d.lddo + h * hd;
-    for (int c = 0; c < hd; ++c) delta = fmaf(ld1_any(d.o, oo + c, bf), ld1_any(d.d_o, og + c, bf), delta);
+    for (int c = 0; c < hd; ++c) delta = fmaf(ld1_any(d.o, oo + c, bf_o), ld1_any(d.d_o, og + c, bf_do), delta);
     lse2 = d.lse[(int64_t)bh * Lq + i] * 1.4426950408889634f;
     if (half == 0) d.delta[(int64_t)bh * Lq + i] = delta;
   }
   stage_wait();
+  if (bf_do) fix_rows256<false>(dOs, d.d_o, d.lddo, d.B, b, h, hd, i0, TQ);
+  if (bf) {
+    fix_rows256<false>(Qs, d.q, d.ldq, d.B, b, h, hd, i0, TQ);
+    fix_rows256<false>(Ks, d.k, d.ldk, d.B, b, h, hd, 0, TK);
+    fix_rows256<false>(Vs, d.v, d.ldv, d.B, b, h, hd, 0, TK);
+    fix_rows256<true>(Kmn, d.k, d.ldk, d.B, b, h, hd, 0, TK);
+  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -568,6 +604,11 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
       dq_math<true>(s, dp, lse2, delta, kbits, dc.on, dc.inv_keep, c2, d.scale, i, j0 + half * 32, Lk, off, my_ds, row);
     QTRACE(8 + t * 8 + 4);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (bf && t + 1 < T) {
+      fix_rows256<false>(Ks, d.k, d.ldk, d.B, b, h, hd, j0 + TK, TK);
+      fix_rows256<false>(Vs, d.v, d.ldv, d.B, b, h, hd, j0 + TK, TK);
+      fix_rows256<true>(Kmn + ((t + 1) & 1) * (TK * 128), d.k, d.ldk, d.B, b, h, hd, j0 + TK, TK);
+    }
     QTRACE(8 + t * 8 + 5);
     fence_async_smem();
     __syncthreads();                           // dS written, S / dP read by everyone, next K / V / Kmn landed
@@ -597,7 +638,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
       const int64_t qo = ((int64_t)i * d.B + b) * d.lddq + h * hd + half * 16;
 #pragma unroll
       for (int c = 0; c < 16; ++c)
-        if (half * 16 + c < hd) st1_any(d.dq, qo + c, dq[c], bf);
+        if (half * 16 + c < hd) st1_any(d.dq, qo + c, dq[c], bf_dx);
     }
   }
   tc_fence_before();
@@ -693,7 +734,8 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
   const int off = abs(Lk - Lq);
   const int Lk4 = a_round4(Lk);
   const DropCtx dc = make_drop(d.rng, d.p);
-  const bool bf = d.bf16 != 0;                      // q / k / v / d_o / dk / dv are bfloat16 in HBM
+  const bool bf = (d.bf16 & 1) != 0;                // q / k / v are bfloat16 in HBM
+  const bool bf_do = (d.bf16 & 4) != 0, bf_dx = (d.bf16 & 8) != 0;   // d_o, dk / dv likewise
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, half = warp >> 2;
   const int row = quad * 32 + lane;                 // key row inside the tile = TMEM lane
@@ -718,13 +760,25 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
   const int i_begin = (max(0, j0 - off) / TI) * TI;
   const int T = (Lq - i_begin + TI - 1) / TI;
   const float c2 = d.scale * 1.4426950408889634f;
+  auto fix_q = [&](int t) {                   // bf16 staging, second half (see fix_rows256)
+    uint8_t* qb = QB + (t & 1) * (4 * TI * 128);
+    const int i0 = i_begin + t * TI;
+    if (bf) {
+      fix_rows256<false>(qb, d.q, d.ldq, d.B, b, h, hd, i0, TI);
+      fix_rows256<true>(qb + 2 * TI * 128, d.q, d.ldq, d.B, b, h, hd, i0, TI);
+    }
+    if (bf_do) {
+      fix_rows256<false>(qb + TI * 128, d.d_o, d.lddo, d.B, b, h, hd, i0, TI);
+      fix_rows256<true>(qb + 3 * TI * 128, d.d_o, d.lddo, d.B, b, h, hd, i0, TI);
+    }
+  };
   auto stage_q = [&](int t) {                 // operand tiles + per-query-row lse / delta of query tile t
     uint8_t* qb = QB + (t & 1) * (4 * TI * 128);
     const int i0 = i_begin + t * TI;
     stage_rows256<false>(qb, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TI, bf);
-    stage_rows256<false>(qb + TI * 128, d.d_o, d.lddo, d.B, b, h, hd, i0, Lq, TI, bf);
+    stage_rows256<false>(qb + TI * 128, d.d_o, d.lddo, d.B, b, h, hd, i0, Lq, TI, bf_do);
     stage_rows256<true>(qb + 2 * TI * 128, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TI, bf);
-    stage_rows256<true>(qb + 3 * TI * 128, d.d_o, d.lddo, d.B, b, h, hd, i0, Lq, TI, bf);
+    stage_rows256<true>(qb + 3 * TI * 128, d.d_o, d.lddo, d.B, b, h, hd, i0, Lq, TI, bf_do);
     if (tid < TI) {
       const int ii = i0 + tid;
       col_lse2[t & 1][tid] = ii < Lq ? d.lse[(int64_t)bh * Lq + ii] * 1.4426950408889634f : 0.f;
@@ -735,6 +789,11 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
   stage_rows256<false>(Vs, d.v, d.ldv, d.B, b, h, hd, j0, Lk, TQ, bf);
   if (T > 0) stage_q(0);
   stage_wait();
+  if (bf) {
+    fix_rows256<false>(Ks, d.k, d.ldk, d.B, b, h, hd, j0, TQ);
+    fix_rows256<false>(Vs, d.v, d.ldv, d.B, b, h, hd, j0, TQ);
+  }
+  if ((bf || bf_do) && T > 0) fix_q(0);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -784,6 +843,7 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
     else
       dkv_math<true>(st, dpt, l2, dl, kw, dc.on, dc.inv_keep, c2, d.scale, i0 + half * 16, j, Lq, Lk, off, PTs, dSTs, row, half * 16);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if ((bf || bf_do) && t + 1 < T) fix_q(t + 1);
     fence_async_smem();
     __syncthreads();                           // P~^T / dS^T written, S^T / dP^T read by everyone, next operand tiles landed
     if (tid == 0) {                            // critical path first: the next tile's S^T / dP^T
@@ -822,7 +882,7 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
       const int64_t vo = ((int64_t)j * d.B + b) * d.lddv + h * hd + half * 16;
 #pragma unroll
       for (int c = 0; c < 16; ++c)
-        if (half * 16 + c < hd) { st1_any(d.dk, ko + c, dk[c], bf); st1_any(d.dv, vo + c, dv[c], bf); }
+        if (half * 16 + c < hd) { st1_any(d.dk, ko + c, dk[c], bf_dx); st1_any(d.dv, vo + c, dv[c], bf_dx); }
     }
   }
   tc_fence_before();

@@ -69,14 +69,25 @@ class GradSync:
 
     def _stage_hook(self, engine, params):
         """called by the plan executor right after a backward stage has been enqueued (its side-stream weight
-        gradients joined): the stage's gradient ranges start their all-reduce on NCCL's stream immediately"""
+        gradients joined): the stage's gradient ranges start their all-reduce on NCCL's stream immediately, as ONE
+        coalesced NCCL group call per stage (<= 5 per step), so the `mems` / three-level / two-level stages reduce under
+        the backward of the earlier ones"""
         rank, n = world()
         if n == 1 or not self.overlap or dist.get_backend(self.group) != "nccl":
             return
         # max_gap = 0: a merged gap could cover parameters of EARLIER stages whose weight gradients are still being
         # written by the compute stream -- an in-place async all-reduce over them would race with those writes
-        for lo, hi in self._ranges_of(engine, params, max_gap=0):
-            self._pending.append(dist.all_reduce(engine.grad_arena[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        rs = self._ranges_of(engine, params, max_gap=0)
+        if not rs:
+            return
+        try:
+            with dist._coalescing_manager(group=self.group, device=engine.grad_arena.device, async_ops=True) as cm:
+                for lo, hi in rs:
+                    dist.all_reduce(engine.grad_arena[lo:hi], op=dist.ReduceOp.AVG, group=self.group)
+            self._pending.append(cm)
+        except Exception:                          # private API moved: one call per range
+            for lo, hi in rs:
+                self._pending.append(dist.all_reduce(engine.grad_arena[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True))
         self._done.update(id(p) for p in params)
 
     def flat_ranges(self, engine):

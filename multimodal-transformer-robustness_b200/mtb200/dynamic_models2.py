@@ -180,6 +180,7 @@ class DynamicMULTModel(nn.Module):
         device pointers and is rebuilt lazily after loading"""
         state = self.__dict__.copy()
         state["_engine"] = None
+        state.pop("_eval_engine", None)
         state.pop("_outside_cache", None)
         return state
 
@@ -193,7 +194,31 @@ class DynamicMULTModel(nn.Module):
 
     # ------------------------------------------------------------------ plan-executor path
     def reset_engine(self):
-        self._engine = None
+        for attr in ("_engine", "_eval_engine"):
+            eng = self.__dict__.get(attr)
+            self.__dict__[attr] = None
+            if eng is not None:
+                eng.release()
+
+    def eval_engine(self):
+        """forward-only plan executor for memoised evaluation (EA fitness): its own persistent regions, sized for inference"""
+        eng = self.__dict__.get("_eval_engine")
+        if eng is None:
+            from .engine import Engine
+            seed = ops.rng.seed if ops.rng.seed is not None else torch.initial_seed()
+            eng = self.__dict__["_eval_engine"] = Engine(self, next(self.parameters()).device, seed=seed, inference_only=True)
+        return eng
+
+    def _forward_engine_memo(self, x, branch_cache: dict):
+        """EA fitness on the plan executor: branch outputs live in the evaluation engine's persistent regions and are reused
+        across candidates for as long as the same ``branch_cache`` dict (= same validation batch, same weights) is passed"""
+        eng = self.eval_engine()
+        meta = tuple((int(t.shape[1]), int(t.shape[0])) for t in x)
+
+        def px_fn():
+            return [self.proj[i](x[i]).permute(2, 0, 1) for i in range(self.modality_num)]
+        branch_cache.setdefault("engine", True)
+        return eng.forward_memo(px_fn, meta, branch_cache), []
 
     def engine(self):
         if self._engine is None:
@@ -227,8 +252,8 @@ class DynamicMULTModel(nn.Module):
             self._outside_cache = ps
         return ps
 
-    def _engine_ok(self, x) -> bool:
-        if not self.use_engine or self.all_steps or not x[0].is_cuda or self.d % 4 != 0:
+    def _engine_ok(self, x, ignore_switch: bool = False) -> bool:
+        if (not self.use_engine and not ignore_switch) or self.all_steps or not x[0].is_cuda or self.d % 4 != 0:
             return False
         sa = self.trans_mems0['mems0' + self.modality_list[0]].layers
         for encs in (self.trans_mems0, self.trans, self.trans_mems):
@@ -268,6 +293,8 @@ class DynamicMULTModel(nn.Module):
         assert len(x) == self.modality_num
         if branch_cache is not None:
             assert not self.training and not torch.is_grad_enabled(), "branch_cache is for no-grad evaluation"
+            if self.__dict__.get("memo_engine", True) and self._engine_ok(x, True) and all(isinstance(pj, Conv1x1FrontEnd) for pj in self.proj):
+                return self._forward_engine_memo(x, branch_cache)
         elif self._engine_ok(x):
             return self._forward_engine(x)
         need = self._needed_modalities() if self.prune_dead_branches else set(self.modality_list)

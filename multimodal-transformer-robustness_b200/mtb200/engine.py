@@ -331,6 +331,10 @@ class PlanBuilder:
         tr = self.training
         ng = self.need_grad
         Hs = self.H
+        # q / k / v (and d_o in backward) stay fp32 even in the bf16 data path: a head's 25-element rows start at odd
+        # element offsets, which at 2 bytes per element falls below cp.async's 4-byte granularity -- the attention kernels
+        # would have to post-process every staged element (measured: +25-70 % kernel time).  Everything the GEMMs read is bf16.
+        Qs = 4
         # 1. embed (q, k, v streams) -------------------------------------------------------
         descs = []
         for e in group:
@@ -409,16 +413,16 @@ class PlanBuilder:
                     # pruned final layer: q from the last step only, k / v (packed) from every step
                     xn = e.saved["xn"]
                     xq = xn.rows_slice(r0, Tr)
-                    q, kv = A.mat(Tr, D, Hs), A.mat(Tq, 2 * D, Hs)
+                    q, kv = A.mat(Tr, D, Qs), A.mat(Tq, 2 * D, Qs)
                     S["q_last"], S["kv"] = q, kv
                     descs.append(self.lin(xq, W, b, q, D, e.E, col_idx=cidx, csegs=_segs(e.mask)))
                     descs.append(self.lin(xn, W, b, kv, 2 * D, e.E, row0=D, col_idx=cidx, csegs=_segs(e.mask)))
                 elif not e.cross:
-                    qkv = A.mat(Tq, 3 * D, Hs)
+                    qkv = A.mat(Tq, 3 * D, Qs)
                     S["qkv"] = qkv
                     descs.append(self.lin(e.saved["xn"], W, b, qkv, 3 * D, e.E, col_idx=cidx, csegs=_segs(e.mask)))
                 else:
-                    q, k, v = A.mat(Tq, D, Hs), A.mat(Tk, D, Hs), A.mat(Tk, D, Hs)
+                    q, k, v = A.mat(Tq, D, Qs), A.mat(Tk, D, Qs), A.mat(Tk, D, Qs)
                     S["q"], S["k"], S["v"] = q, k, v
                     srcs = (e.saved["xn"], S["kn"][0], S["vn"][0])
                     for part, (src, dst) in enumerate(zip(srcs, (q, k, v))):
@@ -454,7 +458,7 @@ class PlanBuilder:
                 bits = A.alloc(e.B * H * Lq_a * ((e.Lk + 31) // 32)) if (ng and pa > 0.0 and lib.mtb_get_gemm_mode() >= 1) else None
                 S["keep_bits"] = bits
                 descs.append(AttnDesc(qm.ptr, qm.ld, km.ptr, km.ld, vm.ptr, vm.ld, o.ptr, o.ld, lse, Lq_a, e.Lk, e.B, H, hd,
-                                      hd ** -0.5, pa, r, bits, o.h))
+                                      hd ** -0.5, pa, r, bits, qm.h | (o.h << 1)))
             self.emit(self.fwd, lib.mtb_attn_fwd, AttnDesc, descs, f"attn[{i}]")
             # d. out-projection ----------------------------------------------------------------
             descs = []
@@ -643,7 +647,7 @@ class PlanBuilder:
                 Wo = sa.out_proj.weight
                 ridx = e.mask.idx.data_ptr() if e.mask is not None else None
                 sg = _segs(e.mask)
-                g_o = A.mat(Tq, D, Hs)
+                g_o = A.mat(Tq, D, 4)                 # fp32: streamed operand of the attention backward kernels (see Qs)
                 S["g_o"] = g_o
                 if defer:
                     descs.append(self.lin_bwd(S["g_a"], Wo, e.E, D, dX=g_o, row_idx=ridx, rsegs=sg))
@@ -678,7 +682,8 @@ class PlanBuilder:
                 r, pa = S["rng_attn"]
                 descs.append(AttnBwdDesc(qm.ptr, qm.ld, km.ptr, km.ld, vm.ptr, vm.ld, S["o"].ptr, S["o"].ld, S["g_o"].ptr, S["g_o"].ld,
                                          S["lse"], delta, dq.ptr, dq.ld, dk.ptr, dk.ld, dv.ptr, dv.ld, Lq_a, e.Lk, e.B, H, hd,
-                                         hd ** -0.5, pa, r, S.get("keep_bits"), qm.h))
+                                         hd ** -0.5, pa, r, S.get("keep_bits"),
+                                         qm.h | (S["o"].h << 1) | (S["g_o"].h << 2) | (dq.h << 3)))
             self.emit(self.bwd, lib.mtb_attn_bwd, AttnBwdDesc, descs, f"attn_bwd[{i}]")
             # b'. in-projection backward
             descs, descs_q = [], []
@@ -913,7 +918,7 @@ def _install_fast_attrs(model):
 class Engine:
     """Owns the arenas and the plan cache of one DynamicMULTModel on one device."""
 
-    def __init__(self, model, device, seed: int = 0, graph_after: int = -1):
+    def __init__(self, model, device, seed: int = 0, graph_after: int = -1, inference_only: bool = False):
         # graph_after: capture a plan into CUDA graphs once it has been hit more than this many times
         # (-1 = never).  Off by default: under `random_sample` almost every step draws a new
         # sub-network, and a capture costs far more than the eager run of a cached plan; fixed-config
@@ -926,6 +931,11 @@ class Engine:
                 _ops.preload()
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.graph_after = graph_after
+        # inference_only: no backward, no gradient arena; the persistent regions are sized from a forward-only dry run
+        # (what a 2048-sample EA validation batch needs), and branch outputs can be memoised between forwards
+        self.inference_only = inference_only
+        self._memo_token = None
+        self._memo_valid: Dict[int, tuple] = {}
         self.plans: Dict[tuple, Plan] = {}
         self.arena: Optional[Arena] = None
         self.enc_buf: Optional[torch.Tensor] = None
@@ -946,9 +956,14 @@ class Engine:
         for p in self.params:
             self._grad_off[id(p)] = total
             total += (p.numel() + 63) // 64 * 64
-        self.grad_arena = torch.zeros(total, dtype=torch.float32, device=self.device)
-        self.grad_views = {id(p): self.grad_arena[self._grad_off[id(p)]:self._grad_off[id(p)] + p.numel()].view(p.shape)
-                           for p in self.params}
+        self._arena_numel = total
+        if inference_only:
+            self.grad_arena = torch.zeros(1, dtype=torch.float32, device=self.device)
+            self.grad_views = {}
+        else:
+            self.grad_arena = torch.zeros(total, dtype=torch.float32, device=self.device)
+            self.grad_views = {id(p): self.grad_arena[self._grad_off[id(p)]:self._grad_off[id(p)] + p.numel()].view(p.shape)
+                               for p in self.params}
         self.shadow: Optional[torch.Tensor] = None
         self._shadow_ver: Dict[int, int] = {}
         self.rng_state = torch.zeros(2, dtype=torch.int64, device=self.device)     # {seed_add, offset_add}
@@ -973,12 +988,27 @@ class Engine:
     def grad_ptr(self, p) -> int:
         return self.grad_arena.data_ptr() + F4 * self._grad_off[id(p)]
 
+    def release(self):
+        """Drop every cached plan and the persistent activation buffer NOW (not whenever the garbage collector gets to
+        this object: the prewarm freezes the GC generations, and a data-parallel hook may hold a reference cycle)."""
+        self.plans.clear()
+        self._enc_cache.clear()
+        self._merge_cache.clear()
+        self._warmed.clear()
+        self._memo_token, self._memo_valid = None, {}
+        self.last_plan = None
+        self.enc_buf = None
+        self.arena = None
+        self._layout = None
+        self._regions = {}
+        self.stage_hook = None
+
     # -- bf16 data path: bf16 shadow of every weight, laid out like the gradient arena.  The fp32 parameters stay the master
     #    copy (optimizer, checkpoints); the fused Adam kernel rewrites the shadow of what it updates, any other in-place
     #    update is noticed through the tensor version counter and re-cast before the next forward.
     def shadow_ptr(self, p) -> int:
         if self.shadow is None:
-            self.shadow = torch.empty(self.grad_arena.numel(), dtype=torch.bfloat16, device=self.device)
+            self.shadow = torch.empty(self._arena_numel, dtype=torch.bfloat16, device=self.device)
             self._shadow_ver = {}
         return self.shadow.data_ptr() + 2 * self._grad_off[id(p)]
 
@@ -1076,13 +1106,15 @@ class Engine:
             for mode in (0, 1, 2):               # the GEMM engines allocate different scratch / element sizes
                 lib.mtb_set_gemm_mode(mode)
                 ca = CountingArena()
-                pb = PlanBuilder(self, ca, True, True)
+                grad = not self.inference_only
+                pb = PlanBuilder(self, ca, grad, grad)
                 src = (1 << 20, B * E, E, 1)
                 e = EncSpec("", enc, Lq, Lk, B, E, len(layers), mask, src, src if kind == "cross" else None,
                             Mat(1 << 20, Lq * B, E), kind, name)
                 pb.encoders_forward([e])
-                e.d_out = Mat(1 << 20, Lq * B, E)
-                pb.encoders_backward([e])
+                if grad:
+                    e.d_out = Mat(1 << 20, Lq * B, E)
+                    pb.encoders_backward([e])
                 peak = max(peak, ca.peak)
             return peak
         finally:
@@ -1128,7 +1160,7 @@ class Engine:
             else:
                 Lk, E, mask = Lq, d, None
             r = Region()
-            r.out, r.dout = take(Lq * B * E), take(Lq * B * E)
+            r.out, r.dout = take(Lq * B * E), take(0 if self.inference_only else Lq * B * E)
             r.cat = take(Lq * B * E) if kind == "mems" else None
             r.work_cap = int(self._measure(kind, name, enc, Lq, Lk, B, E, mask) * 1.02) + (1 << 20)
             r.work = take(r.work_cap // F4)
@@ -1384,10 +1416,14 @@ class Engine:
             C_total += w
         groups.append(gm)
 
+        eval_stages = []                     # (ops that always run before the stage, encoder plans of the stage, is the `mems` stage)
         for gi, g in enumerate(groups):
+            n0 = len(pb.fwd)
             if gi == len(groups) - 1:
                 pb.addn(pb.fwd, cat_items, "cat_gather")
+            eval_stages.append((pb.fwd[n0:], list(g), gi == len(groups) - 1))
             self._merge(pb.fwd, g, "fwd")
+        n_head0 = len(pb.fwd)
 
         # head ---------------------------------------------------------------------------------
         assert not m.all_steps, "engine path implements the last-step head (all_steps=False)"
@@ -1420,6 +1456,7 @@ class Engine:
         pb.emit(pb.fwd, lib.mtb_linear_fwd, LinearDesc, [pb.lin(z3, W3, b3, pred, m.output_dim, C_total, col_idx=hp, csegs=hs)], "out_layer")
 
         plan.inputs = [(i, stage_in[ch]) for i, ch in enumerate(names) if ch in need]
+        plan.eval_stages, plan.eval_head = eval_stages, pb.fwd[n_head0:]
         plan._pred_mat = pred
         plan._stage_in = stage_in
 
@@ -1571,6 +1608,52 @@ class Engine:
             side = self._side
         _run(ops, stream, side, self.stage_hook if which == "bwd" else None, self if not torch.cuda.is_current_stream_capturing() else None)
         self.stats["eager_runs"] += 1
+
+    def forward_memo(self, px_fn, meta, token) -> torch.Tensor:
+        """Inference with memoised branch outputs (EA fitness, EA.py:149-169: many candidate sub-networks scored on the SAME
+        validation batch with the SAME weights).  Every encoder owns a persistent output region, so a `mems0` stack or a
+        cross-modal branch that already ran for this batch (`token`) under the same configuration is simply not run again:
+        a candidate only costs its masked `mems` stacks and the head.  ``px_fn()`` returns the front-end outputs of ALL
+        modalities ([L, B, d] views) and is only called when ``token`` changes; ``meta`` = ((L, B), ...) per modality.
+        Invalidate with a new token whenever weights or inputs change."""
+        m = self.model
+        assert not torch.is_grad_enabled() and not m.training, "forward_memo is for no-grad evaluation"
+        plan = self.plan_for(meta, False, False)
+        plan.hits += 1
+        self.generation += 1
+        if plan.used_weights:
+            self.refresh_shadow(plan.used_weights)
+        if token is not self._memo_token:
+            self._memo_token = token
+            self._memo_valid = {}
+            px = px_fn()
+            for i, ch in enumerate(m.modality_list):
+                L, B = meta[i]
+                self.view(Mat(self._stage_ptr[ch], L * B, m.d)).view(L, B, m.d).copy_(px[i])
+        self.last_plan = plan
+        stream = torch.cuda.current_stream().cuda_stream
+        valid = self._memo_valid
+        for si, (pre_ops, eps, is_mems) in enumerate(plan.eval_stages):
+            if pre_ops:
+                _run(pre_ops, stream)
+            run = eps if is_mems else [ep for ep in eps if valid.get(id(ep.spec.enc), (None,))[0] is not ep]
+            if not run:
+                continue
+            if not is_mems:
+                # a producer is being (re)computed: whatever consumed an older version of it is stale
+                for k in [k for k, (_, s2) in valid.items() if s2 > si]:
+                    del valid[k]
+            lst: List = []
+            self._merge(lst, run, "fwd")
+            _run(lst, stream, None, None, self)
+            self.stats["memo_encoder_runs"] = self.stats.get("memo_encoder_runs", 0) + len(run)
+            self.stats["memo_encoder_skips"] = self.stats.get("memo_encoder_skips", 0) + len(eps) - len(run)
+            if not is_mems:
+                for ep in run:
+                    valid[id(ep.spec.enc)] = (ep, si)
+        _run(plan.eval_head, stream)
+        self.stats["eager_runs"] += 1
+        return plan.pred.clone()
 
     def forward(self, px: Sequence[torch.Tensor]) -> torch.Tensor:
         """px[i]: front-end output of modality i as a [L, B, d] view (any strides)."""

@@ -198,22 +198,26 @@ def test_addn_mixed_types(bf16_mode):
 
 
 @pytest.mark.parametrize("Lq,Lk,B,H,hd", [(50, 50, 4, 8, 25), (500, 50, 2, 8, 25), (50, 500, 2, 8, 25), (300, 300, 2, 8, 25), (70, 130, 2, 4, 32)])
-def test_attention_bf16_io(bf16_mode, Lq, Lk, B, H, hd):
-    """q / k / v / o / d_o / dq / dk / dv in bf16; scores, softmax, lse in fp32 (tcgen05 kernels, dropout replayed)"""
+@pytest.mark.parametrize("mixed", [False, True], ids=["all_bf16", "engine_mix"])
+def test_attention_bf16_io(bf16_mode, Lq, Lk, B, H, hd, mixed):
+    """all_bf16: q / k / v / o / d_o / dq / dk / dv in bf16.  engine_mix: what the plan executor uses -- q / k / v / d_o fp32
+    (bf16-valued here so both variants share one reference), o / dq / dk / dv bf16.  Scores, softmax, lse in fp32
+    (tcgen05 kernels, dropout replayed)."""
     L = _lib()
     ops = bf16_mode
     g = torch.Generator().manual_seed(Lq * 7 + Lk)
     D = H * hd
-    q = (torch.randn(Lq * B, D, generator=g)).to(BF).cuda()
-    k = (torch.randn(Lk * B, D, generator=g)).to(BF).cuda()
-    v = (torch.randn(Lk * B, D, generator=g)).to(BF).cuda()
+    IN = torch.float32 if mixed else BF
+    q = (torch.randn(Lq * B, D, generator=g)).to(BF).to(IN).cuda()
+    k = (torch.randn(Lk * B, D, generator=g)).to(BF).to(IN).cuda()
+    v = (torch.randn(Lk * B, D, generator=g)).to(BF).to(IN).cuda()
     o = torch.full((Lq * B, D), float("nan"), dtype=BF, device="cuda")
     lse = torch.empty(B * H * Lq, device="cuda")
     p, scale = 0.1, hd ** -0.5
     Lk4 = (Lk + 3) // 4 * 4
     bits = torch.zeros(B * H * Lq * ((Lk + 31) // 32), dtype=torch.int32, device="cuda")
     d = L.AttnDesc(q.data_ptr(), D, k.data_ptr(), D, v.data_ptr(), D, o.data_ptr(), D, lse.data_ptr(), Lq, Lk, B, H, hd, scale, p,
-                   L.Rng(11, 3, None), bits.data_ptr(), 1)
+                   L.Rng(11, 3, None), bits.data_ptr(), 2 if mixed else 3)
     L.check(L.lib.mtb_attn_fwd((L.AttnDesc * 1)(d), 1, _stream()), "attn_fwd")
     keep = ops.dropout_mask(11, 3, p, B * H * Lq * Lk4, "cuda").view(B, H, Lq, Lk4)[..., :Lk].double().cpu()
     qd = q.double().cpu().view(Lq, B, H, hd).permute(1, 2, 0, 3).requires_grad_(True)
@@ -228,11 +232,11 @@ def test_attention_bf16_io(bf16_mode, Lq, Lk, B, H, hd):
     ref_t = ref.permute(2, 0, 1, 3).reshape(Lq * B, D)
     assert torch.isfinite(o.float()).all()
     assert rel(o, ref_t) < 8e-3, rel(o, ref_t)
-    d_o = torch.randn(Lq * B, D, generator=g).to(BF).cuda()
+    d_o = torch.randn(Lq * B, D, generator=g).to(BF).to(IN).cuda()
     dq, dk, dv = (torch.full((n, D), float("nan"), dtype=BF, device="cuda") for n in (Lq * B, Lk * B, Lk * B))
     delta = torch.empty(B * H * Lq, device="cuda")
     db = L.AttnBwdDesc(q.data_ptr(), D, k.data_ptr(), D, v.data_ptr(), D, o.data_ptr(), D, d_o.data_ptr(), D, lse.data_ptr(), delta.data_ptr(),
-                       dq.data_ptr(), D, dk.data_ptr(), D, dv.data_ptr(), D, Lq, Lk, B, H, hd, scale, p, L.Rng(11, 3, None), bits.data_ptr(), 1)
+                       dq.data_ptr(), D, dk.data_ptr(), D, dv.data_ptr(), D, Lq, Lk, B, H, hd, scale, p, L.Rng(11, 3, None), bits.data_ptr(), 10 if mixed else 15)
     L.check(L.lib.mtb_attn_bwd((L.AttnBwdDesc * 1)(db), 1, _stream()), "attn_bwd")
     ref.backward(d_o.double().cpu().view(Lq, B, H, hd).permute(1, 2, 0, 3))
     for name, got, want, n in (("dq", dq, qd.grad, Lq), ("dk", dk, kd.grad, Lk), ("dv", dv, vd.grad, Lk)):

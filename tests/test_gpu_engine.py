@@ -489,3 +489,40 @@ def test_engine_backward_of_a_stale_forward_raises():
     with pytest.raises(RuntimeError, match="no longer the engine's latest"):
         p1.sum().backward()
     p2.sum().backward()                # the latest forward is fine
+
+
+def test_memoised_evaluation_engine_equals_per_op_path():
+    """EA fitness (EA.py:149-169) on the forward-only plan executor: branch outputs memoised in persistent regions across
+    candidates == the per-op path evaluated from scratch, for a stream of sampled candidates incl. repeats, a change of
+    the `mems0` depth (invalidates consumers) and a new validation batch (new token)."""
+    from mtb200 import ops
+    from mtb200.dynamic_models2 import DynamicMULTModel
+    ops.set_gemm_mode("fp32")
+    torch.manual_seed(17)
+    m = DynamicMULTModel(origin_dimensions=[12, 7, 5], dimension=40, num_heads=8, head_dim=5, layers_single_attn=2,
+                         layers_hybrid_attn=2, layers_self_attn=2, attn_dropout=[0.1, 0.1, 0.0, 0.0], relu_dropout=0.1,
+                         res_dropout=0.3, out_dropout=0.1, embed_dropout=0.3, attn_mask=True, output_dim=1,
+                         modality_set=["l", "a", "v"], all_steps=False, front_end="conv1d").cuda().eval()
+    m.use_engine = False                       # the memo path is independent of the training engine switch
+    xs = [torch.randn(6, 9, d, device="cuda") for d in (12, 7, 5)]
+    xs2 = [torch.randn(6, 9, d, device="cuda") for d in (12, 7, 5)]
+    cands = [m.gen_active_cross([0, 1, 2]) for _ in range(10)]
+    cands = cands + cands[:3]
+    with torch.no_grad():
+        cache = {}
+        for k, (cross, outs) in enumerate(cands):
+            if k == 7:
+                m.trans_mems0["mems0a"].set_active(1, 40, 8, 5)        # a producer changes: its consumers must be recomputed
+            m.set_active_modalities([0, 1, 2], cross, outs)
+            m.memo_engine = True
+            a, _ = m(xs, branch_cache=cache)
+            m.memo_engine = False
+            b, _ = m(xs, branch_cache={})
+            assert_rel(a, b, 2e-5, f"candidate {k}")
+        st = m.eval_engine().stats
+        assert st["memo_encoder_skips"] > st["memo_encoder_runs"] // 4, st        # memoisation actually happened
+        m.memo_engine = True
+        a2, _ = m(xs2, branch_cache={})                                             # new batch -> new token -> everything recomputed
+        m.memo_engine = False
+        b2, _ = m(xs2, branch_cache={})
+        assert_rel(a2, b2, 2e-5, "new batch")

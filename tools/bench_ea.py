@@ -7,6 +7,7 @@ import argparse, json, os, sys, time, types
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench as B
+B._product_paths()
 import torch
 import torch.distributed as dist
 

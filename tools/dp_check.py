@@ -4,6 +4,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench as B
+B._product_paths()
 import torch
 import torch.distributed as dist
 from mtb200 import ops

@@ -3,6 +3,7 @@ import os, sys, cProfile, pstats
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench as B
+B._product_paths()
 import torch
 from mtb200 import ops
 from mtb200.train import sample_next_config

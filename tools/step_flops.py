@@ -8,6 +8,7 @@ for p in (os.path.join(ROOT, "multimodal-transformer-robustness_b200"), ROOT):
     sys.path.insert(0, p)
 import torch
 import bench as B
+B._product_paths()
 from mtb200 import _lib
 from mtb200.engine import Batch, Engine, Op
 from mtb200.train import sample_next_config
