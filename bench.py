@@ -188,7 +188,7 @@ def run_reference(args):
             "gpu_launches": 0, "ms_per_step_min": min(times) * 1e3, "ms_per_step_max": max(times) * 1e3}
     if world > 1:
         line["note"] = "single host process (rank 0); the other ranks exit without work"
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def _harness(argv, timeout):
@@ -312,6 +312,10 @@ def main():
     clk = clocks.stop() if clocks else None
     ms, ms_e2e = statistics.median(t_val), statistics.median(t_e2e)
 
+    eng0 = getattr(model, "_engine", None)
+    engine_stats = {k: int(v) for k, v in eng0.stats.items()} if eng0 is not None else None
+    if eng0 is not None:
+        engine_stats["stage_graphs_after_hits"] = eng0.stage_graphs
     cfg3 = None
     if args.workload == "cfg2" and not args.no_cfg3:
         cfg3 = cfg3_throughput(args, model, opt, crit, sync, dev, world, rank)
@@ -330,10 +334,8 @@ def main():
                         "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / K, "ms_per_step_min": min(t_e2e) / K,
                         "ms_per_step_max": max(t_e2e) / K},
                 "gpu_launches": int(launches)}
-        eng = getattr(model, "_engine", None)
-        if eng is not None:
-            line["engine"] = {k: int(v) for k, v in eng.stats.items()}
-            line["engine"]["stage_graphs_after_hits"] = eng.stage_graphs
+        if engine_stats is not None:
+            line["engine"] = engine_stats
         if ea is not None:
             line["ea"] = ea
         if cfg3 is not None:
@@ -361,7 +363,7 @@ def main():
                 "speedup_vs_stock": (stock["ms_per_step"] / (ms / K)) if "ms_per_step" in stock else None,
                 "speedup_vs_clean": (clean["ms_per_step"] / (ms / K)) if "ms_per_step" in clean else None,
                 "errors": [r["error"] for r in (stock, clean) if "error" in r] or None}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

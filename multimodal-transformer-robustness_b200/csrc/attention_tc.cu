@@ -199,6 +199,37 @@ __device__ __forceinline__ void a_tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Store vals[0 .. n) (n <= N) as one head's row at ELEMENT offset `off` of a tensor that is fp32 or bf16.  bf16 rows start at
+// 2-byte aligned offsets: elements are paired into 4-byte words (one cvt.rn.bf16x2 + one store per pair) around an optional
+// leading / trailing single element; the parity is uniform across a CTA (leading dimensions are even, so it is h * hd & 1).
+template <int N>
+__device__ __forceinline__ void store_row(void* base, int64_t off, const float (&vals)[N], int n, bool bf16) {
+  if (!bf16) {
+    float* p = reinterpret_cast<float*>(base) + off;
+#pragma unroll
+    for (int c = 0; c < N; ++c)
+      if (c < n) p[c] = vals[c];
+    return;
+  }
+  uint16_t* p = reinterpret_cast<uint16_t*>(base) + off;
+  if ((reinterpret_cast<uintptr_t>(p) & 2) == 0) {
+#pragma unroll
+    for (int c = 0; c + 1 < N; c += 2) {
+      if (c + 1 < n) *reinterpret_cast<uint32_t*>(p + c) = pack_bf16x2(vals[c], vals[c + 1]);
+      else if (c < n) p[c] = (uint16_t)(pack_bf16x2(vals[c], 0.f) & 0xffffu);
+    }
+    if ((N & 1) && N - 1 < n) p[N - 1] = (uint16_t)(pack_bf16x2(vals[N - 1], 0.f) & 0xffffu);
+  } else {
+    if (0 < n) p[0] = (uint16_t)(pack_bf16x2(vals[0], 0.f) & 0xffffu);
+#pragma unroll
+    for (int c = 1; c + 1 < N; c += 2) {
+      if (c + 1 < n) *reinterpret_cast<uint32_t*>(p + c) = pack_bf16x2(vals[c], vals[c + 1]);
+      else if (c < n) p[c] = (uint16_t)(pack_bf16x2(vals[c], 0.f) & 0xffffu);
+    }
+    if (!(N & 1) && N - 1 < n) p[N - 1] = (uint16_t)(pack_bf16x2(vals[N - 1], 0.f) & 0xffffu);
+  }
+}
+
 #ifdef MTB_TC_TRACE
 __device__ unsigned long long g_attn_trace[128];
 __device__ __forceinline__ unsigned long long a_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) :: "memory"); return t; }
@@ -439,8 +470,8 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
     const float inv = 1.f / l;
     const int64_t oo = ((int64_t)i * d.B + b) * d.ldo + h * hd;
 #pragma unroll
-    for (int c = 0; c < HP; ++c)
-      if (c < hd) st1_any(d.o, oo + c, (o[c] * wa + e[4 + c] * wb) * inv, bf_o);
+    for (int c = 0; c < HP; ++c) o[c] = (o[c] * wa + e[4 + c] * wb) * inv;
+    store_row<HP>(d.o, oo, o, hd, bf_o);
     if (d.lse) d.lse[(int64_t)bh * Lq + i] = m * 0.6931471805599453f + logf(l);
   }
   tc_fence_before();
@@ -636,9 +667,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
     a_tmem_ld16(t_dq + lane_addr + half * 16, dq);
     if (i < Lq) {
       const int64_t qo = ((int64_t)i * d.B + b) * d.lddq + h * hd + half * 16;
-#pragma unroll
-      for (int c = 0; c < 16; ++c)
-        if (half * 16 + c < hd) st1_any(d.dq, qo + c, dq[c], bf_dx);
+      store_row<16>(d.dq, qo, dq, hd - half * 16, bf_dx);
     }
   }
   tc_fence_before();
@@ -880,9 +909,8 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
     if (j < Lk) {
       const int64_t ko = ((int64_t)j * d.B + b) * d.lddk + h * hd + half * 16;
       const int64_t vo = ((int64_t)j * d.B + b) * d.lddv + h * hd + half * 16;
-#pragma unroll
-      for (int c = 0; c < 16; ++c)
-        if (half * 16 + c < hd) { st1_any(d.dk, ko + c, dk[c], bf_dx); st1_any(d.dv, vo + c, dv[c], bf_dx); }
+      store_row<16>(d.dk, ko, dk, hd - half * 16, bf_dx);
+      store_row<16>(d.dv, vo, dv, hd - half * 16, bf_dx);
     }
   }
   tc_fence_before();

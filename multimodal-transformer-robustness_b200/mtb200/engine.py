@@ -935,7 +935,7 @@ class Engine:
         # (what a 2048-sample EA validation batch needs), and branch outputs can be memoised between forwards
         self.inference_only = inference_only
         self._memo_token = None
-        self._memo_valid: Dict[int, tuple] = {}
+        self._memo_valid: Dict[str, object] = {}
         self.plans: Dict[tuple, Plan] = {}
         self.arena: Optional[Arena] = None
         self.enc_buf: Optional[torch.Tensor] = None
@@ -1632,17 +1632,22 @@ class Engine:
                 self.view(Mat(self._stage_ptr[ch], L * B, m.d)).view(L, B, m.d).copy_(px[i])
         self.last_plan = plan
         stream = torch.cuda.current_stream().cuda_stream
-        valid = self._memo_valid
+        valid = self._memo_valid             # encoder name ('a', 'la', 'lav', ...) -> the EncPlan whose output its region holds
         for si, (pre_ops, eps, is_mems) in enumerate(plan.eval_stages):
             if pre_ops:
                 _run(pre_ops, stream)
-            run = eps if is_mems else [ep for ep in eps if valid.get(id(ep.spec.enc), (None,))[0] is not ep]
+            run = eps if is_mems else [ep for ep in eps if valid.get(ep.spec.name) is not ep]
             if not run:
                 continue
             if not is_mems:
-                # a producer is being (re)computed: whatever consumed an older version of it is stale
-                for k in [k for k, (_, s2) in valid.items() if s2 > si]:
-                    del valid[k]
+                # a producer is being (re)computed: every branch that read an older version of it is stale -- branch 'xyz'
+                # reads 'z' (queries) and 'xy' (keys / values); later stages are checked when their turn comes
+                stale = [ep.spec.name for ep in run]
+                while stale:
+                    n = stale.pop()
+                    for k in [k for k in valid if len(k) > len(n) and (k[:-1] == n or (len(n) == 1 and k[-1] == n))]:
+                        del valid[k]
+                        stale.append(k)
             lst: List = []
             self._merge(lst, run, "fwd")
             _run(lst, stream, None, None, self)
@@ -1650,7 +1655,7 @@ class Engine:
             self.stats["memo_encoder_skips"] = self.stats.get("memo_encoder_skips", 0) + len(eps) - len(run)
             if not is_mems:
                 for ep in run:
-                    valid[id(ep.spec.enc)] = (ep, si)
+                    valid[ep.spec.name] = ep
         _run(plan.eval_head, stream)
         self.stats["eager_runs"] += 1
         return plan.pred.clone()
