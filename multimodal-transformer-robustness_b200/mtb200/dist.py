@@ -32,10 +32,14 @@ class GradSync:
         self.group = group
         self.last_active = 0
         self.last_bytes = 0
-        # Optional (MTB_DP_OVERLAP=1): reduce each backward stage's gradients while the earlier stages still run.  Off by
-        # default: at 16 samples per GPU the extra NCCL launches cost more than the ~0.3 ms they hide (2 GPUs: 3.86 vs
-        # 3.60 ms per step); results are identical either way (tools/dp_check.py).
-        self.overlap = os.environ.get("MTB_DP_OVERLAP", "0") == "1"
+        # MTB_DP_OVERLAP: which gradients start their all-reduce DURING backward (results are identical either way,
+        # tools/dp_check.py):  "head" (default) -- the head's projections (~70 % of the bytes, final right at the start of
+        # backward) in one extra NCCL call, everything else in one coalesced call after backward;  "1" -- additionally one
+        # coalesced call per backward stage (more NCCL launches than the bytes they hide at 16 samples per GPU: 2 GPUs
+        # 3.39 vs 3.35 ms per step);  "0" -- one coalesced call after backward.
+        mode = os.environ.get("MTB_DP_OVERLAP", "head")
+        self.overlap = mode in ("1", "head")
+        self.overlap_stages = mode == "1"
         self._pending = []
         self._done = set()
 
@@ -75,6 +79,8 @@ class GradSync:
         rank, n = world()
         if n == 1 or not self.overlap or dist.get_backend(self.group) != "nccl":
             return
+        if not self.overlap_stages and not any(p is engine.model.proj1.l.weight for p in params):
+            return                                 # "head" mode: only the head's hook point starts an early reduce
         # max_gap = 0: a merged gap could cover parameters of EARLIER stages whose weight gradients are still being
         # written by the compute stream -- an in-place async all-reduce over them would race with those writes
         rs = self._ranges_of(engine, params, max_gap=0)

@@ -211,6 +211,14 @@ class ZeroOp:
         self.t = t
 
 
+class HookOp:
+    """marks the point of a backward op list after which the gradients of `params` are final (data-parallel hook)"""
+    __slots__ = ("params",)
+
+    def __init__(self, params):
+        self.params = list(params)
+
+
 # ----------------------------------------------------------------------------- encoder spec
 class EncSpec:
     """One encoder invocation inside a stage group."""
@@ -880,6 +888,10 @@ def _run(ops, stream: int, side=None, stage_hook=None, graphs=None):
         if tp is ZeroOp:
             op.t.zero_()
             continue
+        if tp is HookOp:
+            if stage_hook is not None:
+                stage_hook(op.params)
+            continue
         tgt = sp
         if side is not None and op.side:
             ev_fork.record()
@@ -1478,6 +1490,9 @@ class Engine:
                     [pb.lin_bwd(g_z1, W1, Cd, C_total, Yact=z1, X=out16, dX=g_outb, gW=True, gb=True, b=b1, col_idx=hp, act=1, p=po,
                                 scratch=scratch.ptr, csegs=hs)], "proj1_bwd")
             pb.addn(pb.bwd, [(g_out, [g_z3, g_outb], False)], "head_residual_bwd")
+            # The head's two 3000 x 3000 projections hold ~70 % of a step's gradient bytes and their backward runs FIRST:
+            # a data-parallel hook can start reducing them here, under the whole rest of the backward pass.
+            pb.bwd.append(HookOp([p_ for p_ in (W1, b1, W2, b2, W3, b3) if p_.requires_grad]))
             # scatter into zero-filled d(mems output): only the last time step received gradient
             items = []
             for (i, c0, w) in head_cols:
@@ -1549,7 +1564,7 @@ class Engine:
         # + every encoder's active_mask through its EncPlan), so evicting the mask / encoder-plan caches can never
         # free memory a cached plan still launches with.
         plan._keep = [hmask] + [ep for g in groups for ep in g]
-        count = lambda lst: sum(len(op.arr) if type(op) is Op else op.launches if type(op) is Batch else 1 for op in lst)
+        count = lambda lst: sum(len(op.arr) if type(op) is Op else op.launches if type(op) is Batch else 0 if type(op) is HookOp else 1 for op in lst)
         plan.n_fwd_launches, plan.n_bwd_launches = count(pb.fwd), count(pb.bwd)
         return plan
 
@@ -1637,6 +1652,7 @@ class Engine:
             if pre_ops:
                 _run(pre_ops, stream)
             run = eps if is_mems else [ep for ep in eps if valid.get(ep.spec.name) is not ep]
+            self.stats["memo_encoder_skips"] = self.stats.get("memo_encoder_skips", 0) + len(eps) - len(run)
             if not run:
                 continue
             if not is_mems:
@@ -1652,7 +1668,6 @@ class Engine:
             self._merge(lst, run, "fwd")
             _run(lst, stream, None, None, self)
             self.stats["memo_encoder_runs"] = self.stats.get("memo_encoder_runs", 0) + len(run)
-            self.stats["memo_encoder_skips"] = self.stats.get("memo_encoder_skips", 0) + len(eps) - len(run)
             if not is_mems:
                 for ep in run:
                     valid[ep.spec.name] = ep
