@@ -9,13 +9,15 @@ from mtb200 import _lib as L, ops
 
 ops.set_gemm_mode("bf16")
 ops.preload()
+REPS = int(os.environ.get("AB_REPS", "20"))
 Lq = Lk = int(os.environ.get("AB_L", "500")); B, H, hd = int(os.environ.get("AB_B", "16")), 8, 25
 D = H * hd
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def timeit(fn, n=20):
+def timeit(fn, n=None):
+    n = n or REPS
     for _ in range(3):
         fn()
     ts = []
@@ -28,6 +30,8 @@ def timeit(fn, n=20):
 
 
 for name, fl_f, fl_b in (("fp32 io", 0, 0), ("engine mix", 2, 10), ("all bf16", 3, 15)):
+    if os.environ.get("AB_ONLY") and os.environ["AB_ONLY"] not in name:
+        continue
     dt_in = torch.bfloat16 if fl_f & 1 else torch.float32
     dt_o = torch.bfloat16 if fl_f & 2 else torch.float32
     dt_do = torch.bfloat16 if fl_b & 4 else torch.float32
