@@ -316,10 +316,21 @@ def main():
     engine_stats = {k: int(v) for k, v in eng0.stats.items()} if eng0 is not None else None
     if eng0 is not None:
         engine_stats["stage_graphs_after_hits"] = eng0.stage_graphs
+    # secondary metrics must never cost the headline line: a failure is reported in place of the number
     cfg3 = None
     if args.workload == "cfg2" and not args.no_cfg3:
-        cfg3 = cfg3_throughput(args, model, opt, crit, sync, dev, world, rank)
-    ea = None if args.no_ea else ea_throughput(args, model, dev, world, rank)
+        try:
+            cfg3 = cfg3_throughput(args, model, opt, crit, sync, dev, world, rank)
+        except Exception as exc:
+            cfg3 = {"value": None, "error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+            model.reset_engine()
+            torch.cuda.empty_cache()
+    ea = None
+    if not args.no_ea:
+        try:
+            ea = ea_throughput(args, model, dev, world, rank)
+        except Exception as exc:
+            ea = {"value": None, "error": f"{type(exc).__name__}: {str(exc)[:300]}"}
 
     if rank == 0:
         gb = args.batch * world
@@ -413,9 +424,8 @@ def cfg3_throughput(args, model, opt, crit, sync, dev, world, rank, global_batch
         ms = statistics.median(ts)
         out.update(value=global_batch * steps / (ms / 1e3), unit="samples/s", ms_per_step=ms / steps,
                    ms_per_step_min=min(ts) / steps, ms_per_step_max=max(ts) / steps)
-    except MemoryError as exc:
-        ok = torch.tensor([0.0], device=dev)
-        out.update(value=None, skipped=str(exc))
+    except (MemoryError, torch.cuda.OutOfMemoryError) as exc:
+        out.update(value=None, skipped=str(exc)[:300])
     model.reset_engine()
     opt._eng = None
     torch.cuda.empty_cache()
