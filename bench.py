@@ -238,9 +238,18 @@ def main():
     ops.manual_seed(SEED + 7919 * rank)                # dropout differs per rank; the sampler stream does not
     gen = torch.Generator().manual_seed(1000 + rank)   # each rank owns a different data shard
     n_host = 4
-    host = [synth_batch(args.batch, args.seq, gen, pin=True) for _ in range(n_host)]
-    resident = [([x.to(dev) for x in xs], y.to(dev)) for xs, y in host]
-    h2d = sum(x.numel() * 4 for x in host[0][0]) + host[0][1].numel() * 4
+    host = [synth_batch(args.batch, args.seq, gen) for _ in range(n_host)]
+    # the package's input pipeline (mtb200/data.py): async H2D from pinned memory into persistent device buffers whose
+    # feature axis is padded to 16-byte row pitches (74 -> 76, 35 -> 36), so the front-end GEMM needs no per-step pad kernel
+    from mtb200.data import InputPipeline
+    pipe = InputPipeline([(args.batch, L, Dm) for L, Dm in zip(args.seq, DIMS)], (args.batch, 1), dev, depth=2, host_slots=n_host)
+    resident = [pipe.resident(xs, y) for xs, y in host]
+    for k, (xs_h, y_h) in enumerate(host):             # the "loader" fills the pipeline's pinned slots in place, once
+        views, yv = pipe.host_views(k)
+        for v, x in zip(views, xs_h):
+            v.copy_(x)
+        yv.copy_(y_h)
+    h2d = pipe.bytes_per_batch
     W = max(args.warmup, 3)
     loss_host = torch.zeros(max(args.steps, W) + 1, dtype=torch.float32).pin_memory()
     loss_evt = [torch.cuda.Event() for _ in range(loss_host.numel())]
@@ -249,9 +258,7 @@ def main():
         losses = []
         for it in range(n):
             if e2e:
-                xs_h, y_h = host[it % n_host]
-                xs = [x.to(dev, non_blocking=True) for x in xs_h]      # this step's inputs: pinned host memory -> device
-                y = y_h.to(dev, non_blocking=True)
+                xs, y = pipe.put_slot(it % n_host)                     # this step's inputs: pinned host memory -> device
             else:
                 xs, y = resident[it % n_host]
             loss = train_step(model, opt, crit, xs, y, hyp, grad_sync=sync)

@@ -72,14 +72,22 @@ class Conv1x1FrontEnd(nn.Module):
 
     def forward(self, x):
         B, L, D = x.shape
-        x2, W = x.reshape(B * L, D), self.weight.view(self.d, self.d_in)
         K = self.d_in
-        if K % 4 != 0 and x.is_cuda and _lib.lib.mtb_get_gemm_mode() >= 1:
-            # TMA needs 16-byte row pitches: feature counts such as 74 / 35 (MOSEI audio / video) are zero-padded to a
-            # multiple of 4 so the projection and its weight gradient run on the tcgen05 engine instead of the fp32
-            # fallback (the padded columns multiply zeros; autograd slices the weight gradient back)
-            pad = (-K) % 4
-            x2, W, K = F.pad(x2, (0, pad)), F.pad(W, (0, pad)), K + pad
+        W = self.weight.view(self.d, self.d_in)
+        Kp = (K + 3) // 4 * 4
+        if D == Kp and Kp != K:
+            # pre-padded input from mtb200.data.InputPipeline: [B, L, round4(D_in)] with zero pad columns -- 16-byte row
+            # pitches without a per-step pad kernel over the batch; only the (tiny) weight is padded here
+            x2, W, K = x.reshape(B * L, Kp), F.pad(W, (0, Kp - K)), Kp
+        else:
+            assert D == K, f"front-end expects {K} (or pre-padded {Kp}) input features, got {D}"
+            x2 = x.reshape(B * L, D)
+            if K % 4 != 0 and x.is_cuda and _lib.lib.mtb_get_gemm_mode() >= 1:
+                # TMA needs 16-byte row pitches: feature counts such as 74 / 35 (MOSEI audio / video) are zero-padded to a
+                # multiple of 4 so the projection and its weight gradient run on the tcgen05 engine instead of the fp32
+                # fallback (the padded columns multiply zeros; autograd slices the weight gradient back)
+                pad = Kp - K
+                x2, W, K = F.pad(x2, (0, pad)), F.pad(W, (0, pad)), Kp
         y = ops.linear(x2, W, None, N=self.d, K=K)
         return y.view(B, L, self.d).transpose(1, 2)            # [B, d, L] view, like the conv output
 

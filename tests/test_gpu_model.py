@@ -194,3 +194,37 @@ def test_model_level_subnet_export_equals_dynamic_forward():
     # the extracted model holds copies: it survives changes to the supernet and pickles as a plain module
     n_sub = sum(p.numel() for p in sub.parameters())
     assert 0 < n_sub < sum(p.numel() for p in m.parameters())
+
+
+def test_input_pipeline_padded_inputs_equal_plain_inputs():
+    """mtb200.data.InputPipeline (pinned staging, async H2D into persistent [B, L, round4(D_in)] buffers) feeds the front-end
+    pre-padded rows: same logits and the same front-end weight gradients as plain [B, L, D_in] inputs (D_in = 74 / 35)."""
+    import torch
+    from mtb200 import ops
+    from mtb200.data import InputPipeline
+    from mtb200.dynamic_models2 import DynamicMULTModel
+    torch.manual_seed(4)
+    dims, lens, Bn = (300, 74, 35), (6, 14, 14), 4
+    m = DynamicMULTModel(origin_dimensions=list(dims), dimension=40, num_heads=8, head_dim=5, layers_single_attn=1, layers_hybrid_attn=1,
+                         layers_self_attn=1, attn_dropout=[0.0] * 4, relu_dropout=0.0, res_dropout=0.0, out_dropout=0.0, embed_dropout=0.0,
+                         attn_mask=True, output_dim=1, modality_set=["l", "a", "v"], all_steps=False, front_end="conv1d").cuda().eval()
+    m.set_active(active_self_attn_layer_num=1, active_single_attn_layer_num=[1, 1, 1], active_hybrid_attn_layer_num=1, active_dimension=40,
+                 active_head_num=8, active_head_dim=5, active_modality=[0, 1, 2], active_cross=[["la"], ["av"], ["va"]],
+                 active_cross_output=[["la"], ["a", "av"], ["v", "va"]])
+    xs_h = [torch.randn(Bn, lens[i], dims[i]) for i in range(3)]
+    y_h = torch.randn(Bn, 1)
+    pipe = InputPipeline([(Bn, lens[i], dims[i]) for i in range(3)], (Bn, 1), "cuda")
+    for mode, tol in (("fp32", 1e-6), ("tf32", 1e-6), ("bf16", 1e-6)):          # same kernels, same operand values: identical up to atomics order
+        ops.set_gemm_mode(mode)
+        res = []
+        for padded in (False, True):
+            xs, y = pipe.put(xs_h, y_h) if padded else ([x.cuda() for x in xs_h], y_h.cuda())
+            assert (xs[1].shape[-1] == 76 and xs[2].shape[-1] == 36) if padded else xs[1].shape[-1] == 74
+            m.zero_grad()
+            pred, _ = m(xs)
+            torch.nn.functional.l1_loss(pred, y).backward()
+            res.append((pred.detach().clone(), [p.weight.grad.detach().clone() for p in m.proj]))
+        assert float((res[0][0] - res[1][0]).abs().max()) <= tol * float(res[0][0].abs().max()) + 1e-7, mode
+        for ga, gb in zip(res[0][1], res[1][1]):
+            assert ga.shape == gb.shape and float((ga - gb).abs().max()) <= 1e-5 * float(ga.abs().max()) + 1e-9, mode
+    ops.set_gemm_mode("fp32")
