@@ -323,6 +323,7 @@ def main():
     engine_stats = {k: int(v) for k, v in eng0.stats.items()} if eng0 is not None else None
     if eng0 is not None:
         engine_stats["stage_graphs_after_hits"] = eng0.stage_graphs
+        engine_stats["region_buffer_gb"] = round(eng0.enc_buf.numel() / 2 ** 30, 2) if eng0.enc_buf is not None else None
     # secondary metrics must never cost the headline line: a failure is reported in place of the number
     cfg3 = None
     if args.workload == "cfg2" and not args.no_cfg3:

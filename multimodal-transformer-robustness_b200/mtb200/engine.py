@@ -1106,8 +1106,9 @@ class Engine:
             out.append(("mems", ch, m.trans_mems['mems' + ch]))
         return out
 
-    def _measure(self, kind, name, enc, Lq, Lk, B, E, mask) -> int:
-        """bytes one invocation of `enc` allocates at full depth (forward + backward), from a dry run"""
+    def _measure(self, kind, name, enc, Lq, Lk, B, E, mask, modes=(0, 1, 2)) -> int:
+        """bytes one invocation of `enc` allocates at full depth (forward + backward), from a dry run under each of the
+        given GEMM engines (they allocate different scratch / element sizes: the bf16 data path needs ~60 % of fp32's)"""
         layers = enc._ll
         saved = [l.__dict__.get("active_hidden_out_fc1") for l in layers]
         mode0 = lib.mtb_get_gemm_mode()
@@ -1115,7 +1116,7 @@ class Engine:
             for l in layers:
                 l.__dict__["active_hidden_out_fc1"] = l.fc1.dim_out
             peak = 0
-            for mode in (0, 1, 2):               # the GEMM engines allocate different scratch / element sizes
+            for mode in modes:
                 lib.mtb_set_gemm_mode(mode)
                 ca = CountingArena()
                 grad = not self.inference_only
@@ -1141,14 +1142,18 @@ class Engine:
         d = m.d
         B = px_meta[0][1]
         Ls = tuple(pm[0] for pm in px_meta)
+        # regions are sized for the GEMM engines seen so far (a process normally uses one): switching to a new engine
+        # re-sizes once for the union, so alternating engines (the parity tests) does not thrash
+        modes = frozenset([lib.mtb_get_gemm_mode()])
         if self._layout is not None:
-            B0, Ls0 = self._layout
-            if B <= B0 and all(l <= l0 for l, l0 in zip(Ls, Ls0)):
+            B0, Ls0, modes0 = self._layout
+            if B <= B0 and all(l <= l0 for l, l0 in zip(Ls, Ls0)) and modes <= modes0:
                 return
-            B, Ls = max(B, B0), tuple(max(l, l0) for l, l0 in zip(Ls, Ls0))
+            B, Ls, modes = max(B, B0), tuple(max(l, l0) for l, l0 in zip(Ls, Ls0)), modes | modes0
             self.plans.clear()
             self._enc_cache.clear()
             self._merge_cache.clear()
+            self._memo_token, self._memo_valid = None, {}
         names = list(m.modality_list)
         length = dict(zip(names, Ls))
         off = 0
@@ -1174,7 +1179,7 @@ class Engine:
             r = Region()
             r.out, r.dout = take(Lq * B * E), take(0 if self.inference_only else Lq * B * E)
             r.cat = take(Lq * B * E) if kind == "mems" else None
-            r.work_cap = int(self._measure(kind, name, enc, Lq, Lk, B, E, mask) * 1.02) + (1 << 20)
+            r.work_cap = int(self._measure(kind, name, enc, Lq, Lk, B, E, mask, tuple(sorted(modes))) * 1.02) + (1 << 20)
             r.work = take(r.work_cap // F4)
             regs[id(enc)] = r
         if self.device.type == "cuda":          # (plans can be BUILT on any device -- CPU structure tests -- but only run on CUDA)
@@ -1192,7 +1197,7 @@ class Engine:
                 r.cat += base
         self._regions = regs
         self._stage_ptr = {ch: base + o for ch, o in stage_off.items()}
-        self._layout = (B, Ls)
+        self._layout = (B, Ls, modes)
         # plan-level scratch (head, fan-in temporaries): re-used by every plan
         self.arena = Arena(self.device, (64 << 20) + B * max(m.combined_dim, 1) * F4 * 64)
 
