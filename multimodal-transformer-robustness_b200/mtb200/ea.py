@@ -86,19 +86,33 @@ class EvolutionSearch:
     def _replay_loader_draw(self):
         torch.empty((), dtype=torch.int64).random_()      # the DataLoader-iterator draw of EA.py:157
 
-    def eval_model(self, test: bool = False) -> float:
-        """One inference pass over the (validation | test) batches with the model's current config."""
+    def predict(self, test: bool = False):
+        """One inference pass over the (validation | test) batches with the model's current config; returns the device
+        predictions per batch WITHOUT reading them back (no host synchronisation)."""
         self.model.eval()
         batches = self.test_batches if test else self.valid_batches
-        outs, ys = [], []
+        outs = []
         with torch.no_grad():
             for bi, (xs, y) in enumerate(batches):
                 cache = self._caches.setdefault((test, bi), {}) if self.memoize else None
                 pred, _ = self.model(xs, branch_cache=cache) if cache is not None else self.model(xs)
                 outs.append(pred)
-                ys.append(y)
         self.evaluations += 1
-        return self.metric(torch.cat(outs).float().cpu(), torch.cat(ys).float().cpu())
+        return outs
+
+    def _truths(self, test: bool = False) -> torch.Tensor:
+        key = ("truths", test)
+        t = self.__dict__.get("_truth_cache", {}).get(key)
+        if t is None:
+            batches = self.test_batches if test else self.valid_batches
+            t = torch.cat([y for _, y in batches]).float().cpu()
+            self.__dict__.setdefault("_truth_cache", {})[key] = t
+        return t
+
+    def eval_model(self, test: bool = False) -> float:
+        """EA.py:149-169: predictions over the whole loader, then the metric on the host."""
+        outs = self.predict(test)
+        return self.metric(torch.cat(outs).float().cpu(), self._truths(test))
 
     def get_acc(self, sample) -> float:
         self.model.set_active_modalities(active_modality=self.active_modality, active_cross=copy.deepcopy(sample[0]),
@@ -106,9 +120,25 @@ class EvolutionSearch:
         return self.eval_model()
 
     def score_many(self, samples: List) -> List[float]:
-        """Fitness of a list of candidates, sharded across ranks; scores all-gathered."""
+        """Fitness of a list of candidates, sharded across ranks (candidate r, r + N, ...); only the scores are all-reduced.
+        The forwards of ALL of this rank's candidates are enqueued before the first prediction is read back, so building
+        the next candidate's plan on the host overlaps the GPU work of the previous ones (the reference's get_acc reads
+        every score back before it configures the next candidate, EA.py:75-81)."""
         dev = next(self.model.parameters()).device
-        return mdist.evaluate_population(samples, self.get_acc, device=dev)
+        rank, n = mdist.world()
+        pending = []
+        for i in mdist.shard_indices(len(samples), rank, n):
+            self.model.set_active_modalities(active_modality=self.active_modality, active_cross=copy.deepcopy(samples[i][0]),
+                                             active_cross_output=copy.deepcopy(samples[i][1]))
+            pending.append((i, self.predict()))
+        scores = torch.zeros(len(samples), dtype=torch.float32, device=dev)
+        truths = self._truths()
+        for i, outs in pending:
+            scores[i] = float(self.metric(torch.cat(outs).float().cpu(), truths))
+        if n > 1:
+            import torch.distributed as dist
+            dist.all_reduce(scores, op=dist.ReduceOp.SUM)
+        return scores.tolist()
 
     # ------------------------------------------------------------------ search (EA.py:84-137)
     def search(self):

@@ -533,3 +533,28 @@ def test_memoised_evaluation_engine_equals_per_op_path():
         m.memo_engine = False
         b2, _ = m(xs2, branch_cache={})
         assert_rel(a2, b2, 2e-5, "new batch")
+
+
+def test_ea_score_many_equals_sequential_get_acc():
+    """EvolutionSearch.score_many (all forwards enqueued, scores read back at the end, memoised plan-executor path) returns
+    what the reference's one-candidate-at-a-time get_acc (EA.py:75-81) returns on the unmemoised per-op path."""
+    import types
+    from mtb200 import ops
+    from mtb200.dynamic_models2 import DynamicMULTModel
+    from mtb200.ea import EvolutionSearch
+    ops.set_gemm_mode("fp32")
+    torch.manual_seed(23)
+    m = DynamicMULTModel(origin_dimensions=[12, 7, 5], dimension=40, num_heads=8, head_dim=5, layers_single_attn=2,
+                         layers_hybrid_attn=2, layers_self_attn=1, attn_dropout=[0.1, 0.1, 0.0, 0.0], relu_dropout=0.1,
+                         res_dropout=0.3, out_dropout=0.1, embed_dropout=0.3, attn_mask=True, output_dim=1,
+                         modality_set=["l", "a", "v"], all_steps=False, front_end="conv1d").cuda().eval()
+    m.use_engine = False
+    batches = [([torch.randn(32, 9, d, device="cuda") for d in (12, 7, 5)], torch.randn(32, 1, device="cuda")) for _ in range(2)]
+    hp = types.SimpleNamespace(mutate_prob=0.5, population_size=12, max_time_budget=1, parent_ratio=0.8, mutation_ratio=0.8,
+                               active_modality=[0, 1, 2])
+    cands = [list(m.gen_active_cross([0, 1, 2])) for _ in range(12)]
+    fast = EvolutionSearch(m, hp, batches, memoize=True).score_many(cands)
+    slow_ea = EvolutionSearch(m, hp, batches, memoize=False)
+    slow = [slow_ea.get_acc(c) for c in cands]
+    assert len(fast) == 12 and all(abs(a - b) < 1e-6 for a, b in zip(fast, slow)), (fast, slow)
+    assert m.eval_engine().stats.get("memo_encoder_skips", 0) > 0

@@ -9,6 +9,8 @@ from mtb200 import _lib as L, ops
 
 ops.set_gemm_mode("bf16")
 ops.preload()
+if os.environ.get("AB_ATTN") == "simt":          # CUDA-core flash kernels (fp32 I/O only): AB_ONLY="fp32 io"
+    L.lib.mtb_set_attn_mode(0)
 REPS = int(os.environ.get("AB_REPS", "20"))
 Lq = Lk = int(os.environ.get("AB_L", "500")); B, H, hd = int(os.environ.get("AB_B", "16")), 8, 25
 D = H * hd
