@@ -86,18 +86,21 @@ class EvolutionSearch:
     def _replay_loader_draw(self):
         torch.empty((), dtype=torch.int64).random_()      # the DataLoader-iterator draw of EA.py:157
 
-    def predict(self, test: bool = False):
-        """One inference pass over the (validation | test) batches with the model's current config; returns the device
-        predictions per batch WITHOUT reading them back (no host synchronisation)."""
+    def predict(self, test: bool = False, only_batch: Optional[int] = None):
+        """One inference pass over the (validation | test) batches (or just batch `only_batch`) with the model's current
+        config; returns the device predictions per batch WITHOUT reading them back (no host synchronisation)."""
         self.model.eval()
         batches = self.test_batches if test else self.valid_batches
         outs = []
         with torch.no_grad():
             for bi, (xs, y) in enumerate(batches):
+                if only_batch is not None and bi != only_batch:
+                    continue
                 cache = self._caches.setdefault((test, bi), {}) if self.memoize else None
                 pred, _ = self.model(xs, branch_cache=cache) if cache is not None else self.model(xs)
                 outs.append(pred)
-        self.evaluations += 1
+        if only_batch is None or only_batch == len(batches) - 1:
+            self.evaluations += 1
         return outs
 
     def _truths(self, test: bool = False) -> torch.Tensor:
@@ -126,15 +129,19 @@ class EvolutionSearch:
         every score back before it configures the next candidate, EA.py:75-81)."""
         dev = next(self.model.parameters()).device
         rank, n = mdist.world()
-        pending = []
-        for i in mdist.shard_indices(len(samples), rank, n):
-            self.model.set_active_modalities(active_modality=self.active_modality, active_cross=copy.deepcopy(samples[i][0]),
-                                             active_cross_output=copy.deepcopy(samples[i][1]))
-            pending.append((i, self.predict()))
+        mine = mdist.shard_indices(len(samples), rank, n)
+        pending = {i: [] for i in mine}
+        # batch-major: the memoised branch outputs live in the engine's regions for ONE validation batch at a time, so all
+        # candidates are run on batch 0, then all on batch 1, ...
+        for bi in range(len(self.valid_batches)):
+            for i in mine:
+                self.model.set_active_modalities(active_modality=self.active_modality, active_cross=copy.deepcopy(samples[i][0]),
+                                                 active_cross_output=copy.deepcopy(samples[i][1]))
+                pending[i].extend(self.predict(only_batch=bi))
         scores = torch.zeros(len(samples), dtype=torch.float32, device=dev)
         truths = self._truths()
-        for i, outs in pending:
-            scores[i] = float(self.metric(torch.cat(outs).float().cpu(), truths))
+        for i in mine:
+            scores[i] = float(self.metric(torch.cat(pending[i]).float().cpu(), truths))
         if n > 1:
             import torch.distributed as dist
             dist.all_reduce(scores, op=dist.ReduceOp.SUM)
