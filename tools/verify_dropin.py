@@ -14,6 +14,9 @@ ap.add_argument("--level", type=int, default=1)
 args = ap.parse_args()
 ref_shims.install(use_product_modules=True)
 import torch
+if os.environ.get("MTB_GEMM_MODE"):
+    from mtb200 import ops as _ops
+    _ops.set_gemm_mode(os.environ["MTB_GEMM_MODE"])
 import modules
 assert "multimodal-transformer-robustness_b200" in modules.__file__, modules.__file__
 T = ref_shims.patch_train_module()
