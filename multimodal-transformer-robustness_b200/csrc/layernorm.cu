@@ -4,6 +4,7 @@
 // reductions, two-pass mean/variance).  HBM-bound: forward 4*4 B per element
 // (read branch, read residual, write new residual, write normed) + 8 B per row of stats.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace mtb {
 
@@ -352,7 +353,8 @@ int mtb_resln_bwd(const mtb_resln_bwd_desc* d, int n, void* stream) {
   if (vec && maxE <= 1024) {
     // ~2 CTAs per SM when column sums (d-gamma / d-beta / bias grads) are accumulated -- fewer, longer CTAs
     // mean fewer contended global atomics per feature; ~4 waves otherwise
-    const int target = affine ? sm_count() * 2 : sm_count() * 4;
+    static const int mult_env = getenv("MTB_LN_BWD_CTAS") ? atoi(getenv("MTB_LN_BWD_CTAS")) : 0;
+    const int target = mult_env > 0 ? sm_count() * mult_env : (affine ? sm_count() * 2 : sm_count() * 4);
     int rows = (maxT + target - 1) / target;
     rows = ((rows + LN_WARPS - 1) / LN_WARPS) * LN_WARPS;
     if (rows < LN_WARPS) rows = LN_WARPS;
