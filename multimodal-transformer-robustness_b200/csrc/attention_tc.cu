@@ -16,6 +16,7 @@
 // loads and written to shared memory in the swizzled operand layouts.
 #include "common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace mtb {
 
@@ -482,6 +483,163 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
 }
 
 
+// ---------------------------------------------------------------------------- forward, short sequences (Lq, Lk <= 64)
+// At L <= 64 a (batch, head) problem fills at most half of the 128 TMEM lanes and a single key tile, and a launch is
+// thousands of one-tile CTAs whose cost is their fixed part (TMEM allocation, barrier setup, staging latency, drain):
+// EA fitness at 2048 samples x 8 heads and L = 50 spent 36 % of its kernel time there.  This variant packs TWO
+// (batch, head) problems into one CTA: rows 0-63 are the queries of problem A, rows 64-127 those of problem B; the
+// key / value tiles hold A's keys in rows 0-63 and B's in rows 64-127.  S_A = Q K_A^T and S_B = Q K_B^T are both formed
+// for all 128 rows (the cross blocks are never read), every thread reads the block of its own problem, and
+// PV runs once per (problem, 32-key half) into four accumulators of which a thread reads its own.  Twice the MMAs of
+// the general kernel per useful score -- the tensor pipe idles at this size anyway -- for half the CTAs.
+constexpr int SQ = 64;
+constexpr int ATC_SHORT_TMEM = 256;          // S_A, S_B: 2 x 64 columns; PV: 4 x 32 columns
+constexpr int ATC_SHORT_SMEM = 3 * TQ * 128 + (TK / 32) * TQ * 128 + 1024;
+
+__global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_short_kernel(const __grid_constant__ Group<mtb_attn_desc> g) {
+  pdl_sync();
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_s, bar_o;
+  __shared__ uint32_t tmem_slot;
+  int local;
+  const int pi = find_problem(g, blockIdx.x, local);
+  const mtb_attn_desc& d = g.d[pi];
+  const int BH = d.B * d.H;
+  const int Lq = d.Lq, Lk = d.Lk, hd = d.hd;
+  const int off = abs(Lk - Lq);
+  const int Lk4 = a_round4(Lk);
+  const DropCtx dc = make_drop(d.rng, d.p);
+  const bool bf = (d.bf16 & 1) != 0, bf_o = (d.bf16 & 2) != 0;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane;                  // TMEM lane
+  const int sub = row >> 6;                          // which of the two packed problems this row belongs to
+  const int i = row & (SQ - 1);                      // query index inside that problem
+  const int bh_a = 2 * local, bh_b = 2 * local + 1;  // bh_b may be one past the end (odd B * H): staged as zeros
+  const int bh = sub ? bh_b : bh_a;
+  const bool pvalid = bh < BH;
+  const int b = pvalid ? bh / d.H : 0, h = pvalid ? bh - b * d.H : 0;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Qs = smem;                       // [128][128 B] K-major: rows 0-63 problem A, 64-127 problem B
+  uint8_t* Ks = Qs + TQ * 128;              // [128][128 B] K-major: keys of A, keys of B
+  uint8_t* Vs = Ks + TQ * 128;              // [128][128 B] MN-major (32 B-atom swizzle): values of A, values of B
+  uint8_t* Ps = Vs + TQ * 128;              // 2 regions of [128][128 B], K-major, 32 key columns each
+
+  if (tid == 0) {
+    a_mbar_init(a_smem_u32(&bar_s), 1);
+    a_mbar_init(a_smem_u32(&bar_o), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(&tmem_slot)), "r"(ATC_SHORT_TMEM) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+#pragma unroll
+  for (int s2 = 0; s2 < 2; ++s2) {
+    const int bh2 = 2 * local + s2;
+    const bool ok2 = bh2 < BH;
+    const int b2 = ok2 ? bh2 / d.H : 0, h2 = ok2 ? bh2 - b2 * d.H : 0;
+    const int lq2 = ok2 ? Lq : 0, lk2 = ok2 ? Lk : 0;        // a missing second problem is staged as zeros
+    stage_rows256<false>(Qs + s2 * SQ * 128, d.q, d.ldq, d.B, b2, h2, hd, 0, lq2, SQ, bf);
+    stage_rows256<false>(Ks + s2 * SQ * 128, d.k, d.ldk, d.B, b2, h2, hd, 0, lk2, SQ, bf);
+    stage_rows256<true>(Vs + s2 * SQ * 128, d.v, d.ldv, d.B, b2, h2, hd, 0, lk2, SQ, bf);
+  }
+  stage_wait();
+  if (bf) {
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const int bh2 = 2 * local + s2;
+      const bool ok2 = bh2 < BH;
+      const int b2 = ok2 ? bh2 / d.H : 0, h2 = ok2 ? bh2 - b2 * d.H : 0;
+      fix_rows256<false>(Qs + s2 * SQ * 128, d.q, d.ldq, d.B, b2, h2, hd, 0, SQ);
+      fix_rows256<false>(Ks + s2 * SQ * 128, d.k, d.ldk, d.B, b2, h2, hd, 0, SQ);
+      fix_rows256<true>(Vs + s2 * SQ * 128, d.v, d.ldv, d.B, b2, h2, hd, 0, SQ);
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t t_s = tmem, t_o = tmem + 128;
+  const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+  const uint32_t id_s = idesc_tf32(TQ, SQ, false, false);
+  const uint32_t id_o = idesc_tf32(TQ, HP, false, true);
+  if (tid == 0) {
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+      for (int k = 0; k < HP / 8; ++k)
+        a_mma_tf32(t_s + s2 * SQ, desc_kmajor(a_smem_u32(Qs) + k * 32), desc_kmajor(a_smem_u32(Ks) + s2 * SQ * 128 + k * 32), id_s, k != 0 ? 1u : 0u);
+    a_commit(a_smem_u32(&bar_s));
+  }
+  const int irow = min(i, Lq - 1);
+  const float c2 = d.scale * 1.4426950408889634f;
+  float m_run = -CUDART_INF_F, l_run = 0.f;
+  uint8_t* my_p = Ps + half * (TQ * 128);
+  const int bhc = pvalid ? bh : 0;
+  const uint64_t idx_row = ((uint64_t)((int64_t)bhc * Lq + irow)) * (uint64_t)Lk4 + (uint64_t)(half * 32);
+  const uint32_t kbits = dc.on ? row_keep_bits32(dc, idx_row) : 0u;        // drawn while the S MMAs run
+  const int KW = (Lk + 31) >> 5;
+  a_mbar_wait(a_smem_u32(&bar_s), 0);
+  tc_fence_after();
+  float s[32];
+  a_tmem_ld32(t_s + lane_addr + sub * SQ + half * 32, s);
+  tc_fence_before();
+  float corr;
+  fwd_softmax_half<true>(s, c2, i, half * 32, Lk, off, m_run, l_run, corr, dc.on, dc.inv_keep, kbits, my_p, row);
+  if (d.keep_bits != nullptr && dc.on && pvalid && i < Lq && half < KW) d.keep_bits[((int64_t)bh * Lq + i) * KW + half] = kbits;
+  fence_async_smem();
+  __syncthreads();                            // P written, S read by everyone
+  if (tid == 0) {
+    tc_fence_after();
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)        // accumulator (s2, hf) = P[:, 32 hf : 32 hf + 32] . V_{s2}[32 hf : 32 hf + 32, :]
+          a_mma_tf32(t_o + (s2 * 2 + hf) * 32, desc_kmajor(a_smem_u32(Ps) + hf * (TQ * 128) + k4 * 32),
+                     desc_mnmajor(a_smem_u32(Vs) + s2 * SQ * 128 + (hf * 4 + k4) * 1024), id_o, k4 != 0 ? 1u : 0u);
+    a_commit(a_smem_u32(&bar_o));
+  }
+  a_mbar_wait(a_smem_u32(&bar_o), 0);
+  tc_fence_after();
+  float o[HP];
+  a_tmem_ld32(t_o + lane_addr + (sub * 2 + half) * 32, o);
+  tc_fence_before();
+  // ---- merge the two half-row states (see the general kernel) ----------------------------------------------------------
+  __syncthreads();                            // the PV MMAs have read P: its region is free for the exchange
+  float* ex = reinterpret_cast<float*>(Ps);   // [128][36]
+  if (half == 1) {
+    float* e = ex + row * 36;
+    e[0] = m_run; e[1] = l_run;
+#pragma unroll
+    for (int c = 0; c < HP; c += 4) *reinterpret_cast<float4*>(e + 4 + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+  }
+  __syncthreads();
+  if (half == 0 && pvalid && i < Lq) {
+    const float* e = ex + row * 36;
+    const float m_b = e[0], l_b = e[1];
+    const float m = fmaxf(m_run, m_b);        // finite: key 0 is open for every row and belongs to half 0
+    const float wa = fast_exp2(m_run - m), wb = fast_exp2(m_b - m);
+    const float l = l_run * wa + l_b * wb;
+    const float inv = 1.f / l;
+    const int64_t oo = ((int64_t)i * d.B + b) * d.ldo + h * hd;
+#pragma unroll
+    for (int c = 0; c < HP; ++c) o[c] = (o[c] * wa + e[4 + c] * wb) * inv;
+    store_row<HP>(d.o, oo, o, hd, bf_o);
+    if (d.lse) d.lse[(int64_t)bh * Lq + i] = m * 0.6931471805599453f + logf(l);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ATC_SHORT_TMEM) : "memory");
+  }
+}
+
+
 // ============================================================================ backward: dQ (+ delta)
 // One CTA (256 threads) per (batch, head, 128-row query tile); two threads per query row (key-column halves of
 // every 64-key tile).  Per key tile: S = Q K^T and dP = dO V^T on the tensor core,
@@ -924,11 +1082,19 @@ int attn_fwd_simt(const mtb_attn_desc* d, int n, cudaStream_t st);
 
 int attn_fwd_tc(const mtb_attn_desc* d, int n, cudaStream_t st) {
   mtb_attn_desc rest[MTB_MAX_GROUP];
-  Group<mtb_attn_desc> g;
-  int ntc = 0, nrest = 0, tot = 0;
+  Group<mtb_attn_desc> g, gs;
+  int ntc = 0, nshort = 0, nrest = 0, tot = 0, tots = 0;
+  static const bool no_short = getenv("MTB_ATTN_NO_SHORT") != nullptr;
   for (int i = 0; i < n; ++i) {
     MTB_CHECK(d[i].hd <= HP || !d[i].bf16, "attn_fwd: bf16 operands need head_dim <= %d (problem %d)", HP, i);
     if (d[i].hd > HP) { rest[nrest++] = d[i]; continue; }
+    if (!no_short && d[i].Lq <= SQ && d[i].Lk <= SQ && d[i].B * d[i].H >= 2) {   // two (batch, head) problems per CTA
+      gs.d[nshort] = d[i];
+      gs.start[nshort] = tots;
+      tots += (d[i].B * d[i].H + 1) / 2;
+      ++nshort;
+      continue;
+    }
     g.d[ntc] = d[i];
     g.start[ntc] = tot;
     tot += d[i].B * d[i].H * ((d[i].Lq + TQ - 1) / TQ);
@@ -936,13 +1102,21 @@ int attn_fwd_tc(const mtb_attn_desc* d, int n, cudaStream_t st) {
   }
   g.n = ntc;
   g.start[ntc] = tot;
+  gs.n = nshort;
+  gs.start[nshort] = tots;
+  static bool attr = false;
+  if (!attr) {
+    MTB_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_FWD_SMEM));
+    MTB_CUDA(cudaFuncSetAttribute(attn_fwd_tc_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SHORT_SMEM));
+    attr = true;
+  }
   if (tot > 0) {
-    static bool attr = false;
-    if (!attr) {
-      MTB_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_FWD_SMEM));
-      attr = true;
-    }
     MTB_CUDA(launch_k(attn_fwd_tc_kernel, dim3(tot), dim3(AF_THREADS), ATC_FWD_SMEM, st, g));
+    mtb::note_launch();
+    MTB_CUDA(cudaGetLastError());
+  }
+  if (tots > 0) {
+    MTB_CUDA(launch_k(attn_fwd_tc_short_kernel, dim3(tots), dim3(AF_THREADS), ATC_SHORT_SMEM, st, gs));
     mtb::note_launch();
     MTB_CUDA(cudaGetLastError());
   }
@@ -991,6 +1165,7 @@ namespace mtb {
 int preload_attention_tc() {
   int bad = 0;
   { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_fwd_tc_kernel) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_fwd_tc_short_kernel) != cudaSuccess) ++bad; }
   { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_bwd_dq_tc_kernel) != cudaSuccess) ++bad; }
   { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, attn_bwd_dkv_tc_kernel) != cudaSuccess) ++bad; }
   return bad;

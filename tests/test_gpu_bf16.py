@@ -197,7 +197,9 @@ def test_addn_mixed_types(bf16_mode):
     assert rel(out32, ref) < 1e-6 and rel(out16, ref) < 6e-3
 
 
-@pytest.mark.parametrize("Lq,Lk,B,H,hd", [(50, 50, 4, 8, 25), (500, 50, 2, 8, 25), (50, 500, 2, 8, 25), (300, 300, 2, 8, 25), (70, 130, 2, 4, 32)])
+@pytest.mark.parametrize("Lq,Lk,B,H,hd", [(50, 50, 4, 8, 25), (500, 50, 2, 8, 25), (50, 500, 2, 8, 25), (300, 300, 2, 8, 25), (70, 130, 2, 4, 32),
+                                          # short sequences: the packed two-problems-per-CTA forward kernel (odd B*H, < 32 keys, 1 query, 64 x 64)
+                                          (50, 50, 3, 5, 25), (20, 20, 2, 8, 25), (1, 50, 4, 8, 25), (64, 64, 2, 3, 32), (7, 33, 1, 8, 25)])
 @pytest.mark.parametrize("mixed", [False, True], ids=["all_bf16", "engine_mix"])
 def test_attention_bf16_io(bf16_mode, Lq, Lk, B, H, hd, mixed):
     """all_bf16: q / k / v / o / d_o / dq / dk / dv in bf16.  engine_mix: what the plan executor uses -- q / k / v / d_o fp32
