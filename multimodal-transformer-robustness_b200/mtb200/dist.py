@@ -37,9 +37,11 @@ class GradSync:
         # backward) in one extra NCCL call, everything else in one coalesced call after backward;  "1" -- additionally one
         # coalesced call per backward stage (more NCCL launches than the bytes they hide at 16 samples per GPU: 2 GPUs
         # 3.39 vs 3.35 ms per step);  "0" -- one coalesced call after backward.
+        # "mems" -- the head plus the first backward stage (the wide `mems` stacks, the next largest block of bytes).
         mode = os.environ.get("MTB_DP_OVERLAP", "head")
-        self.overlap = mode in ("1", "head")
-        self.overlap_stages = mode == "1"
+        self.overlap = mode in ("1", "head", "mems")
+        self.early_calls = {"1": 1 << 30, "head": 1, "mems": 2}.get(mode, 0)
+        self._calls = 0
         self._pending = []
         self._done = set()
 
@@ -79,8 +81,9 @@ class GradSync:
         rank, n = world()
         if n == 1 or not self.overlap or dist.get_backend(self.group) != "nccl":
             return
-        if not self.overlap_stages and not any(p is engine.model.proj1.l.weight for p in params):
-            return                                 # "head" mode: only the head's hook point starts an early reduce
+        if self._calls >= self.early_calls:        # "head" / "mems": only the first hook point(s) start an early reduce
+            return
+        self._calls += 1
         # max_gap = 0: a merged gap could cover parameters of EARLIER stages whose weight gradients are still being
         # written by the compute stream -- an in-place async all-reduce over them would race with those writes
         rs = self._ranges_of(engine, params, max_gap=0)
@@ -118,6 +121,7 @@ class GradSync:
                 w.wait()
             self._pending.clear()
             self._done.clear()
+            self._calls = 0
 
     def _reduce_now(self, ts):
         rank, n = world()
