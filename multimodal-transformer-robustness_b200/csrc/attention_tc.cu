@@ -310,7 +310,7 @@ __device__ __forceinline__ void fwd_softmax_half(float (&s)[32], const float c2,
 }
 
 __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid_constant__ Group<mtb_attn_desc> g) {
-  pdl_sync();
+  pdl_begin();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
   const int Lq = d.Lq, Lk = d.Lk, hd = d.hd;
   const int off = abs(Lk - Lq);
   const int Lk4 = a_round4(Lk);
-  const DropCtx dc = make_drop(d.rng, d.p);
+  DropCtx dc;                                       // filled after pdl_ready(): the device counter lives in global memory
   const bool bf = (d.bf16 & 1) != 0;                // q / k / v are bfloat16 in HBM
   const bool bf_o = (d.bf16 & 2) != 0;              // o is bfloat16
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -347,6 +347,8 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(&tmem_slot)), "r"(ATC_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_ready();                 // barrier init and TMEM allocation ran under the tail of the preceding kernel
+  dc = make_drop(d.rng, d.p);
   const int i_last = min(Lq, i0 + TQ) - 1;
   const int j_end = min(Lk, i_last + off + 1);
   const int T = (j_end + TK - 1) / TK;
@@ -497,7 +499,7 @@ constexpr int ATC_SHORT_TMEM = 256;          // S_A, S_B: 2 x 64 columns; PV: 4 
 constexpr int ATC_SHORT_SMEM = 3 * TQ * 128 + (TK / 32) * TQ * 128 + 1024;
 
 __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_short_kernel(const __grid_constant__ Group<mtb_attn_desc> g) {
-  pdl_sync();
+  pdl_begin();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
@@ -508,7 +510,7 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_short_kernel(const 
   const int Lq = d.Lq, Lk = d.Lk, hd = d.hd;
   const int off = abs(Lk - Lq);
   const int Lk4 = a_round4(Lk);
-  const DropCtx dc = make_drop(d.rng, d.p);
+  DropCtx dc;                                       // filled after pdl_ready(): the device counter lives in global memory
   const bool bf = (d.bf16 & 1) != 0, bf_o = (d.bf16 & 2) != 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, half = warp >> 2;
@@ -535,6 +537,8 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_short_kernel(const 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(&tmem_slot)), "r"(ATC_SHORT_TMEM) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_ready();                 // barrier init and TMEM allocation ran under the tail of the preceding kernel
+  dc = make_drop(d.rng, d.p);
 #pragma unroll
   for (int s2 = 0; s2 < 2; ++s2) {
     const int bh2 = 2 * local + s2;
@@ -673,7 +677,7 @@ __device__ __forceinline__ void dq_math(const float (&s)[32], const float (&dp)[
 }
 
 __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __grid_constant__ Group<mtb_attn_bwd_desc> g) {
-  pdl_sync();
+  pdl_begin();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_a, bar_b;
   __shared__ uint32_t tmem_slot;
@@ -688,7 +692,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
   const int Lq = d.Lq, Lk = d.Lk, hd = d.hd;
   const int off = abs(Lk - Lq);
   const int Lk4 = a_round4(Lk);
-  const DropCtx dc = make_drop(d.rng, d.p);
+  DropCtx dc;                                       // filled after pdl_ready(): the device counter lives in global memory
   const bool bf = (d.bf16 & 1) != 0;                // q / k / v are bfloat16 in HBM
   const bool bf_o = (d.bf16 & 2) != 0, bf_do = (d.bf16 & 4) != 0, bf_dx = (d.bf16 & 8) != 0;   // o, d_o, dq likewise
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -712,6 +716,8 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(&tmem_slot)), "r"(ATC_DQ_TMEM) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_ready();                 // barrier init and TMEM allocation ran under the tail of the preceding kernel
+  dc = make_drop(d.rng, d.p);
   stage_rows256<false>(Qs, d.q, d.ldq, d.B, b, h, hd, i0, Lq, TQ, bf);
   stage_rows256<false>(dOs, d.d_o, d.lddo, d.B, b, h, hd, i0, Lq, TQ, bf_do);
   stage_rows256<false>(Ks, d.k, d.ldk, d.B, b, h, hd, 0, Lk, TK, bf);
@@ -904,7 +910,7 @@ __device__ __forceinline__ void dkv_math(const float (&st)[16], const float (&dp
 }
 
 __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __grid_constant__ Group<mtb_attn_bwd_desc> g) {
-  pdl_sync();
+  pdl_begin();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_a, bar_b;
   __shared__ uint32_t tmem_slot;
@@ -920,7 +926,7 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
   const int Lq = d.Lq, Lk = d.Lk, hd = d.hd;
   const int off = abs(Lk - Lq);
   const int Lk4 = a_round4(Lk);
-  const DropCtx dc = make_drop(d.rng, d.p);
+  DropCtx dc;                                       // filled after pdl_ready(): the device counter lives in global memory
   const bool bf = (d.bf16 & 1) != 0;                // q / k / v are bfloat16 in HBM
   const bool bf_do = (d.bf16 & 4) != 0, bf_dx = (d.bf16 & 8) != 0;   // d_o, dk / dv likewise
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -944,6 +950,8 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(&tmem_slot)), "r"(ATC_DKV_TMEM) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_ready();                 // barrier init and TMEM allocation ran under the tail of the preceding kernel
+  dc = make_drop(d.rng, d.p);
   const int i_begin = (max(0, j0 - off) / TI) * TI;
   const int T = (Lq - i_begin + TI - 1) / TI;
   const float c2 = d.scale * 1.4426950408889634f;

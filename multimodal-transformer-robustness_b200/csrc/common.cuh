@@ -152,15 +152,29 @@ __device__ __forceinline__ void st1_any(void* base, int64_t off, float v, bool b
 }
 
 // ---------------------------------------------------------------- programmatic dependent launch
-// Every hot kernel starts with pdl_sync(): it waits until the preceding kernel of the stream has completed and
-// flushed its writes, then lets the NEXT kernel's CTAs be scheduled while this one is still running (they park in
-// their own pdl_sync()).  Launched through launch_k() with the programmatic-stream-serialization attribute this
-// removes the ~2-3 us launch bubble between the small dependent kernels of a step; without the attribute (or after
-// a kernel that never triggers) both instructions are no-ops / the edge is a normal full serialisation.
-__device__ __forceinline__ void pdl_sync() {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
+// Every hot kernel waits (griddepcontrol.wait) until the preceding kernel of the stream has completed and flushed its
+// writes, and lets the NEXT kernel's CTAs be scheduled (griddepcontrol.launch_dependents) while this one is still
+// running -- they park in their own wait.  Launched through launch_k() with the programmatic-stream-serialization
+// attribute this removes the ~2-3 us launch bubble between the small dependent kernels of a step; without the
+// attribute (or after a kernel that never triggers) both instructions are no-ops / the edge is a normal full
+// serialisation.
+//   pdl_sync()                : wait, then trigger -- the first statement of the HBM-bound kernels
+//   pdl_begin() / pdl_ready() : the tcgen05 kernels trigger first, run their prologue (mbarrier init, TMEM allocation,
+//                               tensor-map prefetch: nothing that touches global memory) under the tail of the
+//                               preceding kernel, and wait right before their first global access.  EVERY thread of
+//                               every CTA executes pdl_ready() before it exits, so "kernel N complete" still implies
+//                               "kernel N-1 complete" for the kernel after it.
+//   -DMTB_PDL_EARLY_WAIT      : variant build with the wait back at the top (A/B measurement).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+#ifdef MTB_PDL_EARLY_WAIT
+__device__ __forceinline__ void pdl_begin() { pdl_sync(); }
+__device__ __forceinline__ void pdl_ready() {}
+#else
+__device__ __forceinline__ void pdl_begin() { pdl_trigger(); }
+__device__ __forceinline__ void pdl_ready() { pdl_wait(); }
+#endif
 extern int g_pdl;
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

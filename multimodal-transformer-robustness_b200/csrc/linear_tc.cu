@@ -162,7 +162,7 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 
 template <int CAP>
 __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ TcGroupT<CAP> g) {
-  pdl_sync();
+  pdl_begin();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_slot;
   if (threadIdx.x == 0) TRACE(1);
+  pdl_ready();                 // everything above ran under the tail of the preceding kernel; global memory from here on
 
   if (nkb > 0) {
     if (warp == 0) {
