@@ -123,8 +123,10 @@ __global__ void __launch_bounds__(LN_THREADS) resln_fwd_generic(const __grid_con
 // ------------------------------------------------------------------ backward (vector path)
 // Each CTA owns `rows_per_cta` consecutive rows; per-lane partial dgamma/dbeta live in
 // registers, are combined through shared memory once per CTA and leave as one atomicAdd
-// per feature per CTA.
-template <int MAXV, bool AFFINE_GRAD>
+// per feature per CTA.  gamma is read once per CTA, not per row (the gathered read is two dependent loads).
+// R = rows a warp keeps in flight: measured on the bench step R = 1 3.04 ms, R = 2 3.05-3.07 ms (122 registers),
+// R = 4 3.21 ms (177 registers: one CTA per SM, a second wave) -- only R = 1 is instantiated.
+template <int MAXV, bool AFFINE_GRAD, int R>
 __global__ void __launch_bounds__(LN_THREADS) resln_bwd_kernel(const __grid_constant__ Group<mtb_resln_bwd_desc> g,
                                                                int rows_per_cta) {
   pdl_sync();
@@ -145,54 +147,89 @@ __global__ void __launch_bounds__(LN_THREADS) resln_bwd_kernel(const __grid_cons
     for (int c = threadIdx.x; c < 3 * E; c += LN_THREADS) sred[c] = 0.f;
     __syncthreads();
   }
+  float4 gm[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + 32 * i;
+    gm[i] = (v < nv && has_ln) ? gather4(d.gamma, d.idx, v << 2) : make_float4(0, 0, 0, 0);
+  }
   const int row0 = local * rows_per_cta;
   const int row1 = min(d.T, row0 + rows_per_cta);
-  for (int t = row0 + warp; t < row1; t += LN_WARPS) {
-    float4 wdy[MAXV], xh[MAXV];
-    float s1 = 0.f, s2 = 0.f;
-    float mean = 0.f, rstd = 0.f;
-    if (has_ln) { mean = d.mean[t]; rstd = d.rstd[t]; }
+  for (int tb = row0 + warp; tb < row1; tb += LN_WARPS * R) {
+    float4 wdy[R][MAXV], xh[R][MAXV], ex[R > 1 ? R : 1][R > 1 ? MAXV : 1];   // R == 1 (wide rows): no register room to prefetch ex
+    float mean[R], rstd[R], c1[R], c2[R];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int v = lane + 32 * i;
-      wdy[i] = make_float4(0, 0, 0, 0); xh[i] = make_float4(0, 0, 0, 0);
-      if (v < nv && has_ln) {
-        const int c = v << 2;
-        const float4 dy = ld4_any(d.dy, (int64_t)t * d.ld_dy + c, d.dy_bf16 != 0);
-        const float4 x = ld4(d.x_new + (int64_t)t * d.ld_x + c);
-        const float4 gm = gather4(d.gamma, d.idx, c);
-        xh[i] = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
-        wdy[i] = make_float4(dy.x * gm.x, dy.y * gm.y, dy.z * gm.z, dy.w * gm.w);
-        s1 += (wdy[i].x * xh[i].x + wdy[i].y * xh[i].y) + (wdy[i].z * xh[i].z + wdy[i].w * xh[i].w);
-        s2 += (wdy[i].x + wdy[i].y) + (wdy[i].z + wdy[i].w);
-        if (AFFINE_GRAD && agrad) {
-          dg[i].x += dy.x * xh[i].x; dg[i].y += dy.y * xh[i].y; dg[i].z += dy.z * xh[i].z; dg[i].w += dy.w * xh[i].w;
-          db[i].x += dy.x; db[i].y += dy.y; db[i].z += dy.z; db[i].w += dy.w;
+    for (int r = 0; r < R; ++r) {
+      const int t = tb + r * LN_WARPS;
+      mean[r] = 0.f; rstd[r] = 0.f;
+      if (t < row1 && has_ln) { mean[r] = d.mean[t]; rstd[r] = d.rstd[t]; }
+    }
+    // all loads of the R rows first (dy and x_new land in wdy / xh, the pass-through gradient in ex)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int t = tb + r * LN_WARPS;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + 32 * i, c = v << 2;
+        const bool ok = v < nv && t < row1;
+        wdy[r][i] = make_float4(0, 0, 0, 0); xh[r][i] = make_float4(0, 0, 0, 0);
+        if (ok && has_ln) {
+          wdy[r][i] = ld4_any(d.dy, (int64_t)t * d.ld_dy + c, d.dy_bf16 != 0);
+          xh[r][i] = ld4(d.x_new + (int64_t)t * d.ld_x + c);
         }
+        if constexpr (R > 1) ex[r][i] = (ok && d.d_xnew) ? ld4(d.d_xnew + (int64_t)t * d.ld_dx + c) : make_float4(0, 0, 0, 0);
       }
     }
-    const float c1 = warp_sum(s1) / (float)E, c2 = warp_sum(s2) / (float)E;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nv) {
-        const int c = v << 2;
-        float4 gx;
-        gx.x = rstd * (wdy[i].x - c2 - xh[i].x * c1); gx.y = rstd * (wdy[i].y - c2 - xh[i].y * c1);
-        gx.z = rstd * (wdy[i].z - c2 - xh[i].z * c1); gx.w = rstd * (wdy[i].w - c2 - xh[i].w * c1);
-        if (d.d_xnew) {
-          const float4 e = ld4(d.d_xnew + (int64_t)t * d.ld_dx + c);
-          gx.x += e.x; gx.y += e.y; gx.z += e.z; gx.w += e.w;
-        }
-        if (d.d_res) st4(d.d_res + (int64_t)t * d.ld_dres + c, gx);
-        if (d.d_a) {
-          const float4 k = keep4(dc, ((uint64_t)t * E + c) >> 2);
-          float4 da = make_float4(gx.x * k.x, gx.y * k.y, gx.z * k.z, gx.w * k.w);
-          if (d.da_bf16) {     // the bias gradient sums exactly what the GEMMs will read
-            da = make_float4(bf16_round(da.x), bf16_round(da.y), bf16_round(da.z), bf16_round(da.w));
+    for (int r = 0; r < R; ++r) {
+      float s1 = 0.f, s2 = 0.f;
+      if (has_ln) {
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+          const int v = lane + 32 * i;
+          if (v < nv && tb + r * LN_WARPS < row1) {
+            const float4 dy = wdy[r][i], x = xh[r][i];
+            xh[r][i] = make_float4((x.x - mean[r]) * rstd[r], (x.y - mean[r]) * rstd[r], (x.z - mean[r]) * rstd[r], (x.w - mean[r]) * rstd[r]);
+            wdy[r][i] = make_float4(dy.x * gm[i].x, dy.y * gm[i].y, dy.z * gm[i].z, dy.w * gm[i].w);
+            s1 += (wdy[r][i].x * xh[r][i].x + wdy[r][i].y * xh[r][i].y) + (wdy[r][i].z * xh[r][i].z + wdy[r][i].w * xh[r][i].w);
+            s2 += (wdy[r][i].x + wdy[r][i].y) + (wdy[r][i].z + wdy[r][i].w);
+            if (AFFINE_GRAD && agrad) {
+              dg[i].x += dy.x * xh[r][i].x; dg[i].y += dy.y * xh[r][i].y; dg[i].z += dy.z * xh[r][i].z; dg[i].w += dy.w * xh[r][i].w;
+              db[i].x += dy.x; db[i].y += dy.y; db[i].z += dy.z; db[i].w += dy.w;
+            }
           }
-          st4_any(d.d_a, (int64_t)t * d.ld_da + c, da, d.da_bf16 != 0);
-          if (AFFINE_GRAD && bgrad) { dba[i].x += da.x; dba[i].y += da.y; dba[i].z += da.z; dba[i].w += da.w; }
+        }
+      }
+      c1[r] = s1; c2[r] = s2;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) { c1[r] = warp_sum(c1[r]) / (float)E; c2[r] = warp_sum(c2[r]) / (float)E; }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int t = tb + r * LN_WARPS;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nv && t < row1) {
+          const int c = v << 2;
+          float4 gx;
+          gx.x = rstd[r] * (wdy[r][i].x - c2[r] - xh[r][i].x * c1[r]); gx.y = rstd[r] * (wdy[r][i].y - c2[r] - xh[r][i].y * c1[r]);
+          gx.z = rstd[r] * (wdy[r][i].z - c2[r] - xh[r][i].z * c1[r]); gx.w = rstd[r] * (wdy[r][i].w - c2[r] - xh[r][i].w * c1[r]);
+          if (d.d_xnew) {
+            float4 e;
+            if constexpr (R > 1) e = ex[r][i]; else e = ld4(d.d_xnew + (int64_t)t * d.ld_dx + c);
+            gx.x += e.x; gx.y += e.y; gx.z += e.z; gx.w += e.w;
+          }
+          if (d.d_res) st4(d.d_res + (int64_t)t * d.ld_dres + c, gx);
+          if (d.d_a) {
+            const float4 k = keep4(dc, ((uint64_t)t * E + c) >> 2);
+            float4 da = make_float4(gx.x * k.x, gx.y * k.y, gx.z * k.z, gx.w * k.w);
+            if (d.da_bf16) {     // the bias gradient sums exactly what the GEMMs will read
+              da = make_float4(bf16_round(da.x), bf16_round(da.y), bf16_round(da.z), bf16_round(da.w));
+            }
+            st4_any(d.d_a, (int64_t)t * d.ld_da + c, da, d.da_bf16 != 0);
+            if (AFFINE_GRAD && bgrad) { dba[i].x += da.x; dba[i].y += da.y; dba[i].z += da.z; dba[i].w += da.w; }
+          }
         }
       }
     }
@@ -285,10 +322,10 @@ int preload_layernorm() {
   { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_fwd_kernel<2>) != cudaSuccess) ++bad; }
   { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_fwd_kernel<8>) != cudaSuccess) ++bad; }
   { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_fwd_generic) != cudaSuccess) ++bad; }
-  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_bwd_kernel<2, true>) != cudaSuccess) ++bad; }
-  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_bwd_kernel<2, false>) != cudaSuccess) ++bad; }
-  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_bwd_kernel<8, true>) != cudaSuccess) ++bad; }
-  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_bwd_kernel<8, false>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_bwd_kernel<2, true, 1>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_bwd_kernel<2, false, 1>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_bwd_kernel<8, true, 1>) != cudaSuccess) ++bad; }
+  { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_bwd_kernel<8, false, 1>) != cudaSuccess) ++bad; }
   { cudaFuncAttributes a; if (cudaFuncGetAttributes(&a, resln_bwd_generic) != cudaSuccess) ++bad; }
   return bad;
 }
@@ -363,11 +400,11 @@ int mtb_resln_bwd(const mtb_resln_bwd_desc* d, int n, void* stream) {
     if (tot == 0) return 0;
     const size_t smem = affine ? 3 * (size_t)maxE * sizeof(float) : 0;
     if (maxE <= 256) {
-      if (affine) MTB_CUDA(launch_k(resln_bwd_kernel<2, true>, dim3(tot), dim3(LN_THREADS), smem, st, g, rows));
-      else MTB_CUDA(launch_k(resln_bwd_kernel<2, false>, dim3(tot), dim3(LN_THREADS), 0, st, g, rows));
+      if (affine) MTB_CUDA(launch_k(resln_bwd_kernel<2, true, 1>, dim3(tot), dim3(LN_THREADS), smem, st, g, rows));
+      else MTB_CUDA(launch_k(resln_bwd_kernel<2, false, 1>, dim3(tot), dim3(LN_THREADS), 0, st, g, rows));
     } else {
-      if (affine) MTB_CUDA(launch_k(resln_bwd_kernel<8, true>, dim3(tot), dim3(LN_THREADS), smem, st, g, rows));
-      else MTB_CUDA(launch_k(resln_bwd_kernel<8, false>, dim3(tot), dim3(LN_THREADS), 0, st, g, rows));
+      if (affine) MTB_CUDA(launch_k(resln_bwd_kernel<8, true, 1>, dim3(tot), dim3(LN_THREADS), smem, st, g, rows));
+      else MTB_CUDA(launch_k(resln_bwd_kernel<8, false, 1>, dim3(tot), dim3(LN_THREADS), 0, st, g, rows));
     }
   } else {
     for (int i = 0; i < n; ++i) { g.d[i] = d[i]; g.start[i] = tot; tot += (d[i].T + LN_WARPS - 1) / LN_WARPS; }
