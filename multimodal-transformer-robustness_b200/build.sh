@@ -10,6 +10,7 @@ BUILD="$HERE/build${VARIANT:+/$VARIANT}"
 LIBNAME="libmultb200${VARIANT:+_$VARIANT}.so"
 EXTRA=()
 [[ "$VARIANT" == "trace" ]] && EXTRA+=(-DMTB_TC_TRACE)
+[[ "$VARIANT" == "tracefine" ]] && EXTRA+=(-DMTB_TC_TRACE -DMTB_TC_TRACE_FINE)
 [[ "$VARIANT" == "pdlearly" ]] && EXTRA+=(-DMTB_PDL_EARLY_WAIT)       # A/B: griddepcontrol.wait back at the top of the tcgen05 kernels
 mkdir -p "$OUT" "$BUILD"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC

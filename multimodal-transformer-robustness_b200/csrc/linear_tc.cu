@@ -159,6 +159,11 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #else
 #define TRACE(i) do { } while (0)
 #endif
+#ifdef MTB_TC_TRACE_FINE       // per-slab / per-chunk stamps: every stamp costs ~0.3 us, so the coarse build is the one to read totals from
+#define TRACE_FINE(i) TRACE(i)
+#else
+#define TRACE_FINE(i) do { } while (0)
+#endif
 
 template <int CAP>
 __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ TcGroupT<CAP> g) {
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
           const int s = kb % TC_STAGES;
           const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-          if (kb < 16) TRACE(8 + kb);
+          if (kb < 16) TRACE_FINE(8 + kb);
           const uint32_t fb = smem_u32(&full_bar[s]);
           mbar_expect_tx(fb, (uint32_t)TC_A_BYTES + b_bytes);
           const uint32_t sa = smem_base + (uint32_t)s * TC_STAGE_BYTES;
@@ -267,7 +272,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
           const int s = kb % TC_STAGES;
           const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
           mbar_wait(smem_u32(&full_bar[s]), ph);
-          if (kb < 16) TRACE(24 + kb);
+          if (kb < 16) TRACE_FINE(24 + kb);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_base + (uint32_t)s * TC_STAGE_BYTES;
           const uint32_t sb = sa + TC_A_BYTES;
@@ -405,18 +410,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         for (int c0 = 0; c0 < BJ; c0 += 32) {
           if (jl0 + c0 >= j_len || !rows_any) break;      // warp-uniform
           uint32_t v[32];
-          if (threadIdx.x == 64 && nbuf < 3) TRACE(40 + nbuf * 6);
+          if (threadIdx.x == 64 && nbuf < 3) TRACE_FINE(40 + nbuf * 6);
           load32(c0, v);
-          if (threadIdx.x == 64 && nbuf < 3) TRACE(42 + nbuf * 6);
+          if (threadIdx.x == 64 && nbuf < 3) TRACE_FINE(42 + nbuf * 6);
           const uint32_t st = stage0 + (uint32_t)(nbuf % nstage) * 4096u;
           wait_stage();
 #pragma unroll
           for (int c = 0; c < 8; ++c)                     // 16-byte chunk c of row r lives at chunk (c ^ (r & 7)): SWIZZLE_128B
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + my_row + (((uint32_t)c ^ sw) << 4)),
                          "r"(v[4 * c]), "r"(v[4 * c + 1]), "r"(v[4 * c + 2]), "r"(v[4 * c + 3]) : "memory");
-          if (threadIdx.x == 64 && nbuf < 3) TRACE(43 + nbuf * 6);
+          if (threadIdx.x == 64 && nbuf < 3) TRACE_FINE(43 + nbuf * 6);
           tma_out(st, jl0 + c0);
-          if (threadIdx.x == 64 && nbuf < 3) TRACE(45 + nbuf * 6);
+          if (threadIdx.x == 64 && nbuf < 3) TRACE_FINE(45 + nbuf * 6);
           ++nbuf;
         }
       }

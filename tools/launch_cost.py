@@ -31,7 +31,7 @@ for c in range(12):
         for op in which:
             flat.extend(op.ops if type(op) is E.Batch else [op])
         for op in flat:
-            if type(op) is E.ZeroOp:
+            if type(op) in (E.ZeroOp, E.HookOp):
                 continue
             for arr, n in op.arr:
                 if os.environ.get("SYNC_EACH"):
