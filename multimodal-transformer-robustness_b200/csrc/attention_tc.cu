@@ -309,6 +309,26 @@ __device__ __forceinline__ void fwd_softmax_half(float (&s)[32], const float c2,
   m_run = m_new;
 }
 
+// Output rows leave through shared memory: a thread owns one accumulator ROW (TMEM lane), so direct stores are hd scalar
+// stores per thread that each touch 32 scattered sectors (~25 x 32 L1 wavefronts per warp).  Instead every thread parks its
+// values in an (idle) [128][32] fp32 tile -- element (r, c) at r * 32 + (c ^ (r & 31)): conflict-free for thread-per-row
+// writes and for warp-per-row reads -- and after a barrier each warp writes whole rows, one lane per column (one or two
+// sectors per row).  Values and rounding are those of store_row().
+template <int N>
+__device__ __forceinline__ void park_row(float* tile, int r, int c0, const float (&vals)[N]) {
+#pragma unroll
+  for (int c = 0; c < N; ++c) tile[r * 32 + ((c0 + c) ^ (r & 31))] = vals[c];
+}
+template <int NT>
+__device__ __forceinline__ void rows_out(const float* tile, void* base, int64_t ld, int B, int b, int h, int hd, int l0, int L, int rows,
+                                         bool bf16) {
+  const int lane = threadIdx.x & 31;
+  for (int r = threadIdx.x >> 5; r < rows; r += NT / 32) {
+    const int l = l0 + r;
+    if (l < L && lane < hd) st1_any(base, ((int64_t)l * B + b) * ld + h * hd + lane, tile[r * 32 + (lane ^ (r & 31))], bf16);
+  }
+}
+
 __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid_constant__ Group<mtb_attn_desc> g) {
   pdl_begin();
   extern __shared__ uint8_t smem_raw[];
@@ -471,10 +491,9 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
     const float wa = fast_exp2(m_run - m), wb = fast_exp2(m_b - m);
     const float l = l_run * wa + l_b * wb;
     const float inv = 1.f / l;
-    const int64_t oo = ((int64_t)i * d.B + b) * d.ldo + h * hd;
 #pragma unroll
     for (int c = 0; c < HP; ++c) o[c] = (o[c] * wa + e[4 + c] * wb) * inv;
-    store_row<HP>(d.o, oo, o, hd, bf_o);
+    park_row<HP>(reinterpret_cast<float*>(Qs), row, 0, o);          // every MMA that read Q has retired
     if (d.lse) d.lse[(int64_t)bh * Lq + i] = m * 0.6931471805599453f + logf(l);
   }
   tc_fence_before();
@@ -482,6 +501,7 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_kernel(const __grid
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ATC_TMEM_COLS) : "memory");
   }
+  rows_out<AF_THREADS>(reinterpret_cast<const float*>(Qs), d.o, d.ldo, d.B, b, h, hd, i0, Lq, TQ, bf_o);
 }
 
 
@@ -520,7 +540,6 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_short_kernel(const 
   const int bh_a = 2 * local, bh_b = 2 * local + 1;  // bh_b may be one past the end (odd B * H): staged as zeros
   const int bh = sub ? bh_b : bh_a;
   const bool pvalid = bh < BH;
-  const int b = pvalid ? bh / d.H : 0, h = pvalid ? bh - b * d.H : 0;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Qs = smem;                       // [128][128 B] K-major: rows 0-63 problem A, 64-127 problem B
@@ -630,16 +649,21 @@ __global__ void __launch_bounds__(AF_THREADS, 2) attn_fwd_tc_short_kernel(const 
     const float wa = fast_exp2(m_run - m), wb = fast_exp2(m_b - m);
     const float l = l_run * wa + l_b * wb;
     const float inv = 1.f / l;
-    const int64_t oo = ((int64_t)i * d.B + b) * d.ldo + h * hd;
 #pragma unroll
     for (int c = 0; c < HP; ++c) o[c] = (o[c] * wa + e[4 + c] * wb) * inv;
-    store_row<HP>(d.o, oo, o, hd, bf_o);
+    park_row<HP>(reinterpret_cast<float*>(Qs), row, 0, o);
     if (d.lse) d.lse[(int64_t)bh * Lq + i] = m * 0.6931471805599453f + logf(l);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ATC_SHORT_TMEM) : "memory");
+  }
+#pragma unroll
+  for (int s2 = 0; s2 < 2; ++s2) {                  // rows 0-63: problem A, rows 64-127: problem B
+    const int bh2 = 2 * local + s2;
+    if (bh2 < BH)
+      rows_out<AF_THREADS>(reinterpret_cast<const float*>(Qs) + s2 * SQ * 32, d.o, d.ldo, d.B, bh2 / d.H, bh2 % d.H, hd, 0, Lq, SQ, bf_o);
   }
 }
 
@@ -681,6 +705,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_a, bar_b;
   __shared__ uint32_t tmem_slot;
+  __shared__ float delta_s[TQ];
   int local;
   const int pi = find_problem(g, blockIdx.x, local);
   const mtb_attn_bwd_desc& d = g.d[pi];
@@ -725,13 +750,36 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
   stage_rows256<true>(Kmn, d.k, d.ldk, d.B, b, h, hd, 0, Lk, TK, bf);
   const int i = i0 + row;
   const int irow = min(i, Lq - 1);
-  float delta = 0.f, lse2 = 0.f;
-  if (i < Lq) {
-    const int64_t oo = ((int64_t)i * d.B + b) * d.ldo + h * hd, og = ((int64_t)i * d.B + b) * d.lddo + h * hd;
-    for (int c = 0; c < hd; ++c) delta = fmaf(ld1_any(d.o, oo + c, bf_o), ld1_any(d.d_o, og + c, bf_do), delta);
-    lse2 = d.lse[(int64_t)bh * Lq + i] * 1.4426950408889634f;
-    if (half == 0) d.delta[(int64_t)bh * Lq + i] = delta;
+  // delta[r] = sum_c o[r, c] * d_o[r, c]: one warp per row, one lane per column (coalesced 100-byte reads and a shuffle
+  // reduction) -- a thread-per-row loop costs 2 * hd scalar loads of 32 scattered sectors each, ~7 us per CTA of L1
+  // wavefronts.  Four rows in flight per warp; the rows' owners pick their value up from shared memory after the barrier.
+  {
+    constexpr int NW = AQ_THREADS / 32;
+#pragma unroll 1
+    for (int r0 = warp; r0 < TQ; r0 += 4 * NW) {
+      float pr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int ii = i0 + r0 + u * NW;
+        pr[u] = 0.f;
+        if (r0 + u * NW < TQ && ii < Lq && lane < hd) {
+          const int64_t oo = ((int64_t)ii * d.B + b) * d.ldo + h * hd + lane, og = ((int64_t)ii * d.B + b) * d.lddo + h * hd + lane;
+          pr[u] = ld1_any(d.o, oo, bf_o) * ld1_any(d.d_o, og, bf_do);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float sum = warp_sum(pr[u]);
+        const int r = r0 + u * NW;
+        if (lane == 0 && r < TQ) {
+          delta_s[r] = sum;
+          if (i0 + r < Lq) d.delta[(int64_t)bh * Lq + i0 + r] = sum;
+        }
+      }
+    }
   }
+  float lse2 = 0.f;
+  if (i < Lq) lse2 = d.lse[(int64_t)bh * Lq + i] * 1.4426950408889634f;
   stage_wait();
   if (bf_do) fix_rows256<false>(dOs, d.d_o, d.lddo, d.B, b, h, hd, i0, TQ);
   if (bf) {
@@ -744,6 +792,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  const float delta = delta_s[row];
   const uint32_t tmem = tmem_slot;
   const uint32_t t_s = tmem, t_dp = tmem + 64, t_dq = tmem + 128;
   const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
@@ -829,16 +878,14 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) attn_bwd_dq_tc_kernel(const __g
     tc_fence_after();
     float dq[16];
     a_tmem_ld16(t_dq + lane_addr + half * 16, dq);
-    if (i < Lq) {
-      const int64_t qo = ((int64_t)i * d.B + b) * d.lddq + h * hd + half * 16;
-      store_row<16>(d.dq, qo, dq, hd - half * 16, bf_dx);
-    }
+    if (i < Lq) park_row<16>(reinterpret_cast<float*>(Qs), row, half * 16, dq);      // all MMAs have retired: Q's tile is idle
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ATC_DQ_TMEM) : "memory");
   }
+  rows_out<AQ_THREADS>(reinterpret_cast<const float*>(Qs), d.dq, d.lddq, d.B, b, h, hd, i0, Lq, TQ, bf_dx);
 }
 
 // ============================================================================ backward: dK, dV
@@ -918,7 +965,6 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
   int local;
   const int pi = find_problem(g, blockIdx.x, local);
   const mtb_attn_bwd_desc& d = g.d[pi];
-  const int ktiles = (d.Lk + TQ - 1) / TQ;
   const int BH = d.B * d.H;
   const int bh = local % BH, kt = local / BH;       // key tile 0 sees every query tile: heaviest first
   const int b = bh / d.H, h = bh - b * d.H;
@@ -1072,11 +1118,9 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
 #pragma unroll
       for (int c = 0; c < 16; ++c) { dv[c] = 0.f; dk[c] = 0.f; }
     }
-    if (j < Lk) {
-      const int64_t ko = ((int64_t)j * d.B + b) * d.lddk + h * hd + half * 16;
-      const int64_t vo = ((int64_t)j * d.B + b) * d.lddv + h * hd + half * 16;
-      store_row<16>(d.dk, ko, dk, hd - half * 16, bf_dx);
-      store_row<16>(d.dv, vo, dv, hd - half * 16, bf_dx);
+    if (j < Lk) {                                     // all MMAs have retired: the K and V tiles are idle
+      park_row<16>(reinterpret_cast<float*>(Ks), row, half * 16, dk);
+      park_row<16>(reinterpret_cast<float*>(Vs), row, half * 16, dv);
     }
   }
   tc_fence_before();
@@ -1084,6 +1128,8 @@ __global__ void __launch_bounds__(AB_THREADS, 2) attn_bwd_dkv_tc_kernel(const __
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ATC_DKV_TMEM) : "memory");
   }
+  rows_out<AB_THREADS>(reinterpret_cast<const float*>(Ks), d.dk, d.lddk, d.B, b, h, hd, j0, Lk, TQ, bf_dx);
+  rows_out<AB_THREADS>(reinterpret_cast<const float*>(Vs), d.dv, d.lddv, d.B, b, h, hd, j0, Lk, TQ, bf_dx);
 }
 
 int attn_fwd_simt(const mtb_attn_desc* d, int n, cudaStream_t st);
