@@ -322,10 +322,19 @@ __device__ __forceinline__ void park_row(float* tile, int r, int c0, const float
 template <int NT>
 __device__ __forceinline__ void rows_out(const float* tile, void* base, int64_t ld, int B, int b, int h, int hd, int l0, int L, int rows,
                                          bool bf16) {
-  const int lane = threadIdx.x & 31;
-  for (int r = threadIdx.x >> 5; r < rows; r += NT / 32) {
-    const int l = l0 + r;
-    if (l < L && lane < hd) st1_any(base, ((int64_t)l * B + b) * ld + h * hd + lane, tile[r * 32 + (lane ^ (r & 31))], bf16);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane >= hd) return;
+  const int n = min(rows, L - l0);
+  int64_t off = ((int64_t)(l0 + w) * B + b) * ld + h * hd + lane;
+  const int64_t step = (int64_t)(NT / 32) * B * ld;
+  if (bf16) {
+    uint16_t* p = reinterpret_cast<uint16_t*>(base);
+#pragma unroll 4
+    for (int r = w; r < n; r += NT / 32, off += step) p[off] = (uint16_t)(pack_bf16x2(tile[r * 32 + (lane ^ (r & 31))], 0.f) & 0xffffu);
+  } else {
+    float* p = reinterpret_cast<float*>(base);
+#pragma unroll 4
+    for (int r = w; r < n; r += NT / 32, off += step) p[off] = tile[r * 32 + (lane ^ (r & 31))];
   }
 }
 
