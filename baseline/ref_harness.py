@@ -210,7 +210,9 @@ def main():
     et, pool = ("random_sample", ALL_POOL_3) if args.workload == "cfg2" else ("test_single", [[0, 1, 2]])
     times = train_steps(args.device, args.steps, args.warmup, args.batch, tuple(args.seq), args.clean, et, pool)
     sec = sum(times) / len(times)
+    srt = sorted(times)
     print(json.dumps({"impl": "reference-unmodified", "device": args.device, "clean": args.clean, "ms_per_step": sec * 1e3,
+                      "ms_per_step_median": srt[len(srt) // 2] * 1e3, "ms_per_step_max": srt[-1] * 1e3,
                       "samples_per_s": args.batch / sec, "batch": args.batch, "seq": list(args.seq), "steps": args.steps,
                       "cores": os.cpu_count(), "threads": torch.get_num_threads(), "torch": torch.__version__,
                       "gpu": torch.cuda.get_device_name(0) if args.device.startswith("cuda") else None}))
