@@ -13,6 +13,7 @@ unaligned sequences -- both identical to what the product arm runs.  This file a
 
     python baseline/ref_harness.py --device cpu  --steps 2 --warmup 1          # JSON line: CPU baseline
     python baseline/ref_harness.py --device cuda --steps 10 --warmup 3 [--clean]  # the reference's eager CUDA path
+    python baseline/ref_harness.py --device cuda --ea 32 --valid 2048            # the reference's own EvolutionSearch.get_acc
     python baseline/ref_harness.py --stage                                      # copy /root/reference -> baseline/_ref
 """
 import argparse
@@ -188,6 +189,50 @@ def train_steps(device, steps, warmup, batch, seq, clean=False, experiment_type=
     return times
 
 
+def ea_fitness(device, n_cand, valid, seq=(50, 50, 50), warmup=2):
+    """seconds per candidate (list) of the reference's OWN fitness evaluation: `EvolutionSearch.get_acc` (EA.py:75-81) =
+    `set_active_modalities` + `eval_model` (EA.py:149-169: eval mode, one forward per validation batch, results moved to
+    the host, `binary_acc`).  The class is taken from the reference's EA.py (the part above its CLI block, which parses
+    arguments at import).  Candidates: the model's own `gen_active_cross([0, 1, 2])` under seed SEED -- the population
+    bench.py's `ea` leg scores; validation set: ONE synthetic aligned batch of `valid` samples, same generator seed."""
+    import types
+    import torch
+    dev = torch.device(device)
+    if dev.type == "cpu":
+        torch.set_num_threads(os.cpu_count() or 1)
+    m = build_reference_model(dev)
+    root = reference_root()
+    src = open(os.path.join(root, "EA.py")).read().split("import sys\nimport torch\nimport argparse")[0]
+    ns = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        exec(compile(src, os.path.join(root, "EA.py"), "exec"), ns)
+    gen = torch.Generator().manual_seed(1)
+    xs, y = synth_batch(valid, seq, gen)
+    loader = [((torch.arange(valid), xs[0], xs[1], xs[2]), y.unsqueeze(-1))]
+    hp = types.SimpleNamespace(mutate_prob=0.5, population_size=n_cand, max_time_budget=1, parent_ratio=0.8, mutation_ratio=0.8,
+                               subnet_prob=0.5, active_modality=[0, 1, 2], criterion="L1Loss", modality_list=list(NAMES),
+                               use_cuda=dev.type == "cuda")
+    ea = ns["EvolutionSearch"](m, hp, loader, loader)
+    m.set_active(active_self_attn_layer_num=LAYERS["self"], active_single_attn_layer_num=[LAYERS["single"]] * 3,
+                 active_hybrid_attn_layer_num=LAYERS["cross"], active_dimension=D, active_head_num=H, active_head_dim=HD,
+                 active_modality=[0, 1, 2], active_cross=[[], [], []], active_cross_output=[["l"], ["a"], ["v"]])
+    torch.manual_seed(SEED)
+    cands = [list(m.gen_active_cross([0, 1, 2])) for _ in range(n_cand + warmup)]
+    times, accs = [], []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for i, c in enumerate(cands):
+            if dev.type == "cuda":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            acc = ea.get_acc(c)
+            if dev.type == "cuda":
+                torch.cuda.synchronize()
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+                accs.append(float(acc))
+    return times, accs
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--stage", action="store_true")
@@ -198,6 +243,8 @@ def main():
     ap.add_argument("--clean", action="store_true", help="drop the reference's per-step empty_cache() and second .item()")
     ap.add_argument("--seq", type=int, nargs=3, default=list(SEQ))
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
+    ap.add_argument("--ea", type=int, default=0, help="time the reference's own EvolutionSearch.get_acc over this many candidates")
+    ap.add_argument("--valid", type=int, default=2048)
     args = ap.parse_args()
     if args.stage:
         dst = os.path.join(HERE, "_ref")
@@ -207,6 +254,14 @@ def main():
         print("staged", dst)
         return
     import torch
+    if args.ea:
+        times, accs = ea_fitness(args.device, args.ea, args.valid)
+        sec = sum(times) / len(times)
+        print(json.dumps({"impl": "reference-unmodified", "what": "EvolutionSearch.get_acc (EA.py:75-81,149-169)", "device": args.device,
+                          "subnets_per_s": 1.0 / sec, "ms_per_subnet": sec * 1e3, "ms_per_subnet_median": sorted(times)[len(times) // 2] * 1e3,
+                          "candidates": args.ea, "valid_samples": args.valid, "seq": [50, 50, 50], "acc_checksum": sum(accs),
+                          "gpu": torch.cuda.get_device_name(0) if args.device.startswith("cuda") else None}))
+        return
     et, pool = ("random_sample", ALL_POOL_3) if args.workload == "cfg2" else ("test_single", [[0, 1, 2]])
     times = train_steps(args.device, args.steps, args.warmup, args.batch, tuple(args.seq), args.clean, et, pool)
     sec = sum(times) / len(times)

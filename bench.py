@@ -386,6 +386,13 @@ def main():
                 "speedup_vs_stock": (med(stock) / (ms / K)) if med(stock) else None,
                 "speedup_vs_clean": (med(clean) / (ms / K)) if med(clean) else None,
                 "errors": [r["error"] for r in (stock, clean) if "error" in r] or None}
+            if isinstance(line.get("ea"), dict) and line["ea"].get("value"):
+                # the reference's own sequential fitness evaluation (EvolutionSearch.get_acc, EA.py:75-81,149-169) on this GPU:
+                # 24 candidates of the same population recipe over the same-size validation batch
+                r = _harness(["--device", "cuda", "--ea", "24", "--valid", str(args.ea_valid)], timeout=600)
+                line["ea"]["reference_eager_cuda"] = (
+                    {"subnets_per_s": r["subnets_per_s"], "ms_per_subnet_median": r["ms_per_subnet_median"], "candidates": r["candidates"],
+                     "what": r["what"], "speedup": line["ea"]["value"] / r["subnets_per_s"]} if "subnets_per_s" in r else {"error": r.get("error")})
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
